@@ -1,0 +1,139 @@
+// Shared helpers of libcyclevae_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cyclevae_b200.h"
+
+namespace cvb {
+
+void set_error(const char* fmt, ...);
+
+#define CVB_CHECK(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            cvb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define CVB_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            cvb::set_error(__VA_ARGS__);  \
+            return 2;                     \
+        }                                 \
+    } while (0)
+
+#define CVB_LAUNCH_CHECK() CVB_CHECK(cudaGetLastError())
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
+static inline size_t round_up_sz(size_t a, size_t b) { return ceil_div_sz(a, b) * b; }
+
+struct DeviceInfo {
+    int n_sm;
+    int max_smem_optin;
+    int cc_major, cc_minor;
+};
+int get_device_info(DeviceInfo* out);
+
+// conv geometry of TwoSidedDilConv1d (gru_vae.py:40-51)
+static inline int ipow(int b, int e) {
+    int r = 1;
+    for (int i = 0; i < e; ++i) r *= b;
+    return r;
+}
+static inline int conv_pad(const cvb_net* n) { return (ipow(n->kernel_size, n->n_conv) - 1) / 2; }
+static inline int conv_dim(const cvb_net* n) { return n->in_dim * ipow(n->kernel_size, n->n_conv); }
+static inline int tot_in_dim(const cvb_net* n) { return conv_dim(n) + n->out_dim; }
+
+// internal GEMM (row-major semantics), gemm.cu
+int gemm_rm(cudaStream_t s, bool transA, bool transB, int M, int N, int K, float alpha,
+            const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc);
+
+// elementwise / small kernels, elementwise.cu
+int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out, bool accumulate);
+int fill_rows(cudaStream_t s, float* dst, size_t rows, int cols, int ld, const float* bias);
+int zero_floats(cudaStream_t s, float* p, size_t n);
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier for a co-resident (cooperatively launched) grid.  `ctr` is zero at kernel
+// start; `target` is this thread's running count of expected arrivals (starts at 0).
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target, unsigned n_cta) {
+    __syncthreads();
+    target += n_cta;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_release_gpu_add(ctr, 1u);
+        while (ld_acquire_gpu(ctr) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based RNG
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint64_t ctr, uint32_t stream = 0) const {
+        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0x9E3779B9u;
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
+#endif
+
+}  // namespace cvb

@@ -1,0 +1,86 @@
+// Off-critical-path dense products of the GRU-VAE path (gx = xc*W_x^T, conv taps as shifted-view
+// GEMMs, deferred weight gradients of BPTT).  Row-major semantics over cuBLAS fp32 (no TF32: the
+// parity bar is 1e-4 after 800 recurrent steps).
+#include <cublas_v2.h>
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cvb {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static std::mutex g_mu;
+static cublasHandle_t g_handles[64] = {nullptr};
+
+static int get_handle(cublasHandle_t* out) {
+    int dev = 0;
+    CVB_CHECK(cudaGetDevice(&dev));
+    CVB_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_handles[dev]) {
+        cublasStatus_t st = cublasCreate(&g_handles[dev]);
+        CVB_REQUIRE(st == CUBLAS_STATUS_SUCCESS, "cublasCreate failed (%d)", (int)st);
+        cublasSetMathMode(g_handles[dev], CUBLAS_PEDANTIC_MATH);
+        cublasSetPointerMode(g_handles[dev], CUBLAS_POINTER_MODE_HOST);
+    }
+    *out = g_handles[dev];
+    return 0;
+}
+
+int gemm_rm(cudaStream_t s, bool transA, bool transB, int M, int N, int K, float alpha,
+            const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc) {
+    if (M <= 0 || N <= 0) return 0;
+    cublasHandle_t h;
+    if (int rc = get_handle(&h)) return rc;
+    cublasSetStream(h, s);
+    if (K <= 0) {  // C = beta*C
+        alpha = 0.f;
+        K = 0;
+    }
+    // row-major C = op(A) op(B)  <=>  column-major C^T = op(B)^T op(A)^T
+    cublasStatus_t st = cublasSgemm(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N,
+                                    N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc);
+    CVB_REQUIRE(st == CUBLAS_STATUS_SUCCESS, "cublasSgemm failed (%d) M=%d N=%d K=%d lda=%d ldb=%d ldc=%d",
+                (int)st, M, N, K, lda, ldb, ldc);
+    return 0;
+}
+
+int get_device_info(DeviceInfo* out) {
+    int dev = 0;
+    CVB_CHECK(cudaGetDevice(&dev));
+    CVB_CHECK(cudaDeviceGetAttribute(&out->n_sm, cudaDevAttrMultiProcessorCount, dev));
+    CVB_CHECK(cudaDeviceGetAttribute(&out->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CVB_CHECK(cudaDeviceGetAttribute(&out->cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    CVB_CHECK(cudaDeviceGetAttribute(&out->cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return 0;
+}
+
+}  // namespace cvb
+
+extern "C" {
+const char* cvb_last_error(void) { return cvb::last_error(); }
+int cvb_abi_version(void) { return CVB_ABI_VERSION; }
+int cvb_device_info(int* n_sm, int* max_smem_optin, int* cc_major, int* cc_minor) {
+    cvb::DeviceInfo d;
+    if (cvb::get_device_info(&d)) return -1;
+    if (n_sm) *n_sm = d.n_sm;
+    if (max_smem_optin) *max_smem_optin = d.max_smem_optin;
+    if (cc_major) *cc_major = d.cc_major;
+    if (cc_minor) *cc_minor = d.cc_minor;
+    return 0;
+}
+int cvb_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* Bm, int ldb, float beta, float* C, int ldc, void* stream) {
+    return cvb::gemm_rm((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, alpha, A, lda, Bm, ldb, beta, C, ldc);
+}
+}

@@ -1,0 +1,46 @@
+// Argument blocks of the persistent recurrence kernels (gru_ar.cu) shared with api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace cvb {
+
+struct GruFwdArgs {
+    const float* gx;    // [T,B,3H]  = W_x xc' + b_ih
+    const float* Whh;   // [3H,H]
+    const float* bhh;   // [3H]
+    const float* Wy;    // [3H,out] with row stride ldwy (= W_ih[:, C:])
+    int ldwy;
+    const float* Wo;    // [out,H]
+    const float* bo;    // [out]
+    const float* mask;  // [T,B,H] or null
+    float* hs;          // [T+1,B,H]
+    float* ys;          // [T+1,B,out]
+    float *sv_r, *sv_z, *sv_n, *sv_ghn, *sv_o;  // [T,B,H] or null
+    float* part;        // [G,B,out]
+    unsigned* bar;
+    int B, T, H, out;
+};
+
+struct GruBwdArgs {
+    const float* Whh;
+    const float* Wy;
+    int ldwy;
+    const float* Wo;
+    const float* mask;
+    const float* hs;
+    const float *sv_r, *sv_z, *sv_n, *sv_ghn;
+    float* dy_tot;  // [T+1,B,out]: in: grad of ys slots from the head; out: total grads (slot 0 = dy_in)
+    float* dgi;     // [T,B,3H]
+    float* dghn;    // [T,B,H]
+    float* gxch;    // [2,B,3H] exchange of dgh_t
+    float* dhc;     // [B,H] in: d_h_last (or 0); out: dh_in
+    float* part;    // [G,B,out]
+    unsigned* bar;
+    int B, T, H, out;
+};
+
+int gru_exact_grid(int H);
+int gru_ar_fwd_exact(GruFwdArgs& a, cudaStream_t s);
+int gru_ar_bwd_exact(GruBwdArgs& a, cudaStream_t s);
+
+}  // namespace cvb

@@ -1,0 +1,226 @@
+"""Host-side composition of one CycleVAE optimisation step on top of the drop-in GRU_RNN:
+the caller-side logic of src/bin/train_gru_cyclevae_gauss_batch.py restated so the benchmark and
+the parity tests drive the hot path exactly as the reference's trainer does (the trainer itself
+cannot run here: h5py / dtw_c / pysptk are absent).
+
+    chunk_schedule   train_generator's frame-chunk bookkeeping      train_*.py:70-134   (integers)
+    cyc_forward      the 5 x n_cyc GRU_RNN passes of one chunk      train_*.py:1298-1311 / 1326-1338
+    cyc_loss         loss assembly incl. the KL-cv cat quirk        train_*.py:1363-1410
+    FlatAdam         Adam over conv+gru+out_1 of both nets          train_*.py:373-377, 1418-1420
+    allreduce_grads  the one data-parallel collective (SUM)         new
+    convert          stage-6 conversion composition                 decode_*.py:303-305,318
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import gru_vae as gv
+from ._lib import check, lib, ptr
+
+
+# ------------------------------------------------------------------------------------------------
+def chunk_schedule(flens: Sequence[int], batch_size: int, spcidx: Optional[Sequence[Sequence[int]]] = None):
+    """Frame-chunk schedule of train_generator (train_*.py:70-134).  Returns one tuple per yielded
+    chunk: (src_idx_s, src_idx_e, spcidx_s_idx[], spcidx_e_idx[], flen_acc[], select_utt_idx[]).
+    Integer-only; the reference's behaviours are kept: the first chunk always spans batch_size
+    frames (:72), flen_acc starts at batch_size (:77) and shrinks only when a later chunk crosses the
+    utterance end (:107-108), an utterance stays selected until its last speech frame is consumed (:106).
+    """
+    flens = [int(f) for f in flens]
+    n_utt = len(flens)
+    if spcidx is None:
+        spcidx = [range(f) for f in flens]
+    n_spc = [len(s) for s in spcidx]
+    max_flen = max(flens)
+    start_i = [-1] * n_utt
+    end_i = [-1] * n_utt
+    seeking_start = [True] * n_utt
+
+    def advance(j: int, lo: int, hi: int) -> None:
+        """Move utterance j's speech-frame cursors to cover the chunk [lo, hi] (:79-98, :109-128)."""
+        idx = spcidx[j]
+        i = end_i[j] + 1
+        while i < n_spc[j]:
+            v = int(idx[i])
+            if seeking_start[j]:
+                if v >= lo:
+                    if v > hi:            # no speech frame inside this chunk
+                        start_i[j] = -1
+                        return
+                    start_i[j] = i
+                    seeking_start[j] = False
+                    if i == n_spc[j] - 1:  # the very last speech frame opens and closes the span
+                        end_i[j] = i
+                        seeking_start[j] = True
+                        return
+            elif v >= hi or i == n_spc[j] - 1:
+                end_i[j] = i - 1 if v > hi else i
+                seeking_start[j] = True
+                return
+            i += 1
+
+    lo, hi = 0, batch_size - 1
+    flen_acc = [batch_size] * n_utt
+    for j in range(n_utt):
+        advance(j, lo, hi)
+    rows = [(lo, hi, list(start_i), list(end_i), list(flen_acc), list(range(n_utt)))]
+    while hi < max_flen - 1:
+        lo = hi + 1
+        hi = min(lo + batch_size - 1, max_flen - 1)
+        selected = []
+        for j in range(n_utt):
+            if end_i[j] >= n_spc[j] - 1:
+                continue
+            if hi >= flens[j]:
+                flen_acc[j] = flens[j] - lo
+            advance(j, lo, hi)
+            selected.append(j)
+        rows.append((lo, hi, list(start_i), list(end_i), list(flen_acc), selected))
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+PASS_NAMES = ("pp_src", "src_src", "src_trg", "pp_src_trg", "src_trg_src")
+OUT_KEYS = ("lat_src", "trj_src_src", "trj_src_trg", "lat_src_trg", "trj_src_trg_src")
+
+
+def cyc_forward(enc: gv.GRU_RNN, dec: gv.GRU_RNN, *, x, cv, src_code, trg_code, n_cyc: int, lat_dim: int, stdim: int,
+                y0_enc, y0_dec, do: bool = True, eps=None, masks=None, state: Optional[dict] = None):
+    """The cyc graph of one chunk: per cycle ENC -> DEC(src) / DEC(trg) -> ENC(cv | converted) -> DEC(src)
+    (first chunk: train_*.py:1326-1338 with the initial y_in and h_in=None; later chunks: :1298-1311
+    with the carried, detached (y, h) in `state`).  eps[i][0..2] / masks[i][p] = (mask_conv, mask_gru)
+    inject the noise / dropout masks for parity tests; None draws them on the device."""
+    out: Dict[str, List[torch.Tensor]] = {k: [] for k in OUT_KEYS}
+    new_state = {}
+
+    def run(net, inp, name, i, p, **kw):
+        if state is None:
+            y0, h0 = (y0_enc if net is enc else y0_dec), None
+        else:
+            y0, h0 = state[(name, i)]
+            y0, h0 = y0.detach(), h0.detach()
+        if masks is not None and masks[i][p][0] is not None:
+            net.inject_dropout_masks(*masks[i][p])
+        trj, y_last, h_last = net(inp, y0, h_in=h0, do=do, **kw)
+        new_state[(name, i)] = (y_last, h_last)
+        return trj
+
+    def e(i, k):
+        return None if eps is None else eps[i][k]
+
+    for i in range(n_cyc):
+        enc_in = x if i == 0 else torch.cat((x[:, :, :stdim], out["trj_src_trg_src"][i - 1]), 2)
+        lat_src = run(enc, enc_in, "pp_src", i, 0, clamp_vae=True, lat_dim=lat_dim)
+        trj_src_src = run(dec, gv.reparam_concat(lat_src, src_code, e(i, 0), lat_dim), "src_src", i, 1)
+        trj_src_trg = run(dec, gv.reparam_concat(lat_src, trg_code, e(i, 1), lat_dim), "src_trg", i, 2)
+        lat_src_trg = run(enc, torch.cat((cv, trj_src_trg), 2), "pp_src_trg", i, 3, clamp_vae=True, lat_dim=lat_dim)
+        trj_src_trg_src = run(dec, gv.reparam_concat(lat_src_trg, src_code, e(i, 2), lat_dim), "src_trg_src", i, 4)
+        for k, v in zip(OUT_KEYS, (lat_src, trj_src_src, trj_src_trg, lat_src_trg, trj_src_trg_src)):
+            out[k].append(v)
+    return out, new_state
+
+
+def cyc_loss(out: dict, x, *, n_cyc: int, lat_dim: int, stdim: int, flen_acc: Sequence[int],
+             select_utt_idx: Sequence[int], kl_cv_quirk: bool = True, flens_dev: Optional[torch.Tensor] = None):
+    """train_*.py:1363-1410 with one kernel per loss term instead of a Python loop over utterances:
+    sum over selected utterances of mean-L1-MCD(src_src), mean-L1-MCD(src_trg_src), KL(lat_src) and the
+    'cv' KL term, which reproduces line 1393 (cat onto batch_loss_lat_src) when kl_cv_quirk is set."""
+    B = x.shape[0]
+    if flens_dev is None:
+        fl = [0] * B
+        for j in select_utt_idx:
+            fl[j] = int(flen_acc[j])
+        flens_dev = torch.tensor(fl, dtype=torch.int32, device=x.device)
+    last = int(select_utt_idx[-1])
+    total = None
+    parts = []
+    for i in range(n_cyc):
+        _, m_ss, _ = gv.mcd_l1_per_utt(out["trj_src_src"][i], x, flens_dev, 0, stdim)
+        _, m_sts, _ = gv.mcd_l1_per_utt(out["trj_src_trg_src"][i], x, flens_dev, 0, stdim)
+        kl_s = gv.kl_per_utt(out["lat_src"][i], flens_dev, lat_dim)
+        kl_cv = gv.kl_per_utt(out["lat_src_trg"][i], flens_dev, lat_dim)
+        s_ss, s_sts, s_kl = m_ss.sum(), m_sts.sum(), kl_s.sum()
+        s_cv = s_kl + kl_cv[last] if (kl_cv_quirk and len(select_utt_idx) > 1) else kl_cv.sum()
+        c = s_ss + s_sts + s_kl + s_cv
+        total = c if total is None else total + c
+        parts.append((s_ss, s_sts, s_kl, s_cv))
+    return total, parts
+
+
+# ------------------------------------------------------------------------------------------------
+def trainable_parameters(enc: gv.GRU_RNN, dec: gv.GRU_RNN) -> List[torch.nn.Parameter]:
+    """The parameter list the trainer hands to Adam (train_*.py:373-376): conv, gru, out_1 of both nets
+    (scale_in / scale_out are frozen statistics, :369-372)."""
+    ps: List[torch.nn.Parameter] = []
+    for net in (enc, dec):
+        ps += list(net.conv.parameters()) + list(net.gru.parameters()) + list(net.out_1.parameters())
+    return ps
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr=1e-4) of train_*.py:377 over ONE flat fp32 buffer: parameters and their
+    .grad become views of two contiguous tensors, so the data-parallel exchange is a single all-reduce
+    and the update is a single kernel (cvb_adam_step)."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        params = list(params)
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p.data)
+            p.grad = self.grad[off:off + k].view_as(p.data)
+            p.requires_grad_(True)
+            off += k
+        self.params, self.n = params, n
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self, grad_scale: float = 1.0):
+        self.t += 1
+        check(lib.cvb_adam_step(self.n, ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.lr,
+                                self.betas[0], self.betas[1], self.eps, self.t, grad_scale,
+                                torch.cuda.current_stream().cuda_stream), "cvb_adam_step")
+
+
+def allreduce_grads(flat_grad: torch.Tensor) -> None:
+    """The only collective of the data-parallel path: SUM (not mean -- the reference sums the
+    per-utterance losses, train_*.py:1403,1408, so summed shard gradients equal the gradient of one
+    process holding every shard's utterances)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+
+
+def shard_utterances(n_utt: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous utterance shard [lo, hi) of rank `rank` (np.array_split semantics, the split
+    decode_*.py:190 applies to file lists)."""
+    base, rem = divmod(n_utt, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def convert(enc: gv.GRU_RNN, dec: gv.GRU_RNN, feat, code, *, lat_dim: int, y0_enc, y0_dec, eps_mean=None, n_smpl: int = 300):
+    """decode_*.py:303-305,318: ENC -> latent averaged over n_smpl samples -> DEC with the target
+    code.  mean_k(mu + e^{s/2} eps_k) == mu + e^{s/2} mean_k(eps_k): the averaged noise is drawn
+    (or given as eps_mean) once instead of materialising [n_smpl, T, 2*lat] as the reference does.
+    feat: [T,in] (reference layout) or [B,T,in]."""
+    lat, _, _ = enc(feat, y0_enc, clamp_vae=True, lat_dim=lat_dim)
+    if eps_mean is None:
+        shp = lat.shape[:-1] + (lat_dim,)
+        eps_mean = torch.randn(shp, device=lat.device) / float(n_smpl) ** 0.5
+    z = gv.reparam_concat(lat, code, eps_mean, lat_dim)
+    cvm, _, _ = dec(z, y0_dec)
+    return cvm

@@ -1,0 +1,470 @@
+"""Drop-in replacement of the reference module `gru_vae` (src/nets/gru_vae.py) for the GRU-VAE hot path.
+
+Same names, constructor / forward signatures, submodule tree and state_dict keys as the reference,
+so src/bin/train_gru_cyclevae_gauss_batch.py, decode_gru-cyclevae_gauss.py and
+calc_cvgv_gru-cyclevae_gauss.py import and call it unchanged (put cyclevae_vc_b200/dropin ahead of
+src/nets on PYTHONPATH).  The arithmetic runs in libcyclevae_b200.so (sm_100a
+CUDA) through the ctypes layer in _lib.py; torch only owns the tensors and the autograd graph.
+
+    reference                                  here
+    initialize                 gru_vae.py:21   initialize            (identical torch init calls)
+    TwoSidedDilConv1d          gru_vae.py:36   TwoSidedDilConv1d     (parameter container)
+    sampling_vae_batch         gru_vae.py:85   sampling_vae_batch    (cvb_reparam_concat_fwd)
+    loss_vae                   gru_vae.py:117  loss_vae              (cvb_kl_fwd/bwd)
+    GRU_RNN                    gru_vae.py:265  GRU_RNN               (cvb_gru_rnn_forward/backward)
+    TWFSEloss                  gru_vae.py:466  TWFSEloss             (cvb_mcd_l1_fwd/bwd)
+
+Only the argument combinations the reference's own scripts use are implemented (do, clamp_vae,
+lat_dim, h_in; hidden_layers == 1); anything else raises NotImplementedError -- there is no
+fallback to eager PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import CvbNet, CvbNetGrads, check, lib, ptr
+
+__all__ = ["initialize", "TwoSidedDilConv1d", "GRU_RNN", "TWFSEloss", "sampling_vae_batch", "sampling_vae", "loss_vae",
+           "reparam_concat", "kl_per_utt", "mcd_l1_per_utt", "draw_dropout_masks", "LOG_VAR_FLOOR"]
+
+LOG_VAR_FLOOR = -13.815510557964274104107948728106  # gru_vae.py:412
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"cyclevae_vc_b200 computes in float32; got {t.dtype}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# counter-based RNG bookkeeping: (seed, offset) pairs handed to the Philox kernels.  The seed follows
+# torch.manual_seed; offsets never repeat within a seed.
+class _Rng:
+    seed: Optional[int] = None
+    offset: int = 0
+
+    @classmethod
+    def take(cls, n_counters: int):
+        s = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        if cls.seed != s:
+            cls.seed, cls.offset = s, 0
+        off = cls.offset
+        cls.offset += int(n_counters) + 1
+        return s, off
+
+
+def initialize(m):
+    """gru_vae.py:21-33 -- Xavier-uniform for '*weight*', zeros for '*bias*' (init only: plain torch,
+    same call order as the reference so a seeded .apply(initialize) gives identical parameters)."""
+    for name, param in m.named_parameters():
+        if 'weight' in name:
+            nn.init.xavier_uniform_(param)
+        elif 'bias' in name:
+            nn.init.constant_(param, 0.0)
+        else:
+            logging.info("ERROR: " + name)
+
+
+class TwoSidedDilConv1d(nn.Module):
+    """Parameter container with the reference's layout (gru_vae.py:36-51): `layers` Conv1d's,
+    layer i: in*k^i -> in*k^(i+1), dilation k^i, layer 0 zero-padded (k^layers-1)/2 on both sides.
+    The arithmetic is fused into GRU_RNN.forward's front-end kernels."""
+
+    def __init__(self, in_dim=39, kernel_size=3, layers=2):
+        super().__init__()
+        self.in_dim = in_dim
+        self.kernel_size = kernel_size
+        self.layers = layers
+        self.rec_field = self.kernel_size ** self.layers
+        self.padding = int((self.rec_field - 1) / 2)
+        self.conv = nn.ModuleList()
+        for i in range(self.layers):
+            cin = self.in_dim * (self.kernel_size ** i)
+            self.conv += [nn.Conv1d(cin, cin * self.kernel_size, self.kernel_size, stride=1, dilation=self.kernel_size ** i,
+                                    padding=self.padding if i == 0 else 0)]
+
+    def forward(self, x):
+        raise NotImplementedError("TwoSidedDilConv1d is evaluated inside GRU_RNN.forward's fused front-end "
+                                  "(cvb_frontend_fwd); it has no stand-alone eager path")
+
+
+# ------------------------------------------------------------------------------------------------
+class _GruRnnFn(torch.autograd.Function):
+    """GRU_RNN.forward / BPTT through the C ABI.  Inputs after `mod`..: x [B,T,in], y_in [B,out],
+    h_in [B,H] | None, masks (time-major) | None, then the parameters in `mod._param_order`."""
+
+    @staticmethod
+    def forward(ctx, mod, head_mode, lat_dim, x, y_in, h_in, mask_conv_tm, mask_gru_tm, *params):
+        B, T, _ = x.shape
+        dev = x.device
+        net = mod._net_struct(params)
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or y_in.requires_grad or
+                                                  (h_in is not None and h_in.requires_grad) or
+                                                  any(p.requires_grad for p in params))
+        training = 1 if needs_grad else 0
+        netp = C.byref(net)
+        fe_n = lib.cvb_frontend_ws_floats(netp, B, T)
+        rec_n = lib.cvb_recurrent_ws_floats(netp, B, T, training, 1 if mask_gru_tm is not None else 0)
+        scr_n = lib.cvb_scratch_floats(netp, B, T, training)
+        fe_ws = torch.empty(fe_n, dtype=torch.float32, device=dev)
+        rec_ws = torch.empty(rec_n, dtype=torch.float32, device=dev)
+        scratch = mod._scratch(scr_n, dev)
+        trj = torch.empty(B, T, mod.out_dim, dtype=torch.float32, device=dev)
+        y_last = torch.empty(B, mod.out_dim, dtype=torch.float32, device=dev)
+        h_last = torch.empty(B, mod.hidden_units, dtype=torch.float32, device=dev)
+        check(lib.cvb_gru_rnn_forward(netp, B, T, ptr(x), ptr(y_in), ptr(h_in), ptr(mask_conv_tm), ptr(mask_gru_tm),
+                                      head_mode, lat_dim, training, ptr(trj), ptr(y_last), ptr(h_last), ptr(fe_ws),
+                                      ptr(rec_ws), ptr(scratch), _stream()), "cvb_gru_rnn_forward")
+        if needs_grad:
+            ctx.mod, ctx.head_mode, ctx.lat_dim, ctx.dims = mod, head_mode, lat_dim, (B, T)
+            ctx.has_h = h_in is not None
+            ctx.save_for_backward(x, mask_conv_tm, mask_gru_tm, fe_ws, rec_ws, *params)
+        return trj, y_last, h_last
+
+    @staticmethod
+    def backward(ctx, d_trj, d_y_last, d_h_last):
+        mod = ctx.mod
+        B, T = ctx.dims
+        x, mask_conv_tm, mask_gru_tm, fe_ws, rec_ws, *params = ctx.saved_tensors
+        dev = x.device
+        net = mod._net_struct(params)
+        netp = C.byref(net)
+        d_trj = _f32c(d_trj) if d_trj is not None else torch.zeros(B, T, mod.out_dim, device=dev)
+        d_y_last = _f32c(d_y_last) if d_y_last is not None else None
+        d_h_last = _f32c(d_h_last) if d_h_last is not None else None
+        need = ctx.needs_input_grad  # (mod, head, lat, x, y_in, h_in, mc, mg, *params)
+        dx = torch.empty_like(x) if need[3] else None
+        dy_in = torch.empty(B, mod.out_dim, device=dev) if need[4] else None
+        dh_in = torch.empty(B, mod.hidden_units, device=dev) if (ctx.has_h and need[5]) else None
+        grads = CvbNetGrads()
+        gts = []
+        for (field, idx), p, nd in zip(mod._param_fields, params, need[8:]):
+            g = torch.empty_like(p) if nd else None
+            gts.append(g)
+            if g is not None:
+                if idx is None:
+                    setattr(grads, field, ptr(g))
+                else:
+                    getattr(grads, field)[idx] = ptr(g)
+        grads.accumulate = 0
+        scratch = mod._scratch(lib.cvb_scratch_floats(netp, B, T, 1), dev)
+        check(lib.cvb_gru_rnn_backward(netp, B, T, ptr(x), ptr(mask_conv_tm), ptr(mask_gru_tm), ctx.head_mode, ctx.lat_dim,
+                                       None, ptr(d_trj), ptr(d_y_last), ptr(d_h_last), ptr(fe_ws), ptr(rec_ws), ptr(scratch),
+                                       ptr(dx), ptr(dy_in), ptr(dh_in), C.byref(grads), _stream()), "cvb_gru_rnn_backward")
+        return (None, None, None, dx, dy_in, dh_in, None, None, *gts)
+
+
+class GRU_RNN(nn.Module):
+    """GRU-RNN for the VAE encoder / decoder (gru_vae.py:265-455): scale_in -> two-sided dilated conv
+    -> autoregressive GRU (y_{t-1} fed back) -> out_1 -> scale_out.  Constructor and forward keep the
+    reference's signatures; parameters live in the same torch submodules (same state_dict keys)."""
+
+    def __init__(self, in_dim=39, out_dim=35, hidden_units=1024, hidden_layers=1, kernel_size=3, dilation_size=2, do_prob=0,
+                 scale_in_flag=True, scale_out_flag=True, scale_in_out_flag=False):
+        super().__init__()
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        self.hidden_units = hidden_units
+        self.hidden_layers = hidden_layers
+        self.kernel_size = kernel_size
+        self.dilation_size = dilation_size
+        self.do_prob = do_prob
+        self.scale_in_flag = scale_in_flag
+        self.scale_out_flag = scale_out_flag
+        self.scale_in_out_flag = scale_in_out_flag
+        if hidden_layers != 1:
+            raise NotImplementedError("cyclevae_vc_b200: hidden_layers must be 1 (the only value the reference's recipes use)")
+        if scale_in_out_flag:
+            raise NotImplementedError("cyclevae_vc_b200: scale_in_out_flag is never enabled by the reference's scripts")
+        if kernel_size % 2 != 1 or not (1 <= dilation_size <= 4):
+            raise NotImplementedError("cyclevae_vc_b200: kernel_size must be odd and dilation_size in 1..4")
+        # same registration order as gru_vae.py:295-320 (state_dict order and seeded-init parity)
+        if self.scale_in_flag:
+            self.scale_in = nn.Conv1d(self.in_dim, self.in_dim, 1)
+        self.conv = TwoSidedDilConv1d(in_dim=self.in_dim, kernel_size=self.kernel_size, layers=self.dilation_size)
+        self.receptive_field = self.conv.rec_field
+        self.tot_in_dim = self.in_dim * self.receptive_field + self.out_dim
+        if self.do_prob > 0:
+            self.conv_drop = nn.Dropout(p=self.do_prob)
+        self.gru = nn.GRU(self.tot_in_dim, self.hidden_units, self.hidden_layers, batch_first=True)
+        if self.do_prob > 0:
+            self.gru_drop = nn.Dropout(p=self.do_prob)
+        self.out_1 = nn.Conv1d(self.hidden_units, self.out_dim, 1)
+        if self.scale_out_flag:
+            self.scale_out = nn.Conv1d(self.out_dim, self.out_dim, 1)
+        self._injected_masks = None
+        self._scratch_buf = None
+
+    # -- plumbing ----------------------------------------------------------------------------------
+    @property
+    def _param_fields(self):
+        f = []
+        if self.scale_in_flag:
+            f += [("scale_in_w", None), ("scale_in_b", None)]
+        for i in range(self.dilation_size):
+            f += [("conv_w", i), ("conv_b", i)]
+        f += [("w_ih", None), ("w_hh", None), ("b_ih", None), ("b_hh", None), ("out_w", None), ("out_b", None)]
+        if self.scale_out_flag:
+            f += [("scale_out_w", None), ("scale_out_b", None)]
+        return f
+
+    def _param_list(self):
+        p = []
+        if self.scale_in_flag:
+            p += [self.scale_in.weight, self.scale_in.bias]
+        for i in range(self.dilation_size):
+            p += [self.conv.conv[i].weight, self.conv.conv[i].bias]
+        p += [self.gru.weight_ih_l0, self.gru.weight_hh_l0, self.gru.bias_ih_l0, self.gru.bias_hh_l0,
+              self.out_1.weight, self.out_1.bias]
+        if self.scale_out_flag:
+            p += [self.scale_out.weight, self.scale_out.bias]
+        return p
+
+    def _net_struct(self, params) -> CvbNet:
+        net = CvbNet()
+        net.in_dim, net.out_dim, net.hidden = self.in_dim, self.out_dim, self.hidden_units
+        net.kernel_size, net.n_conv = self.kernel_size, self.dilation_size
+        net.has_scale_in, net.has_scale_out = int(self.scale_in_flag), int(self.scale_out_flag)
+        for (field, idx), p in zip(self._param_fields, params):
+            if not p.is_contiguous():
+                raise RuntimeError(f"parameter {field} is not contiguous")
+            if idx is None:
+                setattr(net, field, ptr(p))
+            else:
+                getattr(net, field)[idx] = ptr(p)
+        return net
+
+    def _scratch(self, n_floats: int, dev) -> torch.Tensor:
+        """Scratch shared by successive calls on the same stream (stream order makes reuse safe)."""
+        b = self._scratch_buf
+        if b is None or b.numel() < n_floats or b.device != dev:
+            b = torch.empty(int(n_floats * 1.25) + 64, dtype=torch.float32, device=dev)
+            self._scratch_buf = b
+        return b
+
+    def inject_dropout_masks(self, mask_conv, mask_gru):
+        """Test hook: use these masks ([B,T,C] / [B,T,H], already scaled by 1/(1-p)) for the next
+        forward(do=True) instead of drawing them (the oracle and the reference get the same masks)."""
+        self._injected_masks = (mask_conv, mask_gru)
+
+    # -- forward -----------------------------------------------------------------------------------
+    def forward(self, x, y_in, softmax=False, sigmoid=False, exp=False, h_in=None, noise=0, res=False, res_stdim=0,
+                res_endim=35, do=False, clamp_vae=False, relu_vae=False, lat_dim=16, clamp_vae_laplace=False):
+        """gru_vae.py:322-455.  x: [B,T,in] or [T,in]; y_in: [B,1,out]; h_in: [1,B,H] or None.
+        Returns (trj_out, y_in_last [B,1,out], h [1,B,H])."""
+        if softmax or sigmoid or exp or noise or res or relu_vae or clamp_vae_laplace:
+            raise NotImplementedError("cyclevae_vc_b200.GRU_RNN.forward implements the kwargs the reference's scripts use "
+                                      "(do, clamp_vae, lat_dim, h_in); softmax/sigmoid/exp/noise/res/relu_vae/"
+                                      "clamp_vae_laplace are never passed by them")
+        if not x.is_cuda:
+            raise RuntimeError("cyclevae_vc_b200 runs on CUDA only (no CPU fallback)")
+        batched = x.dim() > 2
+        xb = _f32c(x if batched else x.unsqueeze(0))
+        B, T, cin = xb.shape
+        if cin != self.in_dim:
+            raise ValueError(f"expected {self.in_dim} input features, got {cin}")
+        y0 = _f32c(y_in.reshape(-1, self.out_dim))
+        if y0.shape[0] != B:
+            raise ValueError(f"y_in batch {y0.shape[0]} != x batch {B}")
+        h0 = None
+        if h_in is not None:
+            h0 = _f32c(h_in.reshape(-1, self.hidden_units))
+            if h0.shape[0] != B:
+                raise ValueError(f"h_in batch {h0.shape[0]} != x batch {B}")
+        mc = mg = None
+        if do and self.do_prob > 0:
+            if self._injected_masks is not None:
+                mcb, mgb = self._injected_masks
+                self._injected_masks = None
+                mc = _f32c(mcb.reshape(B, T, -1).transpose(0, 1))
+                mg = _f32c(mgb.reshape(B, T, -1).transpose(0, 1))
+            else:
+                mc, mg = draw_dropout_masks(B, T, self.in_dim * self.receptive_field, self.hidden_units, self.do_prob, xb.device)
+        if self.scale_out_flag:
+            head = _lib.HEAD_SCALE_OUT
+        elif clamp_vae:
+            head = _lib.HEAD_CLAMP
+        else:
+            head = _lib.HEAD_NONE
+        trj, y_last, h_last = _GruRnnFn.apply(self, head, int(lat_dim), xb, y0, h0, mc, mg, *self._param_list())
+        if not batched:
+            trj = trj.squeeze(0)
+        return trj, y_last.unsqueeze(1), h_last.unsqueeze(0)
+
+
+def draw_dropout_masks(B, T, conv_dim, hidden, p, device):
+    """Time-major dropout masks [T,B,conv_dim], [T,B,hidden] with values {0, 1/(1-p)} -- the Bernoulli
+    draws of nn.Dropout at gru_vae.py:355/:369/:380, from Philox4x32-10 keyed by torch's seed."""
+    n1, n2 = T * B * conv_dim, T * B * hidden
+    buf = torch.empty(n1 + n2, dtype=torch.float32, device=device)
+    seed, off = _Rng.take((n1 + n2 + 3) // 4)
+    check(lib.cvb_dropout_mask(n1 + n2, float(p), seed, off, ptr(buf), _stream()), "cvb_dropout_mask")
+    return buf[:n1].view(T, B, conv_dim), buf[n1:].view(T, B, hidden)
+
+
+# ------------------------------------------------------------------------------------------------
+class _ReparamConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lat, code, eps, lat_dim):
+        B, T, _ = lat.shape
+        n_code = 0 if code is None else code.shape[-1]
+        out = torch.empty(B, T, n_code + lat_dim, dtype=torch.float32, device=lat.device)
+        eps_out = None
+        seed = off = 0
+        if eps is None:
+            eps_out = torch.empty(B, T, lat_dim, dtype=torch.float32, device=lat.device)
+            seed, off = _Rng.take((B * T * lat_dim + 3) // 4)
+        check(lib.cvb_reparam_concat_fwd(B, T, lat_dim, n_code, ptr(lat), ptr(code), ptr(eps), seed, off, ptr(eps_out),
+                                         ptr(out), _stream()), "cvb_reparam_concat_fwd")
+        ctx.save_for_backward(lat, eps if eps is not None else eps_out)
+        ctx.n_code, ctx.lat_dim = n_code, lat_dim
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lat, eps = ctx.saved_tensors
+        B, T, _ = lat.shape
+        d_lat = torch.empty_like(lat)
+        check(lib.cvb_reparam_concat_bwd(B, T, ctx.lat_dim, ctx.n_code, ptr(lat), ptr(eps), ptr(_f32c(d_out)), ptr(d_lat),
+                                         _stream()), "cvb_reparam_concat_bwd")
+        return d_lat, None, None, None
+
+
+def reparam_concat(param, code=None, eps=None, lat_dim=None):
+    """Fused `torch.cat((code, sampling_vae_batch(param, lat_dim)), 2)` (train_*.py:1302-1311):
+    [code | mu + exp(sigma/2) * eps].  eps=None draws N(0,1) in-kernel (Philox + Box-Muller)."""
+    if lat_dim is None:
+        lat_dim = param.shape[-1] // 2
+    squeeze = param.dim() == 2
+    p3 = _f32c(param.unsqueeze(0) if squeeze else param)
+    c3 = None if code is None else _f32c(code.unsqueeze(0) if squeeze else code)
+    e3 = None if eps is None else _f32c(eps.reshape(p3.shape[0], p3.shape[1], lat_dim))
+    out = _ReparamConcatFn.apply(p3, c3, e3, int(lat_dim))
+    return out.squeeze(0) if squeeze else out
+
+
+def sampling_vae_batch(param, lat_dim=None, training=False, relu_vae=False, eps=None):
+    """gru_vae.py:85-98: mu + exp(sigma/2) * eps over a [B,T,2*lat] tensor.  The reference draws eps
+    with the CPU generator and copies it to the GPU every call; here eps is drawn on the device
+    (pass `eps` to reproduce a given noise tensor).  `training` only selected no_grad in the
+    reference; autograd already handles that here."""
+    if relu_vae:
+        raise NotImplementedError("sampling_vae_batch(relu_vae=True) is never used by the reference's scripts")
+    return reparam_concat(param, None, eps, lat_dim)
+
+
+def sampling_vae(param, lat_dim=None, eps=None):
+    """gru_vae.py:69-82, the unbatched [T,2*lat] variant."""
+    return reparam_concat(param, None, eps, lat_dim)
+
+
+# ------------------------------------------------------------------------------------------------
+class _KlFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lat, flens, lat_dim):
+        B, T, _ = lat.shape
+        kl = torch.empty(B, dtype=torch.float32, device=lat.device)
+        check(lib.cvb_kl_fwd(B, T, lat_dim, ptr(lat), ptr(flens), ptr(kl), _stream()), "cvb_kl_fwd")
+        ctx.save_for_backward(lat, flens)
+        ctx.lat_dim = lat_dim
+        return kl
+
+    @staticmethod
+    def backward(ctx, d_kl):
+        lat, flens = ctx.saved_tensors
+        B, T, _ = lat.shape
+        d_lat = torch.empty_like(lat)
+        check(lib.cvb_kl_bwd(B, T, ctx.lat_dim, ptr(lat), ptr(flens), ptr(_f32c(d_kl)), ptr(d_lat), _stream()), "cvb_kl_bwd")
+        return d_lat, None, None
+
+
+def kl_per_utt(lat, flens, lat_dim):
+    """loss_vae (gru_vae.py:117-123) for every utterance of a [B,T,2*lat] batch at once:
+    out[j] = loss_vae(lat[j, :flens[j]], lat_dim).  flens: int32 CUDA tensor [B]."""
+    return _KlFn.apply(_f32c(lat), flens, int(lat_dim))
+
+
+def loss_vae(param, lat_dim=None, relu_vae=False):
+    """gru_vae.py:117-127 (Gaussian-prior KL in log-variance form; the relu_vae branch is unused)."""
+    if relu_vae:
+        raise NotImplementedError("loss_vae(relu_vae=True) is never used by the reference's scripts")
+    if lat_dim is None:
+        lat_dim = param.shape[1] // 2
+    F_ = param.shape[0]
+    flens = torch.full((1,), F_, dtype=torch.int32, device=param.device)
+    return kl_per_utt(param.unsqueeze(0), flens, lat_dim)[0]
+
+
+class _McdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, flens, x_off, y_off, D):
+        B, T, _ = x.shape
+        out3 = torch.empty(B, 3, dtype=torch.float32, device=x.device)
+        check(lib.cvb_mcd_l1_fwd(B, T, D, ptr(x), x.shape[2], x_off, ptr(y), y.shape[2], y_off, ptr(flens), ptr(out3),
+                                 _stream()), "cvb_mcd_l1_fwd")
+        ctx.save_for_backward(x, y, flens)
+        ctx.cfg = (x_off, y_off, D)
+        s, m, sd = out3[:, 0], out3[:, 1], out3[:, 2]
+        ctx.mark_non_differentiable(sd)
+        return s, m, sd
+
+    @staticmethod
+    def backward(ctx, d_sum, d_mean, _d_std):
+        x, y, flens = ctx.saved_tensors
+        x_off, y_off, D = ctx.cfg
+        B, T, _ = x.shape
+        dxc = torch.empty(B, T, D, dtype=torch.float32, device=x.device)
+        check(lib.cvb_mcd_l1_bwd(B, T, D, ptr(x), x.shape[2], x_off, ptr(y), y.shape[2], y_off, ptr(flens),
+                                 ptr(_f32c(d_sum)) if d_sum is not None else None,
+                                 ptr(_f32c(d_mean)) if d_mean is not None else None, ptr(dxc), _stream()), "cvb_mcd_l1_bwd")
+        dx = dy = None
+        if ctx.needs_input_grad[0]:
+            if D == x.shape[2]:
+                dx = dxc
+            else:
+                dx = torch.zeros_like(x)
+                dx[:, :, x_off:x_off + D] = dxc
+        if ctx.needs_input_grad[1]:
+            if D == y.shape[2]:
+                dy = -dxc
+            else:
+                dy = torch.zeros_like(y)
+                dy[:, :, y_off:y_off + D] = -dxc
+        return dx, dy, None, None, None, None
+
+
+def mcd_l1_per_utt(x, y, flens, x_off=0, y_off=0, D=None):
+    """TWFSEloss(x[j,:flen], y[j,:flen], L2=False, GV=False) for every utterance j at once; the
+    compared features are x[..., x_off:x_off+D] and y[..., y_off:y_off+D].  Returns (sum, mean, std)
+    tensors of shape [B]."""
+    if D is None:
+        D = x.shape[2] - x_off
+    return _McdFn.apply(_f32c(x), _f32c(y), flens, int(x_off), int(y_off), int(D))
+
+
+class TWFSEloss(nn.Module):
+    """gru_vae.py:466-534 for the one mode every script uses (twf=None, rmse=False, L2=False, GV=False):
+    per-frame (10/ln10)*sqrt(2)*sum_d|x-y|, returning (sum, mean, unbiased std) over frames."""
+
+    def __init__(self):
+        super().__init__()
+        self.criterion = None
+
+    def forward(self, x, y, twf=None, GV=True, rmse=False, L2=True):
+        if twf is not None or rmse or L2 or GV:
+            raise NotImplementedError("cyclevae_vc_b200.TWFSEloss implements (twf=None, rmse=False, L2=False, GV=False), "
+                                      "the only mode the reference's scripts call")
+        F_ = x.shape[0]
+        flens = torch.full((1,), F_, dtype=torch.int32, device=x.device)
+        s, m, sd = mcd_l1_per_utt(x.unsqueeze(0), y.unsqueeze(0), flens)
+        return s[0], m[0], sd[0]

@@ -1,0 +1,167 @@
+/*
+ * cyclevae_b200.h -- C ABI of libcyclevae_b200.so (sm_100a CUDA).
+ *
+ * The reference (patrickltobing/cyclevae-vc) has no FFI: its boundary for this path is the Python
+ * surface of src/nets/gru_vae.py.  These entry points are what a ctypes binding of that module
+ * calls (cyclevae_vc_b200/gru_vae.py is that binding; INTEGRATION.md shows the stub).  Each entry
+ * point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise; the library
+ *     allocates nothing the caller sees: outputs and workspaces are caller-allocated (torch.empty);
+ *   - `stream` is a cudaStream_t passed as void*; no hidden synchronisation;
+ *   - return value 0 = ok, non-zero = error (message via cvb_last_error()); no exceptions cross;
+ *   - "bm" = batch-major [B,T,C] (the reference's tensor layout); "tm" = time-major [T,B,C]
+ *     (the internal layout of the recurrence: one contiguous [B,C] block per frame).
+ *   - no CPU fallback exists: every call needs a CUDA device.
+ */
+#ifndef CYCLEVAE_B200_H
+#define CYCLEVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVB_ABI_VERSION 3
+
+/* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
+ * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
+ * state_dict), so in-place optimizer updates are seen by the next call with no staging step. */
+typedef struct cvb_net {
+    int32_t in_dim;        /* gru_vae.py:284 */
+    int32_t out_dim;       /* gru_vae.py:285 */
+    int32_t hidden;        /* hidden_units, gru_vae.py:286 */
+    int32_t kernel_size;   /* gru_vae.py:288 */
+    int32_t n_conv;        /* "dilation_size" = number of conv layers, gru_vae.py:300 */
+    int32_t has_scale_in;  /* gru_vae.py:295-297 */
+    int32_t has_scale_out; /* gru_vae.py:316-318 */
+    int32_t reserved;
+    const float* scale_in_w;  /* [in,in,1]  */
+    const float* scale_in_b;  /* [in]       */
+    const float* conv_w[4];   /* layer i: [in*k^(i+1), in*k^i, k]  (gru_vae.py:47-51) */
+    const float* conv_b[4];   /* layer i: [in*k^(i+1)] */
+    const float* w_ih;        /* gru.weight_ih_l0 [3H, in*k^n + out], gate rows r,z,n */
+    const float* w_hh;        /* gru.weight_hh_l0 [3H, H] */
+    const float* b_ih;        /* [3H] */
+    const float* b_hh;        /* [3H] */
+    const float* out_w;       /* out_1.weight [out,H,1] */
+    const float* out_b;       /* [out] */
+    const float* scale_out_w; /* [out,out,1] */
+    const float* scale_out_b; /* [out] */
+} cvb_net;
+
+/* Gradient destinations, same shapes as the parameters; any pointer may be NULL (= not wanted).
+ * Values are OVERWRITTEN when accumulate == 0 and ADDED TO when accumulate != 0. */
+typedef struct cvb_net_grads {
+    float* scale_in_w;
+    float* scale_in_b;
+    float* conv_w[4];
+    float* conv_b[4];
+    float* w_ih;
+    float* w_hh;
+    float* b_ih;
+    float* b_hh;
+    float* out_w;
+    float* out_b;
+    float* scale_out_w;
+    float* scale_out_b;
+    int32_t accumulate;
+    int32_t reserved;
+} cvb_net_grads;
+
+/* head modes for cvb_gru_rnn_forward (gru_vae.py:402-412) */
+#define CVB_HEAD_NONE 0      /* trj_out = y                         */
+#define CVB_HEAD_CLAMP 1     /* encoder, clamp_vae=True (:408-412)  */
+#define CVB_HEAD_SCALE_OUT 2 /* decoder, scale_out conv (:402-406)  */
+
+const char* cvb_last_error(void);
+int cvb_abi_version(void);
+/* number of SMs / max dynamic shared memory of the current device; <0 on error */
+int cvb_device_info(int* n_sm, int* max_smem_optin, int* cc_major, int* cc_minor);
+
+/* ---- workspace sizing (host-only arithmetic; callable without a GPU) ------------------------ */
+/* floats of the front-end's padded-grid buffers (all layers) + repacked conv weights */
+size_t cvb_frontend_ws_floats(const cvb_net* net, int B, int T);
+/* floats of the recurrence state kept for backward: hs,ys (+ r,z,n,ghn,o when training) */
+size_t cvb_recurrent_ws_floats(const cvb_net* net, int B, int T, int training, int has_mask);
+/* floats of scratch not needed after the call (gx, y-partials, barrier words) */
+size_t cvb_scratch_floats(const cvb_net* net, int B, int T, int training);
+
+/* ---- GRU_RNN.forward (gru_vae.py:322-455; kwargs do / clamp_vae / lat_dim / h_in) ------------
+ * x_bm [B,T,in]; y_in [B,out] (the reference's [B,1,out]); h_in [B,H] or NULL (= zeros);
+ * mask_conv_tm [T,B,in*k^n] / mask_gru_tm [T,B,H]: dropout masks already scaled by 1/(1-p), or
+ * NULL (eval / do=False) -- the replacement of nn.Dropout at :355/:369/:380.
+ * Outputs: trj_out_bm [B,T,out], y_last [B,out] (pre-head), h_last [B,H].
+ * fe_ws / rec_ws are kept by the caller for cvb_gru_rnn_backward when training != 0. */
+int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, const float* y_in,
+                        const float* h_in, const float* mask_conv_tm, const float* mask_gru_tm,
+                        int head_mode, int lat_dim, int training, float* trj_out_bm, float* y_last,
+                        float* h_last, float* fe_ws, float* rec_ws, float* scratch, void* stream);
+
+/* BPTT of the above (autograd of gru_vae.py:322-455).
+ * d_trj_out_bm [B,T,out], d_y_last [B,out] or NULL, d_h_last [B,H] or NULL.
+ * Outputs (any may be NULL): dx_bm [B,T,in], dy_in [B,out], dh_in [B,H]; parameter grads -> grads. */
+int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm,
+                         const float* mask_conv_tm, const float* mask_gru_tm, int head_mode,
+                         int lat_dim, const float* trj_out_bm, const float* d_trj_out_bm,
+                         const float* d_y_last, const float* d_h_last, const float* fe_ws,
+                         const float* rec_ws, float* scratch, float* dx_bm, float* dy_in,
+                         float* dh_in, const cvb_net_grads* grads, void* stream);
+
+/* ---- pieces, exported for unit tests and for callers that fuse differently ------------------ */
+/* scale_in + TwoSidedDilConv1d (+mask) -> xc_tm [T,B,in*k^n]   (gru_vae.py:336,53-66,355) */
+int cvb_frontend_fwd(const cvb_net* net, int B, int T, const float* x_bm, const float* mask_conv_tm,
+                     float* fe_ws, float* xc_tm, void* stream);
+
+/* ---- sampling_vae_batch + torch.cat((code, z), 2) fused (gru_vae.py:85-98; train_*.py:1302) ---
+ * lat_bm [B,T,2*lat] = [mu | log-var]; eps_bm [B,T,lat] or NULL (then N(0,1) is drawn in-kernel
+ * from Philox4x32-10 keyed by (seed, offset) and, if eps_out != NULL, stored for backward);
+ * code_bm [B,T,n_code] or NULL with n_code == 0.  out_bm [B,T,n_code+lat] = [code | mu+exp(s/2)eps] */
+int cvb_reparam_concat_fwd(int B, int T, int lat, int n_code, const float* lat_bm,
+                           const float* code_bm, const float* eps_bm, uint64_t seed, uint64_t offset,
+                           float* eps_out, float* out_bm, void* stream);
+/* d_out_bm [B,T,n_code+lat] -> d_lat_bm [B,T,2*lat] (code gets no gradient) */
+int cvb_reparam_concat_bwd(int B, int T, int lat, int n_code, const float* lat_bm,
+                           const float* eps_bm, const float* d_out_bm, float* d_lat_bm, void* stream);
+/* generic feature concat [B,T,ca] ++ [B,T,cb] (train_*.py:1304,1307) and its split backward */
+int cvb_concat2_fwd(int rows, int ca, const float* a, int lda, int cb, const float* b, int ldb,
+                    float* out, void* stream);
+
+/* ---- losses -----------------------------------------------------------------------------------
+ * loss_vae (gru_vae.py:117-123) per utterance: kl[j] = mean_{t<flen[j]} 0.5*sum_d(e^s+mu^2-s-1).
+ * lat_bm [B,T,2*lat]; flens int32 [B] (device); utterances with flen<=0 give 0. */
+int cvb_kl_fwd(int B, int T, int lat, const float* lat_bm, const int32_t* flens, float* kl,
+               void* stream);
+int cvb_kl_bwd(int B, int T, int lat, const float* lat_bm, const int32_t* flens, const float* d_kl,
+               float* d_lat_bm, void* stream);
+/* TWFSEloss.forward(x, y, L2=False, GV=False) (gru_vae.py:521-534) per utterance:
+ * per frame mcd_t = (10/ln10)*sqrt(2)*sum_d|x-y|; out3 [B,3] = (sum, mean, unbiased std) over
+ * t<flen[j].  x_bm [B,T,ldx] uses columns [x_off, x_off+D); y likewise. */
+int cvb_mcd_l1_fwd(int B, int T, int D, const float* x_bm, int ldx, int x_off, const float* y_bm,
+                   int ldy, int y_off, const int32_t* flens, float* out3, void* stream);
+/* gradient of d_sum[j]*sum + d_mean[j]*mean w.r.t. x (written to dx_bm [B,T,D], zero beyond flen) */
+int cvb_mcd_l1_bwd(int B, int T, int D, const float* x_bm, int ldx, int x_off, const float* y_bm,
+                   int ldy, int y_off, const int32_t* flens, const float* d_sum,
+                   const float* d_mean, float* dx_bm, void* stream);
+
+/* ---- dropout masks (replacement of nn.Dropout's Bernoulli draw, gru_vae.py:303-304,312-313) ---
+ * out[i] = (u_i >= p) ? 1/(1-p) : 0 with u from Philox4x32-10(seed, offset + i/4) */
+int cvb_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, float* out, void* stream);
+
+/* ---- fused Adam over a flat fp32 buffer (caller = train_*.py:377,1420 torch.optim.Adam) ------ */
+int cvb_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                  void* stream);
+
+/* plain fp32 GEMM used by the path (row-major; C = alpha*op(A)*op(B) + beta*C); exported so the
+ * tests can check it in isolation. */
+int cvb_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* Bm, int ldb, float beta, float* C, int ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYCLEVAE_B200_H */

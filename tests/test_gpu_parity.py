@@ -1,0 +1,394 @@
+"""Parity of the CUDA path (through the drop-in module -> ctypes -> C ABI) against the CPU oracle and
+the reference-generated golden fixtures.  Everything here needs a B200: `pytest -m gpu`.
+
+Tolerances (fp32 arithmetic, different summation order than the reference):
+  * forward outputs (mcep / latent / states): max-abs <= 1e-4  (BASELINE.json north_star)
+  * gradients: 1e-4 relative to max(1, max|ref|) on tiny nets, 2e-4 relative on gradient norms at hu1024
+  * integers (chunk schedule) bit-exact -- covered on CPU in test_host_cpu.py
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gru_vae_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def cvb():
+    import cyclevae_vc_b200 as pkg  # raises if libcyclevae_b200.so is missing: no silent fallback
+    assert torch.cuda.is_available()
+    return pkg
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _params(g, prefix):
+    return {k[len(prefix):]: torch.tensor(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def _module(cvb, spec: orc.NetSpec, P):
+    m = cvb.GRU_RNN(in_dim=spec.in_dim, out_dim=spec.out_dim, hidden_units=spec.hidden_units, kernel_size=spec.kernel_size,
+                    dilation_size=spec.dilation_size, do_prob=spec.do_prob, scale_in_flag=spec.scale_in,
+                    scale_out_flag=spec.scale_out)
+    res = m.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    return m.cuda()
+
+
+def _c(a):
+    return torch.tensor(np.asarray(a)).cuda()
+
+
+def _maxabs(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+
+
+@pytest.fixture(scope="module")
+def tiny(golden_dir, cvb):
+    g = _load(golden_dir, "tiny.npz")
+    enc = orc.NetSpec(in_dim=7, out_dim=6, hidden_units=20, do_prob=0.5, scale_in=True, scale_out=False)
+    dec = orc.NetSpec(in_dim=5, out_dim=4, hidden_units=20, do_prob=0.5, scale_in=False, scale_out=True)
+    Pe, Pd = _params(g, "Pe/"), _params(g, "Pd/")
+    return g, enc, dec, Pe, Pd, _module(cvb, enc, Pe), _module(cvb, dec, Pd)
+
+
+def test_gemm_matches_torch(cvb):
+    from cyclevae_vc_b200._lib import check, lib, ptr
+    torch.manual_seed(0)
+    for (M, N, K, ta, tb) in [(37, 29, 53, 0, 1), (64, 128, 256, 1, 0), (5, 7, 1000, 0, 0), (130, 66, 31, 1, 1)]:
+        A = torch.randn((K, M) if ta else (M, K), device="cuda")
+        Bm = torch.randn((N, K) if tb else (K, N), device="cuda")
+        Cm = torch.randn(M, N, device="cuda")
+        ref = 0.5 * (A.t() if ta else A).double() @ (Bm.t() if tb else Bm).double() + 2.0 * Cm.double()
+        check(lib.cvb_gemm(ta, tb, M, N, K, 0.5, ptr(A), A.shape[1], ptr(Bm), Bm.shape[1], 2.0, ptr(Cm), N,
+                           torch.cuda.current_stream().cuda_stream))
+        assert _maxabs(Cm.double(), ref) < 1e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_tiny_forward_eval_layouts(tiny):
+    g, enc, dec, Pe, Pd, me, md = tiny
+    lat = int(g["lat"])
+    me.eval(); md.eval()
+    with torch.no_grad():
+        o, y, h = me(_c(g["x"]), _c(g["y0e"]), clamp_vae=True, lat_dim=lat)
+        for a, k in ((o, "enc_eval_trj"), (y, "enc_eval_y"), (h, "enc_eval_h")):
+            assert _maxabs(a, g[k]) < TOL, k
+        assert (o.cpu().numpy()[:, :, lat:] == np.float32(orc.LOG_VAR_FLOOR)).any(), "clamp branch not exercised"
+        o, y, h = me(_c(g["x"]), _c(g["y0e"]), h_in=_c(g["h0e"]), clamp_vae=True, lat_dim=lat)
+        for a, k in ((o, "enc_eval_hin_trj"), (y, "enc_eval_hin_y"), (h, "enc_eval_hin_h")):
+            assert _maxabs(a, g[k]) < TOL, k
+        o, y, h = md(_c(g["xd"]), _c(g["y0d"]), h_in=_c(g["h0d"]))
+        for a, k in ((o, "dec_eval_trj"), (y, "dec_eval_y"), (h, "dec_eval_h")):
+            assert _maxabs(a, g[k]) < TOL, k
+        # unbatched [T,C] layout (gru_vae.py:339-346,405-406,423-426)
+        o, y, h = me(_c(g["x"][1]), _c(g["y0e"][1:2]), clamp_vae=True, lat_dim=lat)
+        for a, k in ((o, "enc_unb_trj"), (y, "enc_unb_y"), (h, "enc_unb_h")):
+            assert _maxabs(a, g[k]) < TOL, k
+        o, y, h = md(_c(g["xd"][2]), _c(g["y0d"][2:3]))
+        for a, k in ((o, "dec_unb_trj"), (y, "dec_unb_y"), (h, "dec_unb_h")):
+            assert _maxabs(a, g[k]) < TOL, k
+
+
+def test_tiny_frontend(tiny):
+    import ctypes as C
+    from cyclevae_vc_b200._lib import check, lib, ptr
+    g, enc, dec, Pe, Pd, me, md = tiny
+    for m, xk, ok in ((me, "x", "enc_xconv"), (md, "xd", "dec_xconv")):
+        x = _c(g[xk])
+        B, T, _ = x.shape
+        net = m._net_struct(m._param_list())
+        ws = torch.empty(lib.cvb_frontend_ws_floats(C.byref(net), B, T), device="cuda")
+        Cd = m.in_dim * m.receptive_field
+        xc = torch.empty(T, B, Cd, device="cuda")
+        check(lib.cvb_frontend_fwd(C.byref(net), B, T, ptr(x), None, ptr(ws), ptr(xc), torch.cuda.current_stream().cuda_stream))
+        assert _maxabs(xc.transpose(0, 1), g[ok]) < TOL
+
+
+@pytest.mark.parametrize("net", ["enc", "dec"])
+def test_tiny_forward_backward_with_dropout_masks(tiny, net):
+    g, enc, dec, Pe, Pd, me, md = tiny
+    lat = int(g["lat"])
+    m, xk, y0k, h0k, mck, mgk, kw = ((me, "x", "y0e", "h0e", "mce", "mge", dict(clamp_vae=True, lat_dim=lat)) if net == "enc"
+                                     else (md, "xd", "y0d", "h0d", "mcd", "mgd", {}))
+    m.train()
+    m.zero_grad()
+    x, y0, h0 = (_c(g[n]).requires_grad_(True) for n in (xk, y0k, h0k))
+    m.inject_dropout_masks(_c(g[mck]), _c(g[mgk]))
+    o, y, h = m(x, y0, h_in=h0, do=True, **kw)
+    wt = torch.linspace(-1, 1, o.numel()).reshape(o.shape).cuda()
+    loss = (o * wt).sum() + 0.7 * (y * y).sum() + 0.3 * h.sum()
+    loss.backward()
+    assert _maxabs(o, g[f"{net}_tr_trj"]) < TOL
+    assert _maxabs(y, g[f"{net}_tr_y"]) < TOL
+    assert _maxabs(h, g[f"{net}_tr_h"]) < TOL
+    assert abs(loss.item() - float(g[f"{net}_tr_loss"])) < 1e-3
+    for a, k in ((x.grad, "dx"), (y0.grad, "dy0"), (h0.grad, "dh0")):
+        ref = g[f"{net}_tr_{k}"]
+        assert _maxabs(a, ref) < 1e-4 * max(1.0, np.abs(ref).max()), k
+    n_checked = 0
+    for k, p in m.named_parameters():
+        key = f"{net}_tr_grad/{k}"
+        if key in g.files:
+            ref = g[key]
+            assert p.grad is not None, k
+            assert _maxabs(p.grad, ref) < 1e-4 * max(1.0, np.abs(ref).max()), k
+            n_checked += 1
+    assert n_checked >= 10
+
+
+def test_losses_and_sampling(tiny, cvb):
+    g = tiny[0]
+    kl = cvb.loss_vae(_c(g["loss_lat_in"]), lat_dim=3)
+    assert abs(kl.item() - float(g["loss_kl"])) < 1e-5
+    crit = cvb.TWFSEloss()
+    s, m, sd = crit(_c(g["mcd_a"]), _c(g["mcd_b"]), L2=False, GV=False)
+    assert abs(s.item() - float(g["mcd_sum"])) < 1e-3
+    assert abs(m.item() - float(g["mcd_mean"])) < 1e-4
+    assert abs(sd.item() - float(g["mcd_std"])) < 1e-4
+    # gradients of both losses vs autograd of the oracle, ragged lengths, batched entry points
+    gen = torch.Generator().manual_seed(3)
+    B, T, lat, D = 4, 23, 5, 9
+    latp = torch.randn(B, T, 2 * lat, generator=gen)
+    a, b = torch.randn(B, T, D, generator=gen), torch.randn(B, T, D + 4, generator=gen)
+    flens = [23, 0, 7, 1]
+    lc, ac = latp.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    ref = sum(orc.loss_vae(lc[j, :f], lat) * (j + 1) for j, f in enumerate(flens) if f > 0) + \
+        sum(orc.mcd_l1(ac[j, :f], b[j, :f, 4:])[1] * (j + 2) + 0.1 * orc.mcd_l1(ac[j, :f], b[j, :f, 4:])[0]
+            for j, f in enumerate(flens) if f > 0)
+    ref.backward()
+    lg, ag = latp.cuda().requires_grad_(True), a.cuda().requires_grad_(True)
+    fl = torch.tensor(flens, dtype=torch.int32, device="cuda")
+    wk = torch.arange(1, B + 1, device="cuda", dtype=torch.float32)
+    s, m, sd = cvb.mcd_l1_per_utt(ag, b.cuda(), fl, 0, 4)
+    out = (cvb.kl_per_utt(lg, fl, lat) * wk).sum() + (m * (wk + 1)).sum() + 0.1 * s.sum()
+    out.backward()
+    assert abs(out.item() - ref.item()) < 1e-3 * max(1.0, abs(ref.item()))
+    assert _maxabs(lg.grad, lc.grad) < 1e-5 * max(1.0, lc.grad.abs().max().item())
+    assert _maxabs(ag.grad, ac.grad) < 1e-5 * max(1.0, ac.grad.abs().max().item())
+    # reparameterise + concat, given noise: forward and backward
+    eps = torch.randn(B, T, lat, generator=gen)
+    code = torch.randn(B, T, 2, generator=gen)
+    lc = latp.clone().requires_grad_(True)
+    zr = torch.cat((code, orc.sampling_vae_batch(lc, eps, lat)), 2)
+    wz = torch.linspace(-1, 1, zr.numel()).reshape(zr.shape)
+    (zr * wz).sum().backward()
+    lg = latp.cuda().requires_grad_(True)
+    z = cvb.reparam_concat(lg, code.cuda(), eps.cuda(), lat)
+    (z * wz.cuda()).sum().backward()
+    assert _maxabs(z, zr) < 1e-5
+    assert _maxabs(lg.grad, lc.grad) < 1e-5 * max(1.0, lc.grad.abs().max().item())
+    assert _maxabs(cvb.sampling_vae_batch(latp.cuda(), lat_dim=lat, eps=eps.cuda()), orc.sampling_vae_batch(latp, eps, lat)) < 1e-5
+
+
+def test_device_rng_statistics(cvb):
+    """In-kernel Philox draws: dropout keep-rate and N(0,1) moments; seeded reproducibility."""
+    from cyclevae_vc_b200.gru_vae import draw_dropout_masks
+    torch.manual_seed(11)
+    mc, mg = draw_dropout_masks(16, 40, 486, 1024, 0.5, torch.device("cuda"))
+    for m in (mc, mg):
+        vals = torch.unique(m)
+        assert vals.tolist() == [0.0, 2.0]
+        assert abs((m > 0).float().mean().item() - 0.5) < 5e-3
+    latp = torch.zeros(64, 100, 64, device="cuda")
+    z = cvb.sampling_vae_batch(latp, lat_dim=32)       # mu=0, log-var=0 -> z = eps
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+    assert abs((z ** 4).mean().item() - 3.0) < 0.1
+    torch.manual_seed(11)
+    mc2, _ = draw_dropout_masks(16, 40, 486, 1024, 0.5, torch.device("cuda"))
+    assert torch.equal(mc, mc2)
+
+
+def test_adam_matches_torch(cvb):
+    from cyclevae_vc_b200.cycle import FlatAdam
+    torch.manual_seed(5)
+    ps = [torch.nn.Parameter(torch.randn(37, 11, device="cuda")), torch.nn.Parameter(torch.randn(501, device="cuda"))]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.Adam(qs, lr=1e-2)
+    opt = FlatAdam(ps, lr=1e-2)
+    for it in range(5):
+        gs = [torch.randn_like(p) for p in ps]
+        opt.zero_grad()
+        for p, q, g_ in zip(ps, qs, gs):
+            p.grad.add_(g_)
+            q.grad = g_.clone()
+        opt.step()
+        ref.step()
+    for p, q in zip(ps, qs):
+        assert _maxabs(p, q) < 1e-5
+
+
+def _cyc_setup(cvb, hu, lat, B, T, n_cyc, seed, pe_seed, pd_seed, n_spk=2):
+    stdim = 4
+    mean, std = orc.synth_stats(50)
+    enc, dec = orc.encoder_spec(54, lat, hu), orc.decoder_spec(lat, n_spk, 50, hu)
+    Pe = orc.init_params(enc, pe_seed, mean=mean, scale=std)
+    Pd = orc.init_params(dec, pd_seed, mean=mean[stdim:], scale=std[stdim:])
+    me, md = _module(cvb, enc, Pe).train(), _module(cvb, dec, Pd).train()
+    for m in (me, md):
+        for k, p in m.named_parameters():
+            p.requires_grad_(not k.startswith("scale_"))
+    x, cv, sc, tc = orc.synth_batch(B, T, seed)
+    eps = orc.synth_noise(B, T, lat, n_cyc, seed)
+    masks = orc.synth_masks(B, T, enc, dec, n_cyc, seed)
+    y0e = torch.zeros(B, 1, 2 * lat)
+    y0d = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1).repeat(B, 1, 1)
+    return enc, dec, me, md, x, cv, sc, tc, eps, masks, y0e, y0d
+
+
+def _run_cyc(cvb, me, md, x, cv, sc, tc, eps, masks, y0e, y0d, n_cyc, lat, flen_acc, select):
+    from cyclevae_vc_b200 import cycle
+    cu = lambda t: t.cuda()
+    out, st = cycle.cyc_forward(me, md, x=cu(x), cv=cu(cv), src_code=cu(sc), trg_code=cu(tc), n_cyc=n_cyc, lat_dim=lat,
+                                stdim=4, y0_enc=cu(y0e), y0_dec=cu(y0d), do=True,
+                                eps=[[cu(e) for e in ec] for ec in eps],
+                                masks=[[(cu(a), cu(b)) for a, b in mc] for mc in masks])
+    total, parts = cycle.cyc_loss(out, cu(x), n_cyc=n_cyc, lat_dim=lat, stdim=4, flen_acc=flen_acc, select_utt_idx=select)
+    return out, total
+
+
+def test_cfg0_cyc1_step_vs_reference_golden(golden_dir, cvb):
+    """BASELINE.json configs[0] (hu128 ld16 cyc1, 8x200x50) -- on the GPU path, vs fixtures produced by the
+    unmodified reference: outputs, loss, gradient norms and samples."""
+    g = _load(golden_dir, "cfg0_cyc1.npz")
+    lat, B, T = 16, 8, 200
+    enc, dec, me, md, x, cv, sc, tc, eps, masks, y0e, y0d = _cyc_setup(cvb, 128, lat, B, T, 1, 0, 101, 102)
+    out, total = _run_cyc(cvb, me, md, x, cv, sc, tc, eps, masks, y0e, y0d, 1, lat, g["flen_acc"].tolist(), list(range(B)))
+    total.backward()
+    assert total.item() == pytest.approx(float(g["loss"]), rel=5e-6)
+    for k in out:
+        assert _maxabs(out[k][0][:, ::9], g[k]) < TOL, k
+    for net, m in (("enc", me), ("dec", md)):
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                continue
+            gr = p.grad.detach().cpu().numpy()
+            assert np.sqrt((gr.astype(np.float64) ** 2).sum()) == pytest.approx(float(g[f"gnorm/{net}/{k}"]), rel=2e-4), k
+            samp = gr.reshape(-1)[:: max(1, gr.size // 64)][:64]
+            ref = g[f"gsamp/{net}/{k}"]
+            assert np.abs(samp - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), k
+
+
+def test_flagship_cyc2_step_vs_reference_golden(golden_dir, cvb):
+    """configs[1] shapes (hu1024 ld32 cyc2, T=80) at B=2, ragged flen_acc, KL-cv quirk."""
+    g = _load(golden_dir, "flagship.npz")
+    lat, B, T, n_cyc = 32, 2, 80, 2
+    enc, dec, me, md, x, cv, sc, tc, eps, masks, y0e, y0d = _cyc_setup(cvb, 1024, lat, B, T, n_cyc, 3, 201, 202)
+    out, total = _run_cyc(cvb, me, md, x, cv, sc, tc, eps, masks, y0e, y0d, n_cyc, lat, [T, 61], [0, 1])
+    total.backward()
+    assert total.item() == pytest.approx(float(g["cyc2/loss"]), rel=5e-6)
+    for k in out:
+        for i in range(n_cyc):
+            assert _maxabs(out[k][i][:, ::8], g[f"cyc2/{k}/{i}"]) < TOL, (k, i)
+    for net, m in (("enc", me), ("dec", md)):
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                continue
+            gr = p.grad.detach().cpu().numpy()
+            assert np.sqrt((gr.astype(np.float64) ** 2).sum()) == pytest.approx(float(g[f"cyc2/gnorm/{net}/{k}"]), rel=3e-4), k
+            samp = gr.reshape(-1)[:: max(1, gr.size // 64)][:64]
+            ref = g[f"cyc2/gsamp/{net}/{k}"]
+            assert np.abs(samp - ref).max() < 3e-4 * max(1.0, np.abs(ref).max()), k
+
+
+@pytest.mark.parametrize("tag,gain,bstd", [("init", 1.0, 0.0), ("trained", 3.0, 0.05)])
+def test_flagship_decode_and_carry(golden_dir, cvb, tag, gain, bstd):
+    """hu1024 ld32: stage-6 conversion of an 800-frame utterance in the reference's unbatched layout and
+    two 80-frame chunks with carried (y, h); reference-init and 'trained-like' (x3 weights) parameters."""
+    from cyclevae_vc_b200 import cycle
+    g = _load(golden_dir, "flagship.npz")
+    lat, stdim = 32, 4
+    mean, std = orc.synth_stats(50)
+    enc, dec = orc.encoder_spec(54, lat, 1024), orc.decoder_spec(lat, 2, 50, 1024)
+    Pe = orc.init_params(enc, 201, gain=gain, bias_std=bstd, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 202, gain=gain, bias_std=bstd, mean=mean[stdim:], scale=std[stdim:])
+    me, md = _module(cvb, enc, Pe).eval(), _module(cvb, dec, Pd).eval()
+    y0d1 = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1).cuda()
+    T = 800
+    x, _, sc, tc = orc.synth_batch(1, T, 1)
+    eps_mean = (orc.synth_noise(1, T, lat, 1, 1)[0][0] / np.sqrt(300.0)).cuda()
+    with torch.no_grad():
+        lat_src, _, _ = me(x[0].cuda(), torch.zeros(1, 1, 2 * lat).cuda(), clamp_vae=True, lat_dim=lat)
+        cvm = cycle.convert(me, md, x[0].cuda(), tc[0].cuda(), lat_dim=lat, y0_enc=torch.zeros(1, 1, 2 * lat).cuda(),
+                            y0_dec=y0d1, eps_mean=eps_mean[0])
+    assert lat_src.shape == (T, 2 * lat) and cvm.shape == (T, 50)
+    assert _maxabs(lat_src[::5], g[f"{tag}/dec800_lat"]) < TOL
+    assert _maxabs(cvm[::5], g[f"{tag}/dec800_cvmcep"]) < TOL
+    B, T = 3, 80
+    x, cv, sc, tc = (t.cuda() for t in orc.synth_batch(B, 2 * T, 2))
+    with torch.no_grad():
+        o1, y1, h1 = me(x[:, :T], torch.zeros(B, 1, 2 * lat).cuda(), clamp_vae=True, lat_dim=lat)
+        o2, y2, h2 = me(x[:, T:], y1, h_in=h1, clamp_vae=True, lat_dim=lat)
+        zin = torch.cat((sc, torch.cat((o1, o2), 1)[:, :, :lat]), 2)
+        d1, yd1, hd1 = md(zin[:, :T], y0d1.repeat(B, 1, 1))
+        d2, yd2, hd2 = md(zin[:, T:], yd1, h_in=hd1)
+    assert _maxabs(torch.cat((o1, o2), 1)[:, ::4], g[f"{tag}/carry_lat"]) < TOL
+    assert _maxabs(torch.cat((d1, d2), 1)[:, ::4], g[f"{tag}/carry_mcep"]) < TOL
+    assert _maxabs(h2[:, :, ::8], g[f"{tag}/carry_h_enc"]) < TOL
+    assert _maxabs(hd2[:, :, ::8], g[f"{tag}/carry_h_dec"]) < TOL
+
+
+def test_spk4_decoder(golden_dir, cvb):
+    """configs[3]: 4-speaker one-hot code (decoder in_dim 36)."""
+    g = _load(golden_dir, "spk4.npz")
+    lat, stdim = 32, 4
+    mean, std = orc.synth_stats(50)
+    dec = orc.decoder_spec(lat, 4, 50, 1024)
+    Pd = orc.init_params(dec, 302, mean=mean[stdim:], scale=std[stdim:])
+    md = _module(cvb, dec, Pd).eval()
+    B, T = 2, 40
+    z = torch.randn(B, T, lat, generator=torch.Generator().manual_seed(55))
+    code = torch.zeros(B, T, 4)
+    code[0, :, 2] = 1
+    code[1, :, 3] = 1
+    y0 = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1).repeat(B, 1, 1)
+    with torch.no_grad():
+        o, y, h = md(torch.cat((code, z), 2).cuda(), y0.cuda())
+    assert _maxabs(o, g["trj"]) < TOL
+    assert _maxabs(y, g["y"]) < TOL
+    assert _maxabs(h[:, :, ::8], g["h"]) < TOL
+
+
+def test_full_size_properties(cvb):
+    """BASELINE.json full sizes (hu1024, B=80 x T=80 training chunk; wide decode batch), checked through
+    size-independent properties: run-to-run determinism (no float atomics), batch-row independence
+    (row j of a batched call == the unbatched call on row j), a seeded oracle spot-check of a few rows,
+    and zero gradient to padded frames' inputs when the loss masks them out of reach of the receptive field."""
+    lat, stdim = 32, 4
+    mean, std = orc.synth_stats(50)
+    enc = orc.encoder_spec(54, lat, 1024)
+    Pe = orc.init_params(enc, 201, gain=2.0, bias_std=0.02, mean=mean, scale=std)
+    me = _module(cvb, enc, Pe).eval()
+    B, T = 80, 80
+    x, _, _, _ = orc.synth_batch(B, T, 7)
+    xg = x.cuda()
+    y0 = torch.zeros(B, 1, 2 * lat).cuda()
+    with torch.no_grad():
+        o1, y1, h1 = me(xg, y0, clamp_vae=True, lat_dim=lat)
+        o2, y2, h2 = me(xg, y0, clamp_vae=True, lat_dim=lat)
+        assert torch.equal(o1, o2) and torch.equal(h1, h2) and torch.equal(y1, y2)
+        for j in (0, 37, 79):
+            oj, yj, hj = me(xg[j], y0[j:j + 1], clamp_vae=True, lat_dim=lat)
+            assert _maxabs(oj, o1[j]) < 1e-5 and _maxabs(hj[0, 0], h1[0, j]) < 1e-5
+        ref, _, href = orc.gru_rnn_forward(Pe, enc, x[[3, 64]], torch.zeros(2, 1, 2 * lat), clamp_vae=True, lat_dim=lat)
+    assert _maxabs(o1[[3, 64]], ref) < TOL
+    assert _maxabs(h1[0, [3, 64]], href[0]) < TOL
+    # decode-side wide batch: 256 utterances x 200 frames (two batch tiles of the persistent kernel)
+    Bd, Td = 256, 200
+    xd, _, _, _ = orc.synth_batch(Bd, Td, 8)
+    with torch.no_grad():
+        od, _, hd = me(xd.cuda(), torch.zeros(Bd, 1, 2 * lat).cuda(), clamp_vae=True, lat_dim=lat)
+        refd, _, hrefd = orc.gru_rnn_forward(Pe, enc, xd[[0, 127, 128, 255]], torch.zeros(4, 1, 2 * lat), clamp_vae=True,
+                                             lat_dim=lat)
+    assert _maxabs(od[[0, 127, 128, 255]], refd) < TOL
+    assert torch.isfinite(od).all()

@@ -1,0 +1,180 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares,
+the drop-in module mirrors the reference's surface, integer bookkeeping is bit-exact, and the
+data-parallel sharding + SUM all-reduce reproduces the single-process gradient (gloo, world_size 2)."""
+import json
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gru_vae_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as ge
+    ge.build()
+    import cyclevae_vc_b200
+    return cyclevae_vc_b200
+
+
+def test_abi_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "cyclevae_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cvb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 19
+    from cyclevae_vc_b200 import _lib
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert _lib.lib.cvb_abi_version() == _lib.ABI_VERSION
+    m = re.search(r"#define CVB_ABI_VERSION (\d+)", hdr)
+    assert int(m.group(1)) == _lib.ABI_VERSION
+
+
+def test_workspace_sizing_is_host_arithmetic(pkg):
+    import ctypes as C
+    from cyclevae_vc_b200 import _lib
+    m = pkg.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, scale_out_flag=False, do_prob=0.5)
+    net = _lib.CvbNet()
+    net.in_dim, net.out_dim, net.hidden, net.kernel_size, net.n_conv = 54, 64, 1024, 3, 2
+    B, T = 8, 80
+    fe = _lib.lib.cvb_frontend_ws_floats(C.byref(net), B, T)
+    R = B * (T + 8)
+    assert fe >= R * (54 + 162 + 486) + 3 * (162 * 54 + 486 * 162) + B * T * 486
+    rec = _lib.lib.cvb_recurrent_ws_floats(C.byref(net), B, T, 1, 1)
+    assert rec >= (T + 1) * B * (1024 + 64) + 5 * T * B * 1024
+    assert _lib.lib.cvb_scratch_floats(C.byref(net), B, T, 1) > _lib.lib.cvb_scratch_floats(C.byref(net), B, T, 0)
+
+
+def test_module_surface_matches_reference(pkg, golden_dir):
+    g = np.load(os.path.join(golden_dir, "init.npz"), allow_pickle=False)
+    for tag, kw in (("enc", dict(in_dim=54, out_dim=32, hidden_units=128, scale_out_flag=False, do_prob=0.5)),
+                    ("dec", dict(in_dim=18, out_dim=50, hidden_units=128, scale_in_flag=False, do_prob=0.5))):
+        torch.manual_seed(1)
+        m = pkg.GRU_RNN(**kw)
+        m.apply(pkg.initialize)
+        assert list(m.state_dict().keys()) == [str(k) for k in g[f"{tag}/keys"]]
+        for k, v in m.state_dict().items():
+            want = g[f"{tag}/{k}"]
+            got = np.array([v.double().sum().item(), v.double().abs().sum().item(), float(v.reshape(-1)[v.numel() // 2])])
+            assert np.allclose(got, want, rtol=0, atol=1e-9), (tag, k)
+    m = pkg.GRU_RNN(in_dim=54, out_dim=64, hidden_units=128, scale_out_flag=False, do_prob=0.5)
+    assert (m.in_dim, m.out_dim, m.receptive_field, m.tot_in_dim) == (54, 64, 9, 54 * 9 + 64)
+    # attribute access patterns of the trainer (train_*.py:344-347, 369-376)
+    m.scale_in.weight = torch.nn.Parameter(torch.diag(torch.ones(54)).unsqueeze(2))
+    m.scale_in.bias = torch.nn.Parameter(torch.zeros(54))
+    assert len(list(m.conv.parameters())) == 4 and len(list(m.gru.parameters())) == 4 and len(list(m.out_1.parameters())) == 2
+    import inspect
+    sig = inspect.signature(m.forward)
+    assert list(sig.parameters) == ["x", "y_in", "softmax", "sigmoid", "exp", "h_in", "noise", "res", "res_stdim", "res_endim",
+                                    "do", "clamp_vae", "relu_vae", "lat_dim", "clamp_vae_laplace"]
+    assert list(inspect.signature(pkg.GRU_RNN.__init__).parameters)[1:] == [
+        "in_dim", "out_dim", "hidden_units", "hidden_layers", "kernel_size", "dilation_size", "do_prob", "scale_in_flag",
+        "scale_out_flag", "scale_in_out_flag"]
+
+
+def test_no_cpu_fallback_and_unused_kwargs_raise(pkg):
+    m = pkg.GRU_RNN(in_dim=5, out_dim=4, hidden_units=8)
+    x, y = torch.zeros(2, 3, 5), torch.zeros(2, 1, 4)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(x, y)
+    for kw in (dict(softmax=True), dict(res=True), dict(noise=0.1), dict(relu_vae=True), dict(clamp_vae_laplace=True)):
+        with pytest.raises(NotImplementedError):
+            m(x, y, **kw)
+    with pytest.raises(NotImplementedError):
+        pkg.GRU_RNN(hidden_layers=2)
+    with pytest.raises(NotImplementedError):
+        pkg.TWFSEloss()(torch.zeros(3, 4), torch.zeros(3, 4))   # default L2=True, GV=True is never used by the scripts
+
+
+def test_dropin_shim_imports_as_gru_vae(pkg):
+    sys.path.insert(0, os.path.join(ROOT, "cyclevae_vc_b200", "dropin"))
+    try:
+        sys.modules.pop("gru_vae", None)
+        import gru_vae
+        for n in ("GRU_RNN", "initialize", "TWFSEloss", "sampling_vae_batch", "loss_vae"):
+            assert hasattr(gru_vae, n)
+        assert gru_vae.GRU_RNN is pkg.GRU_RNN
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("gru_vae", None)
+
+
+def test_chunk_schedule_bit_exact(pkg, golden_dir):
+    from cyclevae_vc_b200.cycle import chunk_schedule
+    cases = json.load(open(os.path.join(golden_dir, "chunks.json")))
+    assert cases
+    for c in cases:
+        rows = chunk_schedule(c["flens"], c["bs"], c["spc"])
+        assert len(rows) == len(c["rows"])
+        for got, want in zip(rows, c["rows"]):
+            assert [got[0], got[1], got[2], got[3], got[4], got[5]] == want
+    # default speech-frame index = every frame; same answers as the oracle restatement on ragged inputs
+    for flens, bs in (([5], 80), ([81, 80, 79, 1], 80), ([200, 333, 17], 20)):
+        assert chunk_schedule(flens, bs) == orc.chunk_schedule(flens, bs)
+
+
+def test_shard_utterances(pkg):
+    from cyclevae_vc_b200.cycle import shard_utterances
+    for n, w in ((80, 8), (7, 2), (5, 4), (3, 8)):
+        spans = [shard_utterances(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert [hi - lo for lo, hi in spans] == [len(s) for s in np.array_split(np.arange(n), w)]
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cyclevae_vc_b200.cycle import allreduce_grads, shard_utterances
+    spec = orc.NetSpec(in_dim=6, out_dim=4, hidden_units=12, do_prob=0.0, scale_in=False, scale_out=False)
+    P = {k: v.requires_grad_(True) for k, v in orc.init_params(spec, 9, gain=2.0, bias_std=0.1).items()}
+    g = torch.Generator().manual_seed(0)
+    B, T = 5, 9
+    x, y0 = torch.randn(B, T, 6, generator=g), torch.randn(B, 1, 4, generator=g)
+    tgt = torch.randn(B, T, 4, generator=g)
+    lo, hi = shard_utterances(B, rank, world)
+    o, _, _ = orc.gru_rnn_forward(P, spec, x[lo:hi], y0[lo:hi])
+    loss = sum(orc.mcd_l1(o[j], tgt[lo + j])[1] for j in range(hi - lo))   # per-utterance means, SUMMED (train_*.py:1403)
+    loss.backward()
+    flat = torch.cat([P[k].grad.reshape(-1) for k in sorted(P)])
+    allreduce_grads(flat)
+    if rank == 0:
+        q.put(flat.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_sum_allreduce_equals_single_process(pkg):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    spec = orc.NetSpec(in_dim=6, out_dim=4, hidden_units=12, do_prob=0.0, scale_in=False, scale_out=False)
+    P = {k: v.requires_grad_(True) for k, v in orc.init_params(spec, 9, gain=2.0, bias_std=0.1).items()}
+    g = torch.Generator().manual_seed(0)
+    B, T = 5, 9
+    x, y0 = torch.randn(B, T, 6, generator=g), torch.randn(B, 1, 4, generator=g)
+    tgt = torch.randn(B, T, 4, generator=g)
+    o, _, _ = orc.gru_rnn_forward(P, spec, x, y0)
+    sum(orc.mcd_l1(o[j], tgt[j])[1] for j in range(B)).backward()
+    want = torch.cat([P[k].grad.reshape(-1) for k in sorted(P)]).numpy()
+    assert np.abs(got - want).max() < 1e-5 * max(1.0, np.abs(want).max())
