@@ -27,7 +27,16 @@ void set_error(const char* fmt, ...);
         }                                 \
     } while (0)
 
-#define CVB_LAUNCH_CHECK() CVB_CHECK(cudaGetLastError())
+void count_launch();
+#define CVB_LAUNCH_CHECK()              \
+    do {                                \
+        cvb::count_launch();            \
+        CVB_CHECK(cudaGetLastError());  \
+    } while (0)
+
+// event-pair profiling of selected launches (gemm.cu)
+void prof_begin(cudaStream_t s, int kind);
+void prof_end(cudaStream_t s, int kind);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }

@@ -4,7 +4,9 @@
 #include <cublas_v2.h>
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,6 +20,32 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec {
+    cudaEvent_t a, b;
+    int kind;
+};
+static int g_prof_level = 0;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_open[3];
+void prof_begin(cudaStream_t s, int kind) {
+    if (g_prof_level <= 0 || (kind == CVB_PROF_GEMM && g_prof_level < 2)) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    g_prof_open[kind].push_back(e);
+}
+void prof_end(cudaStream_t s, int kind) {
+    if (g_prof_level <= 0 || (kind == CVB_PROF_GEMM && g_prof_level < 2) || g_prof_open[kind].empty()) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    g_prof.push_back({g_prof_open[kind].back(), e, kind});
+    g_prof_open[kind].pop_back();
+}
 
 static std::mutex g_mu;
 static cublasHandle_t g_handles[64] = {nullptr};
@@ -48,8 +76,10 @@ int gemm_rm(cudaStream_t s, bool transA, bool transB, int M, int N, int K, float
         K = 0;
     }
     // row-major C = op(A) op(B)  <=>  column-major C^T = op(B)^T op(A)^T
+    prof_begin(s, CVB_PROF_GEMM);
     cublasStatus_t st = cublasSgemm(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N,
                                     N, M, K, &alpha, B, ldb, A, lda, &beta, C, ldc);
+    prof_end(s, CVB_PROF_GEMM);
     CVB_REQUIRE(st == CUBLAS_STATUS_SUCCESS, "cublasSgemm failed (%d) M=%d N=%d K=%d lda=%d ldb=%d ldc=%d",
                 (int)st, M, N, K, lda, ldb, ldc);
     return 0;
@@ -79,6 +109,38 @@ int cvb_device_info(int* n_sm, int* max_smem_optin, int* cc_major, int* cc_minor
     if (cc_minor) *cc_minor = d.cc_minor;
     return 0;
 }
+int cvb_profile_enable(int level) {
+    cvb::g_prof_level = level;
+    return 0;
+}
+int cvb_profile_reset(void) {
+    for (auto& r : cvb::g_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    cvb::g_prof.clear();
+    for (auto& v : cvb::g_prof_open) {
+        for (auto e : v) cudaEventDestroy(e);
+        v.clear();
+    }
+    return 0;
+}
+int cvb_profile_summary(int kind, float* total_ms, int* launches) {
+    float tot = 0.f;
+    int n = 0;
+    for (auto& r : cvb::g_prof) {
+        if (r.kind != kind) continue;
+        CVB_CHECK(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CVB_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+        tot += ms;
+        ++n;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return 0;
+}
+long long cvb_launch_count(void) { return cvb::g_launches.load(); }
 int cvb_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* Bm, int ldb, float beta, float* C, int ldc, void* stream) {
     return cvb::gemm_rm((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, alpha, A, lda, Bm, ldb, beta, C, ldc);

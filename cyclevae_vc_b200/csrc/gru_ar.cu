@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(NT, 1) k_gru_fwd(GruFwdArgs a) {
                 const float4* wr = reinterpret_cast<const float4*>(sW + (0 * U + w) * Hp + kc * KC);
                 const float4* wz = reinterpret_cast<const float4*>(sW + (1 * U + w) * Hp + kc * KC);
                 const float4* wn = reinterpret_cast<const float4*>(sW + (2 * U + w) * Hp + kc * KC);
+                // chunk-local accumulators: blocked summation (rounding error ~ sqrt(KC) + sqrt(K/KC) ulp)
+                float cr[4] = {0.f, 0.f, 0.f, 0.f}, cz[4] = {0.f, 0.f, 0.f, 0.f}, cn[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
                 for (int k4 = 0; k4 < KC / 4; ++k4) {
                     float4 fr = wr[k4], fz = wz[k4], fn = wn[k4];
@@ -138,11 +140,17 @@ __global__ void __launch_bounds__(NT, 1) k_gru_fwd(GruFwdArgs a) {
                     for (int i = 0; i < 4; ++i) {
                         if (32 * i < nb) {
                             float4 h4 = *reinterpret_cast<const float4*>(hb + (lane + 32 * i) * KP + 4 * k4);
-                            ar[i] = dot4(fr, h4, ar[i]);
-                            az[i] = dot4(fz, h4, az[i]);
-                            an[i] = dot4(fn, h4, an[i]);
+                            cr[i] = dot4(fr, h4, cr[i]);
+                            cz[i] = dot4(fz, h4, cz[i]);
+                            cn[i] = dot4(fn, h4, cn[i]);
                         }
                     }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ar[i] += cr[i];
+                    az[i] += cz[i];
+                    an[i] += cn[i];
                 }
                 __syncthreads();
             }
@@ -268,6 +276,7 @@ __global__ void __launch_bounds__(NT, 1) k_gru_bwd(GruBwdArgs a) {
                     const float* gb = sG + (kc & 1) * BT * KP;
                     const float4* w0 = reinterpret_cast<const float4*>(sWT + (2 * pair) * K3p + kc * KC);
                     const float4* w1 = reinterpret_cast<const float4*>(sWT + (2 * pair + 1) * K3p + kc * KC);
+                    float ca[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 4
                     for (int k4 = khalf * (KC / 8); k4 < (khalf + 1) * (KC / 8); ++k4) {
                         float4 f0 = w0[k4], f1 = w1[k4];
@@ -275,10 +284,15 @@ __global__ void __launch_bounds__(NT, 1) k_gru_bwd(GruBwdArgs a) {
                         for (int i = 0; i < 4; ++i) {
                             if (32 * i < nb) {
                                 float4 g4 = *reinterpret_cast<const float4*>(gb + (lane + 32 * i) * KP + 4 * k4);
-                                acc[0][i] = dot4(f0, g4, acc[0][i]);
-                                acc[1][i] = dot4(f1, g4, acc[1][i]);
+                                ca[0][i] = dot4(f0, g4, ca[0][i]);
+                                ca[1][i] = dot4(f1, g4, ca[1][i]);
                             }
                         }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[0][i] += ca[0][i];
+                        acc[1][i] += ca[1][i];
                     }
                     __syncthreads();
                 }
@@ -375,7 +389,7 @@ static size_t bwd_smem_bytes(int H, int out) {
 int gru_exact_grid(int H) { return ceil_div(H, U); }
 
 template <typename Args>
-static int launch_coop(void (*kern)(Args), Args& a, int grid, size_t smem, cudaStream_t s, const char* name) {
+static int launch_coop(void (*kern)(Args), Args& a, int grid, size_t smem, cudaStream_t s, const char* name, int prof_kind) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
     CVB_REQUIRE(smem <= (size_t)di.max_smem_optin,
@@ -385,17 +399,20 @@ static int launch_coop(void (*kern)(Args), Args& a, int grid, size_t smem, cudaS
     CVB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CVB_CHECK(cudaMemsetAsync(a.bar, 0, 64, s));
     void* params[] = {&a};
+    prof_begin(s, prof_kind);
     CVB_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(NT), params, smem, s));
+    prof_end(s, prof_kind);
+    count_launch();
     return 0;
 }
 
 int gru_ar_fwd_exact(GruFwdArgs& a, cudaStream_t s) {
     if (a.T <= 0 || a.B <= 0) return 0;
-    return launch_coop(k_gru_fwd, a, gru_exact_grid(a.H), fwd_smem_bytes(a.H, a.out), s, "gru_ar_fwd");
+    return launch_coop(k_gru_fwd, a, gru_exact_grid(a.H), fwd_smem_bytes(a.H, a.out), s, "gru_ar_fwd", CVB_PROF_GRU_FWD);
 }
 int gru_ar_bwd_exact(GruBwdArgs& a, cudaStream_t s) {
     if (a.T <= 0 || a.B <= 0) return 0;
-    return launch_coop(k_gru_bwd, a, gru_exact_grid(a.H), bwd_smem_bytes(a.H, a.out), s, "gru_ar_bwd");
+    return launch_coop(k_gru_bwd, a, gru_exact_grid(a.H), bwd_smem_bytes(a.H, a.out), s, "gru_ar_bwd", CVB_PROF_GRU_BWD);
 }
 
 }  // namespace cvb

@@ -47,20 +47,13 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
-# counter-based RNG bookkeeping: (seed, offset) pairs handed to the Philox kernels.  The seed follows
-# torch.manual_seed; offsets never repeat within a seed.
+# counter-based RNG bookkeeping: every device draw gets a fresh 62-bit Philox key taken from torch's
+# CPU generator (the generator the reference's sampling_vae_batch consumes, gru_vae.py:91), so
+# torch.manual_seed() makes device noise and dropout reproducible; no device sync is involved.
 class _Rng:
-    seed: Optional[int] = None
-    offset: int = 0
-
-    @classmethod
-    def take(cls, n_counters: int):
-        s = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        if cls.seed != s:
-            cls.seed, cls.offset = s, 0
-        off = cls.offset
-        cls.offset += int(n_counters) + 1
-        return s, off
+    @staticmethod
+    def take(n_counters: int):
+        return int(torch.randint(0, 2 ** 62, (1,)).item()), 0
 
 
 def initialize(m):
@@ -108,9 +101,7 @@ class _GruRnnFn(torch.autograd.Function):
         B, T, _ = x.shape
         dev = x.device
         net = mod._net_struct(params)
-        needs_grad = torch.is_grad_enabled() and (x.requires_grad or y_in.requires_grad or
-                                                  (h_in is not None and h_in.requires_grad) or
-                                                  any(p.requires_grad for p in params))
+        needs_grad = any(ctx.needs_input_grad)   # False under torch.no_grad()
         training = 1 if needs_grad else 0
         netp = C.byref(net)
         fe_n = lib.cvb_frontend_ws_floats(netp, B, T)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 3
+#define CVB_ABI_VERSION 4
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -155,6 +155,19 @@ int cvb_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, float* o
 int cvb_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                   void* stream);
+
+/* ---- measurement hooks (bench.py's roofline object) -------------------------------------------
+ * When enabled, CUDA events are recorded on the launching stream around every launch of the
+ * persistent recurrence kernels (kind 0 = forward, 1 = BPTT) and, at level 2, around every dense
+ * product (kind 2).  cvb_profile_summary synchronises those events and returns total ms / launches. */
+#define CVB_PROF_GRU_FWD 0
+#define CVB_PROF_GRU_BWD 1
+#define CVB_PROF_GEMM 2
+int cvb_profile_enable(int level);
+int cvb_profile_reset(void);
+int cvb_profile_summary(int kind, float* total_ms, int* launches);
+/* number of kernels of THIS library launched since process start (library GEMM calls excluded) */
+long long cvb_launch_count(void);
 
 /* plain fp32 GEMM used by the path (row-major; C = alpha*op(A)*op(B) + beta*C); exported so the
  * tests can check it in isolation. */
