@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 4
+#define CVB_ABI_VERSION 5
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -168,6 +168,11 @@ int cvb_profile_reset(void);
 int cvb_profile_summary(int kind, float* total_ms, int* launches);
 /* number of kernels of THIS library launched since process start (library GEMM calls excluded) */
 long long cvb_launch_count(void);
+
+/* self-test of the tcgen05 / TMEM / bulk-copy building blocks: D[128,N] = A[128,K] * B[N,K]^T with bf16
+ * operands (modes 0/1: A,B fp32 row-major, arranged in-kernel; mode 2: A,B bf16 pre-arranged in the
+ * K-major core-matrix order [row/8][k/8][8][8] and fetched with cp.async.bulk).  tests only. */
+int cvb_selftest_umma(int mode, int N, int K, const void* A, const void* B, float* D, void* stream);
 
 /* plain fp32 GEMM used by the path (row-major; C = alpha*op(A)*op(B) + beta*C); exported so the
  * tests can check it in isolation. */
