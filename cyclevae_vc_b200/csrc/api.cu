@@ -1,4 +1,6 @@
 // GRU_RNN.forward / backward composition behind the C ABI (include/cyclevae_b200.h).
+#include <stdlib.h>
+
 #include "gru_ar.cuh"
 
 namespace cvb {
@@ -38,7 +40,7 @@ static RecLayout rec_layout(const cvb_net* net, int B, int T, bool training, boo
 }
 
 struct FwdScratch {
-    size_t gx, part, bar, total;
+    size_t gx, part, bar, tc, total;
 };
 static FwdScratch fwd_scratch(const cvb_net* net, int B, int T) {
     FwdScratch S;
@@ -47,8 +49,15 @@ static FwdScratch fwd_scratch(const cvb_net* net, int B, int T) {
     S.gx = off; off += r4(TB * 3 * H);
     S.part = off; off += r4((size_t)gru_exact_grid(net->hidden) * B * out);
     S.bar = off; off += 16;
+    S.tc = off;
+    if (gru_tc_shape_ok(B, net->hidden, net->out_dim)) off += r4(gru_tc_scratch_floats(B, net->hidden));
     S.total = off;
     return S;
+}
+// CVB_RECURRENCE=exact forces the fp32-FMA kernels; default = tensor-core variant where the shape allows
+static bool want_tc() {
+    const char* e = getenv("CVB_RECURRENCE");
+    return !(e && (e[0] == 'e' || e[0] == 'E'));
 }
 struct BwdScratch {
     size_t dy_tot, dgi, dghn, gxch, dhc, part, bar, dxc, fe, dtrj, total;
@@ -213,7 +222,15 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     a.T = T;
     a.H = H;
     a.out = out;
-    if (int rc = gru_ar_fwd_exact(a, s)) return rc;
+    {
+        DeviceInfo di;
+        if (int rc = get_device_info(&di)) return rc;
+        if (want_tc() && gru_tc_supported(B, H, out, di)) {
+            if (int rc = gru_ar_fwd_tc(a, scratch + FS.tc, s)) return rc;
+        } else {
+            if (int rc = gru_ar_fwd_exact(a, s)) return rc;
+        }
+    }
     size_t smem = head_mode == CVB_HEAD_SCALE_OUT ? (size_t)(out * out + out) * sizeof(float) : 0;
     CVB_REQUIRE(smem <= 48 * 1024, "scale_out matrix too large (out_dim=%d)", out);
     k_head_fwd<<<grid1d(TB * out), 256, smem, s>>>(B, T, out, head_mode, lat_dim, ys + (size_t)B * out, net->scale_out_w,

@@ -43,4 +43,10 @@ int gru_exact_grid(int H);
 int gru_ar_fwd_exact(GruFwdArgs& a, cudaStream_t s);
 int gru_ar_bwd_exact(GruBwdArgs& a, cudaStream_t s);
 
+// tensor-core (tcgen05) variant, gru_tc.cu
+bool gru_tc_shape_ok(int B, int H, int out);               // host-only shape test (no device query)
+bool gru_tc_supported(int B, int H, int out, const DeviceInfo& di);
+size_t gru_tc_scratch_floats(int B, int H);
+int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s);
+
 }  // namespace cvb
