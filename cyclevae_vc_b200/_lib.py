@@ -68,6 +68,8 @@ PROTOTYPES = {
     "cvb_profile_summary": (_i, [_i, C.POINTER(C.c_float), C.POINTER(_i)]),
     "cvb_launch_count": (C.c_longlong, []),
     "cvb_selftest_umma": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cvb_bench_ingest": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "cvb_bench_allgather": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cvb_gemm": (_i, [_i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _f, _vp, _i, _vp]),
 }
 

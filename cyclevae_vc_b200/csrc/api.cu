@@ -60,7 +60,7 @@ static bool want_tc() {
     return !(e && (e[0] == 'e' || e[0] == 'E'));
 }
 struct BwdScratch {
-    size_t dy_tot, dgi, dghn, gxch, dhc, part, bar, dxc, fe, dtrj, total;
+    size_t dy_tot, dgi, dghn, gxch, dhc, part, bar, dxc, fe, dtrj, tc, total;
 };
 static BwdScratch bwd_scratch(const cvb_net* net, int B, int T) {
     BwdScratch S;
@@ -76,6 +76,8 @@ static BwdScratch bwd_scratch(const cvb_net* net, int B, int T) {
     S.dxc = off; off += r4(TB * C);
     S.fe = off; off += r4(frontend_bwd_scratch_floats(net, B, T));
     S.dtrj = off; off += r4(TB * out);
+    S.tc = off;
+    if (gru_tc_bwd_shape_ok(B, net->hidden, net->out_dim)) off += r4(gru_tc_bwd_scratch_floats(B, net->hidden));
     S.total = off;
     return S;
 }
@@ -297,7 +299,15 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
     a.T = T;
     a.H = H;
     a.out = out;
-    if (int rc = gru_ar_bwd_exact(a, s)) return rc;
+    {
+        DeviceInfo di;
+        if (int rc = get_device_info(&di)) return rc;
+        if (want_tc() && gru_tc_bwd_supported(B, H, out, di)) {
+            if (int rc = gru_ar_bwd_tc(a, scratch + BS.tc, s)) return rc;
+        } else {
+            if (int rc = gru_ar_bwd_exact(a, s)) return rc;
+        }
+    }
     if (dy_in) CVB_CHECK(cudaMemcpyAsync(dy_in, dy_tot, (size_t)B * out * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (dh_in) CVB_CHECK(cudaMemcpyAsync(dh_in, dhc, (size_t)B * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
 

@@ -49,4 +49,10 @@ bool gru_tc_supported(int B, int H, int out, const DeviceInfo& di);
 size_t gru_tc_scratch_floats(int B, int H);
 int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s);
 
+// tensor-core BPTT over thread-block clusters, gru_tc_bwd.cu
+bool gru_tc_bwd_shape_ok(int B, int H, int out);
+bool gru_tc_bwd_supported(int B, int H, int out, const DeviceInfo& di);
+size_t gru_tc_bwd_scratch_floats(int B, int H);
+int gru_ar_bwd_tc(GruBwdArgs& b, float* tc_scratch, cudaStream_t s);
+
 }  // namespace cvb

@@ -62,10 +62,6 @@ struct GruTcArgs {
     int smem_max;
 };
 
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
     while (ld_acquire_gpu(ctr) < target) {
     }
@@ -99,7 +95,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         int g = n >> 3, uu = n & 7;
         float w = (g < 3) ? f.Whh[(size_t)(g * H + u0 + uu) * H + k] : 0.f;
         uint16_t hi, lo;
-        split_bf16(w, hi, lo);
+        split_f16(w, hi, lo);
         uint32_t off = (uint32_t)(k / TC_KC) * 4096u + (uint32_t)(n >> 3) * 1024u + (uint32_t)((k % TC_KC) >> 3) * 128u + (uint32_t)(n & 7) * 16u +
                        (uint32_t)(k & 7) * 2u;
         *reinterpret_cast<uint16_t*>(sWh + off) = hi;
@@ -111,7 +107,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         int row = (g == 0) ? u0 + uu : (g == 1) ? H + u0 + uu : (g == 3) ? 2 * H + u0 + uu : -1;   // block 2 (W_hn h) gets no y term
         float w = (row >= 0 && k < out) ? f.Wy[(size_t)row * f.ldwy + k] : 0.f;
         uint16_t hi, lo;
-        split_bf16(w, hi, lo);
+        split_f16(w, hi, lo);
         uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
         *reinterpret_cast<uint16_t*>(sWy + off) = hi;
         *reinterpret_cast<uint16_t*>(sWy + 4096 + off) = lo;
@@ -166,7 +162,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     } else if (warp == 1) {
         // ================= MMA issuer ================================================================
         if (lane == 0) {
-            const uint32_t idesc = idesc_bf16_f32(128, TC_N);
+            const uint32_t idesc = idesc_f16_f32(128, TC_N);
             const uint32_t half = L.MB * 1024u;
             uint32_t it = 0;
             for (int t = 0; t < T; ++t) {
@@ -207,8 +203,8 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint16_t h0, l0, h1, l1;
-                split_bf16(hreg[2 * j], h0, l0);
-                split_bf16(hreg[2 * j + 1], h1, l1);
+                split_f16(hreg[2 * j], h0, l0);
+                split_f16(hreg[2 * j + 1], h1, l1);
                 phi[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                 plo[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
@@ -286,8 +282,8 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint16_t h0, l0, h1, l1;
-                    split_bf16(hreg[2 * j], h0, l0);
-                    split_bf16(hreg[2 * j + 1], h1, l1);
+                    split_f16(hreg[2 * j], h0, l0);
+                    split_f16(hreg[2 * j + 1], h1, l1);
                     phi[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                     plo[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                 }
@@ -367,7 +363,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                     const int bb = q / out, o = q - bb * out;
                     if (round > 0) ydst[q] = yv;
                     uint16_t hi, lo;
-                    split_bf16(yv, hi, lo);
+                    split_f16(yv, hi, lo);
                     size_t off = (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8 + (size_t)(o & 7);
                     yx[off] = hi;
                     yx[yx_part + off] = lo;

@@ -174,6 +174,17 @@ long long cvb_launch_count(void);
  * K-major core-matrix order [row/8][k/8][8][8] and fetched with cp.async.bulk).  tests only. */
 int cvb_selftest_umma(int mode, int N, int K, const void* A, const void* B, float* D, void* stream);
 
+/* micro-benchmark of the L2 -> shared-memory ingest paths of the persistent kernels (profiling hook):
+ * mode 0 = cp.async.bulk, mode 1 = ld.global.v4 + st.shared; out_cycles[grid] = SM cycles for `iters` rounds
+ * of `inflight` x `bytes`.  tools/bench_ingest.py. */
+int cvb_bench_ingest(int grid, int mode, int bytes, int inflight, int shared_src, int iters, const void* src,
+                     long long* out_cycles, void* stream);
+
+/* same for the all-gather pattern (every CTA rewrites a slice each round, global barrier, every CTA ingests all);
+ * out_cycles[2*cta] = ingest cycles, [2*cta+1] = write+fence+barrier cycles. */
+int cvb_bench_allgather(int grid, int mode, int wmode, int bytes, int inflight, int iters, void* buf, unsigned* ctr,
+                        long long* out_cycles, void* stream);
+
 /* plain fp32 GEMM used by the path (row-major; C = alpha*op(A)*op(B) + beta*C); exported so the
  * tests can check it in isolation. */
 int cvb_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,

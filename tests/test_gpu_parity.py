@@ -422,3 +422,57 @@ def test_full_size_properties(cvb):
                                              lat_dim=lat)
     assert _maxabs(od[[0, 127, 128, 255]], refd) < TOL
     assert torch.isfinite(od).all()
+
+
+@pytest.mark.parametrize("net,B", [("enc", 80), ("dec", 80), ("dec", 5), ("enc", 128)])
+def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B):
+    """The tcgen05 recurrence kernels (forward: fp16 hi/lo split; BPTT: bf16 hi/lo split over thread-block
+    clusters) against the fp32-FMA persistent kernels (CVB_RECURRENCE=exact, themselves checked against the
+    oracle above) at the BASELINE.json chunk size hu1024 x T=80, dropout masks, carried h_in / y_in,
+    gradients w.r.t. inputs, carried state and every parameter."""
+    lat, stdim, T = 32, 4, 80
+    mean, std = orc.synth_stats(50)
+    if net == "enc":
+        spec = orc.encoder_spec(54, lat, 1024)
+        P = orc.init_params(spec, 201, gain=1.5, bias_std=0.02, mean=mean, scale=std)
+    else:
+        spec = orc.decoder_spec(lat, 2, 50, 1024)
+        P = orc.init_params(spec, 202, gain=1.5, bias_std=0.02, mean=mean[stdim:], scale=std[stdim:])
+    m = _module(cvb, spec, P).train()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, spec.in_dim, generator=g).cuda()
+    y0 = (0.3 * torch.randn(B, 1, spec.out_dim, generator=g)).cuda()
+    h0 = (0.5 * torch.randn(1, B, 1024, generator=g)).cuda()
+    mc = ((torch.rand(B, T, spec.conv_dim, generator=g) >= 0.5).float() * 2).cuda()
+    mg = ((torch.rand(B, T, 1024, generator=g) >= 0.5).float() * 2).cuda()
+    w_o = torch.randn(B, T, spec.out_dim, generator=g).cuda()
+    w_y = torch.randn(B, 1, spec.out_dim, generator=g).cuda()
+    w_h = torch.randn(1, B, 1024, generator=g).cuda()
+
+    def run(mode):
+        if mode:
+            os.environ["CVB_RECURRENCE"] = mode
+        else:
+            os.environ.pop("CVB_RECURRENCE", None)
+        try:
+            xs, ys, hs = (t.clone().requires_grad_(True) for t in (x, y0, h0))
+            for p in m.parameters():
+                p.grad = None
+            m.inject_dropout_masks(mc, mg)
+            o, yl, hl = m(xs, ys, h_in=hs, do=True, clamp_vae=(net == "enc"), lat_dim=lat)
+            ((o * w_o).sum() + (yl * w_y).sum() + (hl * w_h).sum()).backward()
+            torch.cuda.synchronize()
+            grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            return (o.detach(), yl.detach(), hl.detach()), (xs.grad, ys.grad, hs.grad), grads
+        finally:
+            os.environ.pop("CVB_RECURRENCE", None)
+
+    out_e, gin_e, gp_e = run("exact")
+    out_t, gin_t, gp_t = run(None)
+    for a, b in zip(out_t, out_e):
+        assert _maxabs(a, b) < 2e-5 * max(1.0, float(b.abs().max()))
+    for a, b in zip(gin_t, gin_e):
+        assert _maxabs(a, b) < 1e-4 * max(1e-3, float(b.abs().max())), (float(b.abs().max()))
+    assert set(gp_t) == set(gp_e)
+    for k in gp_e:
+        assert _maxabs(gp_t[k], gp_e[k]) < 1e-4 * max(1e-3, float(gp_e[k].abs().max())), k

@@ -1,0 +1,68 @@
+"""Phase timeline of the persistent tcgen05 recurrence kernels (profiling hook, GPU box only).
+
+CVB_TRACE_FILE makes gru_ar_{fwd,bwd}_tc record clock64 stamps of CTA 0 per step; this script runs one
+ENC forward+backward at the bench shape and prints, per event, the mean offset (in SM cycles and us at the
+sampled clock) from the finaliser's start-of-step stamp, plus the mean step period.
+    python tools/trace_recurrence.py [B] [T]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cyclevae_vc_b200 as cvb  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 80
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 80
+MHZ = 1965.0
+
+NAMES_BWD = {0: "fin: step start", 1: "fin: accum_full seen", 2: "fin: exchange stores+arrive issued", 3: "fin: inbox complete",
+             4: "fin: partial sums added", 5: "fin: q ready (bar5)", 6: "fin: gate math + sG", 7: "fin: stores+partial issued",
+             8: "fin: fences done", 9: "fin: ctrA arrive", 14: "prod: ctrA seen", 15: "prod: last chunk slot free",
+             16: "mma: first chunk full", 17: "mma: last chunk full", 20: "aux: ctrA seen", 21: "aux: partials staged",
+             22: "aux: dy reduced, ctrB arrive", 23: "aux: ctrB seen", 24: "aux: q done", 25: "aux: sG ready (bar6)",
+             26: "aux: partial half done"}
+NAMES_BWD.update({32 + i: f"prod: chunk {i} slot free, issuing" for i in range(8)})
+NAMES_BWD.update({40 + i: f"mma: chunk {i} full" for i in range(8)})
+
+
+def run(tag):
+    enc = cvb.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, do_prob=0.5, scale_out_flag=False).cuda().train()
+    enc.apply(cvb.initialize)
+    x = torch.randn(B, T, 54, device="cuda", requires_grad=True)
+    y0 = torch.zeros(B, 1, 64, device="cuda")
+    for i in range(3):
+        path = os.path.join(ROOT, "gpurun_out", f"trace_{tag}_{i}.bin")
+        os.environ["CVB_TRACE_FILE"] = path
+        o, y, h = enc(x, y0, do=True, clamp_vae=True, lat_dim=32)
+        o.square().sum().backward()
+        torch.cuda.synchronize()
+    os.environ.pop("CVB_TRACE_FILE", None)
+    return path
+
+
+def report(path, names):
+    tr = np.fromfile(path, dtype=np.int64).reshape(-1, 64)
+    n_it = tr.shape[0]
+    base = tr[:, 0].astype(np.float64)
+    sel = slice(5, n_it - 2)
+    period = np.diff(base[sel]).mean()
+    print(f"{path}: {n_it} iterations, mean step period {period:.0f} cycles = {period / MHZ:.2f} us")
+    rows = []
+    for ev in range(64):
+        v = tr[sel, ev].astype(np.float64)
+        if (v == 0).all():
+            continue
+        off = (v - base[sel])
+        rows.append((off.mean(), ev))
+    for off, ev in sorted(rows):
+        print(f"  ev{ev:2d} {names.get(ev, '?'):40s} {off:9.0f} cyc  {off / MHZ:7.2f} us")
+
+
+if __name__ == "__main__":
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    p = run("bwd")
+    report(p, NAMES_BWD)
