@@ -70,6 +70,7 @@ PROTOTYPES = {
     "cvb_selftest_umma": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "cvb_bench_ingest": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "cvb_bench_allgather": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cvb_gemm_tc": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
     "cvb_gemm": (_i, [_i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _f, _vp, _i, _vp]),
 }
 

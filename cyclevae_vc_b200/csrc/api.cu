@@ -316,29 +316,29 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
     const float* xc = fe_ws + frontend_xc_offset(net, B, T);
     if (gr) {
         if (gr->w_hh) {
-            if (int rc = gemm_rm(s, true, false, 2 * H, H, iTB, 1.f, dgi, 3 * H, hs, H, beta, gr->w_hh, H)) return rc;
-            if (int rc = gemm_rm(s, true, false, H, H, iTB, 1.f, dghn, H, hs, H, beta, gr->w_hh + (size_t)2 * H * H, H)) return rc;
+            if (int rc = gemm_rm(s, true, false, 2 * H, H, iTB, 1.f, dgi, 3 * H, hs, H, beta, gr->w_hh, H, true)) return rc;
+            if (int rc = gemm_rm(s, true, false, H, H, iTB, 1.f, dghn, H, hs, H, beta, gr->w_hh + (size_t)2 * H * H, H, true)) return rc;
         }
         if (gr->b_hh) {
             if (int rc = colsum(s, dgi, iTB, 2 * H, 3 * H, gr->b_hh, acc)) return rc;
             if (int rc = colsum(s, dghn, iTB, H, H, gr->b_hh + 2 * H, acc)) return rc;
         }
         if (gr->w_ih) {
-            if (int rc = gemm_rm(s, true, false, 3 * H, C, iTB, 1.f, dgi, 3 * H, xc, C, beta, gr->w_ih, TI)) return rc;
-            if (int rc = gemm_rm(s, true, false, 3 * H, out, iTB, 1.f, dgi, 3 * H, ys, out, beta, gr->w_ih + C, TI)) return rc;
+            if (int rc = gemm_rm(s, true, false, 3 * H, C, iTB, 1.f, dgi, 3 * H, xc, C, beta, gr->w_ih, TI, true)) return rc;
+            if (int rc = gemm_rm(s, true, false, 3 * H, out, iTB, 1.f, dgi, 3 * H, ys, out, beta, gr->w_ih + C, TI, true)) return rc;
         }
         if (gr->b_ih)
             if (int rc = colsum(s, dgi, iTB, 3 * H, 3 * H, gr->b_ih, acc)) return rc;
         const float* o_tm = mask_gru_tm ? rec_ws + RL.o : hs + (size_t)B * H;
         const float* dy1 = dy_tot + (size_t)B * out;
         if (gr->out_w)
-            if (int rc = gemm_rm(s, true, false, out, H, iTB, 1.f, dy1, out, o_tm, H, beta, gr->out_w, H)) return rc;
+            if (int rc = gemm_rm(s, true, false, out, H, iTB, 1.f, dy1, out, o_tm, H, beta, gr->out_w, H, true)) return rc;
         if (gr->out_b)
             if (int rc = colsum(s, dy1, iTB, out, out, gr->out_b, acc)) return rc;
         if (want_so) {
             if (gr->scale_out_w)
                 if (int rc = gemm_rm(s, true, false, out, out, iTB, 1.f, dtrj_tm, out, ys + (size_t)B * out, out, beta,
-                                     gr->scale_out_w, out))
+                                     gr->scale_out_w, out, true))
                     return rc;
             if (gr->scale_out_b)
                 if (int rc = colsum(s, dtrj_tm, iTB, out, out, gr->scale_out_b, acc)) return rc;
@@ -351,7 +351,7 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
     }
     if (fe_needed) {
         float* dxc = scratch + BS.dxc;
-        if (int rc = gemm_rm(s, false, false, iTB, C, 3 * H, 1.f, dgi, 3 * H, net->w_ih, TI, 0.f, dxc, C)) return rc;
+        if (int rc = gemm_rm(s, false, false, iTB, C, 3 * H, 1.f, dgi, 3 * H, net->w_ih, TI, 0.f, dxc, C, true)) return rc;
         if (int rc = frontend_bwd(net, B, T, x_bm, mask_conv_tm, fe_ws, dxc, scratch + BS.fe, dx_bm, gr, s)) return rc;
     }
     return 0;

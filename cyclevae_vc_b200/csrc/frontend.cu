@@ -228,11 +228,11 @@ int frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const floa
             long shift = (long)(j - half) * d;
             if (want_w)
                 if (int rc = gemm_rm(s, true, false, co, ci, (int)rows, 1.f, dout, co, in + (size_t)((long)m + shift) * ci, ci,
-                                     0.f, dWr + (size_t)j * co * ci, ci))
+                                     0.f, dWr + (size_t)j * co * ci, ci, true))
                     return rc;
             if (need_din)
                 if (int rc = gemm_rm(s, false, false, (int)rows, ci, co, 1.f, dout, co, Wr + (size_t)j * co * ci, ci, 1.f,
-                                     din + (size_t)((long)m + shift) * ci, ci))
+                                     din + (size_t)((long)m + shift) * ci, ci, true))
                     return rc;
         }
         if (want_w) {
@@ -256,7 +256,7 @@ int frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const floa
             bool first = (b == 0) && !acc;
             if (gr->scale_in_w)
                 if (int rc = gemm_rm(s, true, false, in_dim, in_dim, T, 1.f, dxh, in_dim, x_bm + (size_t)b * T * in_dim, in_dim,
-                                     first ? 0.f : 1.f, gr->scale_in_w, in_dim))
+                                     first ? 0.f : 1.f, gr->scale_in_w, in_dim, true))
                     return rc;
             if (gr->scale_in_b)
                 if (int rc = colsum(s, dxh, T, in_dim, in_dim, gr->scale_in_b, !first)) return rc;

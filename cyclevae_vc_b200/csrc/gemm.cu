@@ -3,6 +3,7 @@
 // parity bar is 1e-4 after 800 recurrent steps).
 #include <cublas_v2.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -65,9 +66,20 @@ static int get_handle(cublasHandle_t* out) {
     return 0;
 }
 
+static bool want_tc_gemm() {
+    const char* e = getenv("CVB_GEMM");
+    return !(e && (e[0] == 'c' || e[0] == 'C'));
+}
+
 int gemm_rm(cudaStream_t s, bool transA, bool transB, int M, int N, int K, float alpha,
-            const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc) {
+            const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc, bool grad) {
     if (M <= 0 || N <= 0) return 0;
+    if (alpha == 1.f && (beta == 0.f || beta == 1.f) && gemm_tc_eligible(M, N, K) && want_tc_gemm()) {
+        prof_begin(s, CVB_PROF_GEMM);
+        int rc = gemm_tc(s, transA, transB, M, N, K, A, lda, B, ldb, beta == 1.f, nullptr, C, ldc, !grad);
+        prof_end(s, CVB_PROF_GEMM);
+        return rc;
+    }
     cublasHandle_t h;
     if (int rc = get_handle(&h)) return rc;
     cublasSetStream(h, s);
@@ -141,6 +153,14 @@ int cvb_profile_summary(int kind, float* total_ms, int* launches) {
     return 0;
 }
 long long cvb_launch_count(void) { return cvb::g_launches.load(); }
+int cvb_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb, int beta1,
+                const float* bias, float* C, int ldc, int f16, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0) {
+        cvb::set_error("cvb_gemm_tc: empty product (M=%d N=%d K=%d)", M, N, K);
+        return 2;
+    }
+    return cvb::gemm_tc((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, A, lda, Bm, ldb, beta1 != 0, bias, C, ldc, f16 != 0);
+}
 int cvb_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* Bm, int ldb, float beta, float* C, int ldc, void* stream) {
     return cvb::gemm_rm((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, alpha, A, lda, Bm, ldb, beta, C, ldc);

@@ -1,22 +1,24 @@
 // Tensor-core (tcgen05) BPTT of the autoregressive GRU (the reverse of
 // gru_vae.py:364-399), one persistent cooperative launch for all T steps.
 //
-// 2-D work split over thread-block clusters of S CTAs (S = 8, or 4): cluster i owns the block of
-// 8*S hidden units [8*S*i, 8*S*(i+1)); CTA j of the cluster owns the K-slice [j*3H/S, (j+1)*3H/S) of the
-// contraction  dh[b,u] += sum_k dgh_{t+1}[b,k] W_hh[k,u]  for ALL units of the block, and FINALISES the
-// 8 units [8*S*i + 8j, +8).  W_hh^T of (block x K-slice) stays in shared memory for the whole sequence as
-// bf16 hi+lo (x = hi + lo + O(2^-17 x); three MMAs hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM), so a
-// CTA ingests only 1/S of the all-gathered dgh_{t+1} per step (the 1-D split made every CTA read all of it).
-// The S partial accumulators of a unit meet in the finaliser's shared memory through DSMEM stores
-// (st.shared::cluster + cluster-scope mbarrier) and are summed in fixed order (deterministic).
+// 2-D work split over thread-block clusters of S CTAs (S = 8 where 16 such clusters are co-resident, else 4):
+// cluster i owns the block of 8*S hidden units [8*S*i, 8*S*(i+1)); CTA j of the cluster owns the K-slice
+// [j*3H/S, (j+1)*3H/S) of the contraction  dh[b,u] += sum_k dgh_{t+1}[b,k] W_hh[k,u]  for ALL units of the
+// block, and FINALISES the 8 units [8*S*i + 8j, +8).  W_hh^T of (block x K-slice) stays in shared memory for the
+// whole sequence as bf16 hi+lo (x = hi + lo + O(2^-17 x); three MMAs hi*hi + lo*hi + hi*lo, fp32 accumulate in
+// TMEM), so a CTA ingests only 1/S of the all-gathered dgh_{t+1} per step.  The S partial accumulators of a unit
+// meet in the finaliser's shared memory through bulk DSMEM copies (cp.async.bulk.shared::cluster, complete_tx on
+// the receiver's mbarrier) and are summed in fixed order (deterministic).
 //
-// The y feedback (dy_t = dY_t + dgi_{t+1} W_y, then dh_t += (dy_t W_o) * m_t) is a reduction over all of 3H:
-// each finaliser writes its partial [B,out], the per-pair sums are formed in fixed order by the "aux" warps
-// of the CTA that owns the pair, and q = dy_t W_o[:, own units] is recomputed by every CTA's aux warps.
+// The y feedback (dy_t = dY_t + dgi_{t+1} W_y, then dh_t += (dy_t W_o) * m_t) is a reduction over all of 3H.  Both
+// of its dense pieces run on the tensor core as well: the finaliser stages dgi of its 8 units as a [128 x 32] bf16
+// operand and one MMA chain forms its partial [B,out] (accumulator D3); the per-pair sums over the CTAs are formed
+// in fixed order by the "aux" warps of the CTA that owns the pair and published in operand order; every CTA then
+// pulls dy_t through its ring and a second MMA chain forms q = dy_t W_o[:, own units] (accumulator D2).
 //
-// Roles (384 threads): w0 bulk-copy producer (lane 0), w1 MMA issuer (lane 0), w2 TMEM allocator,
-// w4-7 exchange + finalise (TMEM lane == batch row), w8-11 aux (dy reduction, q, half of the partial).
-// Grid-wide ordering is two monotonic counters: A (dgh_t / partials published), B (dy_t complete).
+// Roles (384 threads): w0 bulk-copy producer, w1 MMA issuer, w2 TMEM allocator, w4-7 exchange + finalise
+// (TMEM lane == batch row), w8-11 aux (dy reduction, drain of D3).  Grid-wide ordering is two monotonic
+// counters: A (dgh_t / partials published), B (dy_t published).
 #include <stdlib.h>
 
 #include "gru_ar.cuh"
@@ -26,12 +28,19 @@ namespace cvb {
 using namespace umma;
 
 constexpr int TB_NT = 384;
-constexpr int TB_KC = 64;   // K per ring stage
+constexpr int TB_KC = 64;        // K per ring stage
+// TMEM columns.  Every B operand is stored [hi rows | lo rows], so ONE MMA with N = 2 x rows forms A_hi*B_hi (first
+// half of the columns) and A_hi*B_lo (second half); a second MMA with N = rows adds A_lo*B_hi to the first half.
+// The halves are added in fp32 registers by whoever drains the accumulator (2 instead of 3 MMAs per K step, and
+// the small correction term never shares an accumulator chain with the large one).
+constexpr uint32_t TB_COL_Q = 128;     // D2 (q): 2 x 16 columns
+constexpr uint32_t TB_COL_DUMMY = 160; // keep-alive scratch, 16 columns
+constexpr uint32_t TB_COL_P = 256;     // D3 (partial of the y feedback): 2 x 64 columns
 
 struct TbLayout {
     int MB, S, Ublk, nch, NS;
     uint32_t half, stage_bytes, w_part_bytes, slot_bytes;
-    uint32_t off_ring, off_w, off_inbox, off_stage, off_wo, off_wy, off_aux, off_bar, total;
+    uint32_t off_ring, off_w, off_inbox, off_stage, off_a2, off_b2, off_b3, off_aux, off_bar, total;
 };
 
 __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int out, int smem_max) {
@@ -46,11 +55,8 @@ __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int ou
     L.slot_bytes = (uint32_t)L.MB * 8u * 32u;
     const uint32_t inbox = (uint32_t)S * L.slot_bytes;
     const int Q = (B * out + G - 1) / G;
-    uint32_t aux = (uint32_t)(G * Q) * 4u;                      // staging of the partials being reduced
-    const uint32_t aux2 = 128u * 24u * 4u + 128u * 8u * 4u;     // sG [128][24] + sQ [128][8]
-    if (aux < aux2) aux = aux2;
-    aux = (aux + 127u) & ~127u;
-    const uint32_t fixed = 2u * L.w_part_bytes + 2u * inbox + 64u * 8u * 4u + 24u * 64u * 4u + aux + 256u;
+    const uint32_t aux = (((uint32_t)(G * (Q < 128 ? Q : 128)) * 4u) + 127u) & ~127u;   // staging of the partials being reduced
+    const uint32_t fixed = 2u * L.w_part_bytes + 2u * inbox + 16384u + 4096u + 8192u + aux + 256u;
     int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
     L.NS = ns > 6 ? 6 : ns;
     const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
@@ -58,9 +64,10 @@ __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int ou
     L.off_w = ring;
     L.off_inbox = L.off_w + 2u * L.w_part_bytes;
     L.off_stage = L.off_inbox + inbox;
-    L.off_wo = L.off_stage + inbox;
-    L.off_wy = L.off_wo + 64u * 8u * 4u;
-    L.off_aux = L.off_wy + 24u * 64u * 4u;
+    L.off_a2 = L.off_stage + inbox;     // [2 parts][16 row groups][4 kblk][8][8] bf16: dgi of the own units
+    L.off_b2 = L.off_a2 + 16384u;       // [2 parts][2 n blocks][8 kblk][8][8] bf16: W_o^T (own units)
+    L.off_b3 = L.off_b2 + 4096u;        // [2 parts][8 n blocks][4 kblk][8][8] bf16: W_y rows of the own units
+    L.off_aux = L.off_b3 + 8192u;
     L.off_bar = L.off_aux + aux;
     L.total = L.off_bar + 256u;
     return L;
@@ -69,9 +76,11 @@ __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int ou
 struct GruTcBwdArgs {
     GruBwdArgs f;
     uint16_t* gxh;    // [2 slots][2 parts][3H/64 chunks][MB][8 kblk][8 rows][8 k] bf16 (UMMA order) of dgh_t
+    uint16_t* dyx;    // [2 slots][2 parts][MB][8 kblk][8 rows][8 k] bf16 (UMMA order) of dy_t, zero-initialised
     unsigned* ctr;    // [0] = A, [32] = B (separate 128-B lines), zero-initialised
     int S;
     int smem_max;
+    int keepalive;      // CVB_TC_KEEPALIVE (default 1): dummy MMAs while the issuer polls
     long long* trace;   // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE), else null
 };
 
@@ -85,6 +94,32 @@ static __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned 
     while (ld_acquire_gpu(ctr) < target) {
     }
 }
+static __device__ __forceinline__ uint4 pack_bf16x8(const uint16_t* v) {
+    return make_uint4((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16),
+                      (uint32_t)v[4] | ((uint32_t)v[5] << 16), (uint32_t)v[6] | ((uint32_t)v[7] << 16));
+}
+static __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) split_bf16(x[q], h[q], l[q]);
+    hi = pack_bf16x8(h);
+    lo = pack_bf16x8(l);
+}
+
+// drain columns [o_lo, o_hi) of D3 (hi + correction halves) of this warp's 32 TMEM lanes into part[c][o][b]
+static __device__ __forceinline__ void drain_partial(uint32_t taddr_p, float* pd, int o_lo, int o_hi, int out, int B, bool row_ok) {
+    for (int o0 = o_lo; o0 < o_hi && o0 < out; o0 += 16) {
+        float v[16], v2[16];
+        tmem_ld_x16(taddr_p + o0, v);
+        tmem_ld_x16(taddr_p + 64 + o0, v2);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (o0 + q < out) pd[(size_t)(o0 + q) * B] = v[q] + v2[q];
+        }
+    }
+}
 
 __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -96,22 +131,25 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
     const int ublk0 = (c / S) * L.Ublk;   // first unit of the cluster's block
     const int u0 = ublk0 + 8 * j;         // first of the 8 units this CTA finalises
     const int k0 = j * L.nch * TB_KC;     // first row of W_hh (= column of dgh) of this CTA's K-slice
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+    const int lane = threadIdx.x & 31;
     uint8_t* ring = smem + L.off_ring;
     uint8_t* sW = smem + L.off_w;
     float* inbox = reinterpret_cast<float*>(smem + L.off_inbox);   // [S (from)][MB*8][8]
     float* stage = reinterpret_cast<float*>(smem + L.off_stage);   // [S (to)][MB*8][8]
-    float* sWo = reinterpret_cast<float*>(smem + L.off_wo);        // [64][8]
-    float* sWy = reinterpret_cast<float*>(smem + L.off_wy);        // [24][64]
-    float* sG = reinterpret_cast<float*>(smem + L.off_aux);        // [128][24]
-    float* sQ = sG + 128 * 24;                                     // [128][8]
-    float* sRed = sG;                                              // [G][Q] (aliases sG/sQ, see the step order)
+    uint8_t* sA2 = smem + L.off_a2;
+    uint8_t* sB2 = smem + L.off_b2;
+    uint8_t* sB3 = smem + L.off_b3;
+    float* sRed = reinterpret_cast<float*>(smem + L.off_aux);      // [G][w]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* empty = full + 8;
     uint64_t* accum_full = empty + 8;
     uint64_t* inbox_full = accum_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbox_full + 1);
+    uint64_t* a2_full = inbox_full + 1;
+    uint64_t* part_full = a2_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_full + 1);
     const size_t gx_part = (size_t)(K3 / TB_KC) * L.MB * 512;   // elements per part
+    const size_t dy_part = (size_t)L.MB * 512;
     unsigned* ctrA = a.ctr;
     unsigned* ctrB = a.ctr + 32;
     const int n_pairs = B * out;
@@ -124,97 +162,147 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             const float w = f.Whh[(size_t)(k0 + kl) * H + ublk0 + n];
             uint16_t hi, lo;
             split_bf16(w, hi, lo);
-            const uint32_t off = (uint32_t)(kl / TB_KC) * ((uint32_t)S * 1024u) + (uint32_t)(n >> 3) * 1024u +
+            const uint32_t off = (uint32_t)(kl / TB_KC) * ((uint32_t)S * 2048u) + (uint32_t)(n >> 3) * 1024u +
                                  (uint32_t)((kl % TB_KC) >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(kl & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sW + off) = hi;
-            *reinterpret_cast<uint16_t*>(sW + L.w_part_bytes + off) = lo;
+            *reinterpret_cast<uint16_t*>(sW + off) = hi;                       // chunk layout: [hi: S blocks][lo: S blocks]
+            *reinterpret_cast<uint16_t*>(sW + (uint32_t)S * 1024u + off) = lo;
         }
-        for (int i = threadIdx.x; i < 64 * 8; i += TB_NT) {
-            const int o = i >> 3, uu = i & 7;
-            sWo[i] = (o < out) ? f.Wo[(size_t)o * H + u0 + uu] : 0.f;
+        for (int i = threadIdx.x; i < 16 * 64; i += TB_NT) {   // B2[n][k] = W_o[k][u0 + n]
+            const int n = i >> 6, k = i & 63;
+            const float w = (n < 8 && k < out) ? f.Wo[(size_t)k * H + u0 + n] : 0.f;
+            uint16_t hi, lo;
+            split_bf16(w, hi, lo);
+            const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+            *reinterpret_cast<uint16_t*>(sB2 + off) = hi;
+            *reinterpret_cast<uint16_t*>(sB2 + 2048 + off) = lo;
         }
-        for (int i = threadIdx.x; i < 24 * 64; i += TB_NT) {
-            const int r = i >> 6, o = i & 63;
-            const int g = r >> 3, uu = r & 7;
-            sWy[i] = (o < out) ? f.Wy[(size_t)(g * H + u0 + uu) * f.ldwy + o] : 0.f;
+        for (int i = threadIdx.x; i < 64 * 32; i += TB_NT) {   // B3[n = o][k = g*8+uu] = W_y[g*H + u0 + uu][o]
+            const int k = i >> 6, n = i & 63;
+            const float w = (k < 24 && n < out) ? f.Wy[(size_t)((k >> 3) * H + u0 + (k & 7)) * f.ldwy + n] : 0.f;
+            uint16_t hi, lo;
+            split_bf16(w, hi, lo);
+            const uint32_t off = (uint32_t)(n >> 3) * 512u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+            *reinterpret_cast<uint16_t*>(sB3 + off) = hi;
+            *reinterpret_cast<uint16_t*>(sB3 + 4096 + off) = lo;
         }
+        for (int i = threadIdx.x; i < 16384 / 16; i += TB_NT) reinterpret_cast<uint4*>(sA2)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x == 0) {
             for (int s = 0; s < 8; ++s) {
                 mbar_init(&full[s], 1);
                 mbar_init(&empty[s], 1);
             }
             mbar_init(accum_full, 1);
-            mbar_init(inbox_full, 1);   // armed with expect_tx(S slots) every step; peers' bulk copies complete_tx
+            mbar_init(inbox_full, 1);   // armed with expect_tx(S slots) every step; the peers' bulk copies complete_tx
+            mbar_init(a2_full, 128);    // every finaliser thread has staged its dgi row
+            mbar_init(part_full, 1);
             mbar_fence_init();
         }
         fence_proxy_async_smem();
-        if (warp == 2) tmem_alloc<64>(tmem_slot);
+        if (warp == 2) tmem_alloc<512>(tmem_slot);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
     }
-    cluster_sync_all();   // every CTA's inbox barrier is initialised before any remote arrive
+    cluster_sync_all();   // every CTA's inbox barrier is initialised before any peer copies into it
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ================= producer: this CTA's K-slice of dgh_{t+1}, chunk by chunk ==================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 1;   // parity to wait on the empty barrier of stage s (first pass: free)
-            for (int n = 1; n <= T; ++n) {
-                const uint16_t* src = a.gxh + (size_t)((n - 1) & 1) * 2 * gx_part + (size_t)(j * L.nch) * L.MB * 512;
-                spin_until(ctrA, (unsigned)G * (unsigned)n);
-                TB_TRACE(14);
-                fence_proxy_async_all();
-                for (int ch = 0; ch < L.nch; ++ch) {
+        // ================= producer: K-slice of dgh_{t+1} chunk by chunk, then dy_t ====================
+        int s = 0;
+        uint32_t ph = 1;   // parity to wait on the empty barrier of stage s (first pass: free)
+        for (int n = 0; n <= T; ++n) {
+            const int nchunks = (n >= 1 ? L.nch : 0) + (n < T ? 1 : 0);
+            const uint16_t* src = a.gxh + (size_t)((n - 1) & 1) * 2 * gx_part + (size_t)(j * L.nch) * L.MB * 512;
+            const uint16_t* srcy = a.dyx + (size_t)(n & 1) * 2 * dy_part;
+            if (n >= 1) {
+                if (lane == 0) {
+                    spin_until(ctrA, (unsigned)G * (unsigned)n);   // the writers fenced generic -> async proxy before their release
+                    TB_TRACE(14);
+                }
+                __syncwarp();
+            }
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const bool is_dy = (ch == nchunks - 1) && (n < T);
+                if (lane == 0) {
+                    if (is_dy) {
+                        spin_until(ctrB, (unsigned)G * (unsigned)(n + 1));
+                        TB_TRACE(13);
+                    }
                     mbar_wait(&empty[s], ph);
-                    if (ch == L.nch - 1) TB_TRACE(15);
                     if (ch < 8) TB_TRACE(32 + ch);
                     uint8_t* dst = ring + (size_t)s * L.stage_bytes;
                     mbar_expect_tx(&full[s], 2 * L.half);
-                    bulk_g2s(dst, src + (size_t)ch * L.MB * 512, L.half, &full[s]);
-                    bulk_g2s(dst + L.half, src + gx_part + (size_t)ch * L.MB * 512, L.half, &full[s]);
-                    if (++s == L.NS) {
-                        s = 0;
-                        ph ^= 1;
-                    }
+                    const uint16_t* p0 = is_dy ? srcy : src + (size_t)ch * L.MB * 512;
+                    const uint16_t* p1 = is_dy ? srcy + dy_part : src + gx_part + (size_t)ch * L.MB * 512;
+                    bulk_g2s(dst, p0, L.half, &full[s]);
+                    bulk_g2s(dst + L.half, p1, L.half, &full[s]);
+                }
+                __syncwarp();
+                if (++s == L.NS) {
+                    s = 0;
+                    ph ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer ==================================================================
-        if (lane == 0) {
-            const uint32_t idesc = idesc_bf16_f32(128, L.Ublk);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int n = 1; n <= T; ++n) {
-                for (int ch = 0; ch < L.nch; ++ch) {
-                    mbar_wait(&full[s], ph);
-                    if (ch < 8) TB_TRACE(40 + ch);
-                    if (ch == 0) TB_TRACE(16);
-                    if (ch == L.nch - 1) TB_TRACE(17);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(ring + (size_t)s * L.stage_bytes);
-                    const uint32_t a_lo = a_hi + L.half;
-                    const uint32_t b_hi = smem_u32(sW) + (uint32_t)ch * ((uint32_t)S * 1024u);
-                    const uint32_t b_lo = b_hi + L.w_part_bytes;
+        // ================= MMA issuer (descriptors stay warp-uniform; lane 0 issues) =====================
+        const uint32_t idesc1 = idesc_bf16_f32(128, L.Ublk), idesc1s = idesc_bf16_f32(128, 2 * L.Ublk);
+        const uint32_t idesc2 = idesc_bf16_f32(128, 16), idesc2s = idesc_bf16_f32(128, 32);
+        const uint32_t idesc3 = idesc_bf16_f32(128, 64), idesc3s = idesc_bf16_f32(128, 128);
+        const uint64_t dA0 = smem_desc(smem_u32(ring), 128, 1024);
+        const uint64_t dW0 = smem_desc(smem_u32(sW), 128, 1024);
+        const uint64_t dB2 = smem_desc(smem_u32(sB2), 128, 1024);
+        const uint64_t dA2 = smem_desc(smem_u32(sA2), 128, 512);
+        const uint64_t dB3 = smem_desc(smem_u32(sB3), 128, 512);
+        const uint32_t a_step = L.stage_bytes >> 4, half16 = L.half >> 4, w_step = (uint32_t)S * 128u;
+        // poll an mbarrier; while idle keep the tensor pipe warm with a dummy MMA into scratch columns (the first MMA
+        // after a few microseconds of idleness was measured to stall ~3400 cycles at issue)
+        auto wait_warm = [&](uint64_t* bar, uint32_t parity) {
+            for (;;) {
+                uint32_t ok = (lane == 0) ? (mbar_test_wait(bar, parity) ? 1u : 0u) : 0u;
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) break;
+                if (a.keepalive) mma_bf16_ss_elect(tmem + TB_COL_DUMMY, dA2, dB2, idesc2, false);
+            }
+        };
+        int s = 0;
+        uint32_t ph = 0;
+        for (int n = 0; n <= T; ++n) {
+            const int nchunks = (n >= 1 ? L.nch : 0) + (n < T ? 1 : 0);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const bool is_dy = (ch == nchunks - 1) && (n < T);
+                wait_warm(&full[s], ph);
+                if (lane == 0 && ch < 8) TB_TRACE(40 + ch);
+                tc_fence_after();
+                const uint64_t da = dA0 + (uint64_t)((uint32_t)s * a_step);
+                const uint64_t db = is_dy ? dB2 : dW0 + (uint64_t)((uint32_t)ch * w_step);
+                const uint32_t idesc_s = is_dy ? idesc2s : idesc1s;   // [hi | lo] rows of B
+                const uint32_t idesc_h = is_dy ? idesc2 : idesc1;     // hi rows only
+                const uint32_t d_tmem = is_dy ? tmem + TB_COL_Q : tmem;
+                const bool first = is_dy || ch == 0;
 #pragma unroll
-                    for (int k16 = 0; k16 < TB_KC / 16; ++k16) {
-                        const uint64_t dah = smem_desc(a_hi + k16 * 256, 128, 1024);
-                        const uint64_t dal = smem_desc(a_lo + k16 * 256, 128, 1024);
-                        const uint64_t dbh = smem_desc(b_hi + k16 * 256, 128, 1024);
-                        const uint64_t dbl = smem_desc(b_lo + k16 * 256, 128, 1024);
-                        mma_bf16_ss(tmem, dah, dbh, idesc, (ch | k16) != 0);
-                        mma_bf16_ss(tmem, dal, dbh, idesc, true);
-                        mma_bf16_ss(tmem, dah, dbl, idesc, true);
-                    }
-                    mma_commit(&empty[s]);
-                    if (ch == L.nch - 1) mma_commit(accum_full);
-                    if (++s == L.NS) {
-                        s = 0;
-                        ph ^= 1;
-                    }
+                for (int k16 = 0; k16 < TB_KC / 16; ++k16) {
+                    mma_bf16_ss_elect(d_tmem, da + 16u * k16, db + 16u * k16, idesc_s, !(first && k16 == 0));
+                    mma_bf16_ss_elect(d_tmem, da + half16 + 16u * k16, db + 16u * k16, idesc_h, true);
                 }
+                mma_commit_elect(&empty[s]);
+                if (ch == nchunks - 1) mma_commit_elect(accum_full);
+                if (lane == 0 && ch < 8) TB_TRACE(48 + ch);
+                if (++s == L.NS) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+            if (n < T) {
+                // partial of the y feedback of this step: D3[b][o] = sum_k dgi_own[b][k] W_y[k][o]
+                wait_warm(a2_full, (uint32_t)n & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16) {
+                    mma_bf16_ss_elect(tmem + TB_COL_P, dA2 + 16u * k16, dB3 + 16u * k16, idesc3s, k16 != 0);
+                    mma_bf16_ss_elect(tmem + TB_COL_P, dA2 + 512u + 16u * k16, dB3 + 16u * k16, idesc3, true);
+                }
+                mma_commit_elect(part_full);
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -224,6 +312,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
         const int etid = threadIdx.x - 128;
         const uint32_t inbox_addr = smem_u32(inbox);
         const uint32_t inbox_bar_addr = smem_u32(inbox_full);
+        const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
         float carry[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) carry[q] = act ? f.dhc[(size_t)b * H + u0 + q] : 0.f;
@@ -246,16 +335,18 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             }
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (etid == 0) TB_TRACE(0);
+            if (n > 0 && etid == 0) mbar_expect_tx(inbox_full, (uint32_t)S * L.slot_bytes);
+            mbar_wait(accum_full, (uint32_t)n & 1);
+            if (etid == 0) TB_TRACE(1);
+            tc_fence_after();
             if (n > 0) {
-                if (etid == 0) mbar_expect_tx(inbox_full, (uint32_t)S * L.slot_bytes);
-                mbar_wait(accum_full, (n - 1) & 1);
-                if (etid == 0) TB_TRACE(1);
-                tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
                 for (int k = 0; k < L.Ublk / 16; ++k) {
-                    float v[16];
-                    tmem_ld_x16(taddr + 16 * k, v);
+                    float v[16], v2[16];
+                    tmem_ld_x16(taddr + 16 * k, v);             // A_hi B_hi + A_lo B_hi
+                    tmem_ld_x16(taddr + L.Ublk + 16 * k, v2);   // A_hi B_lo
                     tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] += v2[q];
                     if (b < L.MB * 8) {
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
@@ -265,7 +356,6 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                         }
                     }
                 }
-                tc_fence_before();
                 fence_proxy_async_smem();
                 named_bar_sync(3, 128);
                 // partial sums of peer p's units -> slot j of p's inbox (bulk DSMEM copy, complete_tx on p's barrier)
@@ -273,7 +363,19 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                     bulk_s2c(mapa(inbox_addr + (uint32_t)j * L.slot_bytes, (uint32_t)etid), stage + (size_t)etid * (L.slot_bytes / 4),
                              L.slot_bytes, mapa(inbox_bar_addr, (uint32_t)etid));
                 if (etid == 0) TB_TRACE(2);
-                mbar_wait_cluster(inbox_full, (n - 1) & 1);
+            }
+            float qv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (t >= 0) {   // q = dy_t W_o[:, own units]
+                float q2[8];
+                tmem_ld_x8(taddr + TB_COL_Q, qv);
+                tmem_ld_x8(taddr + TB_COL_Q + 16, q2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) qv[q] += q2[q];
+            }
+            tc_fence_before();
+            if (n > 0) {
+                mbar_wait_cluster(inbox_full, (uint32_t)(n - 1) & 1);
                 if (etid == 0) TB_TRACE(3);
                 if (act) {
                     for (int p = 0; p < S; ++p) {
@@ -292,14 +394,8 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 }
                 break;
             }
-            if (etid == 0) TB_TRACE(4);
-            named_bar_sync(5, 256);   // q = dy_t W_o[:, own units] is in sQ
-            if (etid == 0) TB_TRACE(5);
             float dgr[8], dgz[8], dgn[8], dgnr[8];
             {
-                const float4 q0 = *reinterpret_cast<const float4*>(sQ + b * 8);
-                const float4 q1 = *reinterpret_cast<const float4*>(sQ + b * 8 + 4);
-                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
                 const float* r_ = reinterpret_cast<const float*>(pr);
                 const float* z_ = reinterpret_cast<const float*>(pz);
                 const float* n_ = reinterpret_cast<const float*>(pn);
@@ -324,64 +420,48 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                     }
                 }
             }
-            // dgi of the own units -> aux warps (their half of the partial)
-            {
-                float* g = sG + b * 24;
-                *reinterpret_cast<float4*>(g) = make_float4(dgr[0], dgr[1], dgr[2], dgr[3]);
-                *reinterpret_cast<float4*>(g + 4) = make_float4(dgr[4], dgr[5], dgr[6], dgr[7]);
-                *reinterpret_cast<float4*>(g + 8) = make_float4(dgz[0], dgz[1], dgz[2], dgz[3]);
-                *reinterpret_cast<float4*>(g + 12) = make_float4(dgz[4], dgz[5], dgz[6], dgz[7]);
-                *reinterpret_cast<float4*>(g + 16) = make_float4(dgn[0], dgn[1], dgn[2], dgn[3]);
-                *reinterpret_cast<float4*>(g + 20) = make_float4(dgn[4], dgn[5], dgn[6], dgn[7]);
+            uint4 hr, lr, hz, lz, hn, ln, hnr, lnr;
+            split8(dgr, hr, lr);
+            split8(dgz, hz, lz);
+            split8(dgn, hn, ln);
+            split8(dgnr, hnr, lnr);
+            if (act) {
+                // dgi of the own units as the A operand of the partial's MMA chain: kblk g = gate g
+                uint8_t* a2 = sA2 + (uint32_t)(b >> 3) * 512u + (uint32_t)(b & 7) * 16u;
+                *reinterpret_cast<uint4*>(a2) = hr;
+                *reinterpret_cast<uint4*>(a2 + 128) = hz;
+                *reinterpret_cast<uint4*>(a2 + 256) = hn;
+                *reinterpret_cast<uint4*>(a2 + 8192) = lr;
+                *reinterpret_cast<uint4*>(a2 + 8192 + 128) = lz;
+                *reinterpret_cast<uint4*>(a2 + 8192 + 256) = ln;
             }
-            named_bar_arrive(6, 256);
+            fence_proxy_async_smem();
+            mbar_arrive(a2_full);
             if (etid == 0) TB_TRACE(6);
             if (act) {
                 // publish dgh_t = [dar, daz, dan*r] (bf16 hi/lo, UMMA order) for the next step's contraction
                 uint16_t* dst = a.gxh + (size_t)(n & 1) * 2 * gx_part;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    const float* src = (g == 0) ? dgr : (g == 1) ? dgz : dgnr;
-                    uint32_t phi[4], plo[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint16_t h0, l0, h1, l1;
-                        split_bf16(src[2 * q], h0, l0);
-                        split_bf16(src[2 * q + 1], h1, l1);
-                        phi[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                        plo[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                    }
                     const int kidx = g * H + u0;
                     const size_t off = ((size_t)(kidx >> 6) * L.MB + (b >> 3)) * 512 + (size_t)((kidx & 63) >> 3) * 64 + (size_t)(b & 7) * 8;
-                    *reinterpret_cast<uint4*>(dst + off) = make_uint4(phi[0], phi[1], phi[2], phi[3]);
-                    *reinterpret_cast<uint4*>(dst + gx_part + off) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
-                }
-                // partial of dy_{t-1} feedback, outputs [0, 32)
-                float* pd = f.part + (size_t)c * n_pairs + b;   // [c][o][b]: lanes write consecutive rows
-                const int o_hi = out < 32 ? out : 32;
-                for (int o = 0; o < o_hi; o += 4) {
-                    float p4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int rr = 0; rr < 24; ++rr) {
-                        const float gv = (rr < 8) ? dgr[rr & 7] : (rr < 16) ? dgz[rr & 7] : dgn[rr & 7];
-                        const float4 w = *reinterpret_cast<const float4*>(sWy + rr * 64 + o);
-                        p4[0] = fmaf(gv, w.x, p4[0]);
-                        p4[1] = fmaf(gv, w.y, p4[1]);
-                        p4[2] = fmaf(gv, w.z, p4[2]);
-                        p4[3] = fmaf(gv, w.w, p4[3]);
-                    }
-                    for (int q = 0; q < 4 && o + q < o_hi; ++q) pd[(size_t)(o + q) * B] = p4[q];
+                    *reinterpret_cast<uint4*>(dst + off) = (g == 0) ? hr : (g == 1) ? hz : hnr;
+                    *reinterpret_cast<uint4*>(dst + gx_part + off) = (g == 0) ? lr : (g == 1) ? lz : lnr;
                 }
             }
             if (etid == 0) TB_TRACE(7);
-            __threadfence();
-            fence_proxy_async_all();
+            fence_proxy_async_all();   // own generic writes of dgh_t -> visible to the peers' bulk copies (async proxy)
             if (etid == 0) TB_TRACE(8);
-            named_bar_sync(7, 256);
-            if (etid == 0) red_release_gpu_add(ctrA, 1u);
+            if (out > 32) {   // second half of the partial accumulator (the aux warps drain [0, 32))
+                mbar_wait(part_full, (uint32_t)n & 1);
+                tc_fence_after();
+                drain_partial(taddr + TB_COL_P, f.part + (size_t)c * n_pairs + b, 32, 64, out, B, act);
+                tc_fence_before();
+            }
+            named_bar_sync(7, 256);    // every finaliser published; the aux warps have drained D3 into `part`
+            if (etid == 0) red_release_gpu_add(ctrA, 1u);   // release is cumulative over the barrier: one gpu-scope fence per CTA
             if (etid == 0) TB_TRACE(9);
             if (act) {   // off the critical path: only the products after the kernel read these
-                // saved for the deferred weight-gradient products
                 float* gi = f.dgi + row * K3 + u0;
                 *reinterpret_cast<float4*>(gi) = make_float4(dgr[0], dgr[1], dgr[2], dgr[3]);
                 *reinterpret_cast<float4*>(gi + 4) = make_float4(dgr[4], dgr[5], dgr[6], dgr[7]);
@@ -395,40 +475,70 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             }
         }
     } else if (warp >= 8) {
-        // ================= aux: dy reduction, q, outputs [32, 64) of the partial =========================
+        // ================= aux: dy reduction + publication, drain of the partial accumulator ============
         const int rt = threadIdx.x - 256;
         const int Q = (n_pairs + G - 1) / G;
         const int q_lo = c * Q;
         const int q_n = max(0, min(Q, n_pairs - q_lo));
-        constexpr int LB = 22;   // independent loads in flight per thread
+        const uint32_t taddr = tmem + ((uint32_t)((warp - 8) * 32) << 16) + TB_COL_P;
+        constexpr int LB = 8;   // independent loads in flight per thread
         for (int n = 0; n <= T; ++n) {
             const int t = T - 1 - n;
+            float* dyt = f.dy_tot + (size_t)(t + 1) * n_pairs;
+            uint16_t* dyx = a.dyx + (size_t)(n & 1) * 2 * dy_part;
             if (n > 0) {
-                // dy_tot[t+1] += sum over CTAs of the partials of step t+1 (fixed order)
                 if (rt == 0) spin_until(ctrA, (unsigned)G * (unsigned)n);
                 if (rt == 0) TB_TRACE(20);
                 named_bar_sync(2, 128);
-                float* dyt = f.dy_tot + (size_t)(t + 1) * n_pairs;
-                for (int qb = 0; qb < q_n; qb += 128) {
-                    // stage the [G][w] block of partials: thread -> (row r0 of every RP-th CTA, pair qc); no divisions inside
-                    const int w = min(128, q_n - qb);
-                    const int RP = 128 / w;
-                    const int r0 = rt / w, qc = rt - r0 * w;
-                    if (r0 < RP) {
-                        const float* src = f.part + (size_t)r0 * n_pairs + q_lo + qb + qc;
-                        float* dstp = sRed + r0 * w + qc;
-                        for (int cc0 = 0; cc0 < G; cc0 += RP * LB) {
-                            float v[LB];
+            }
+            // dy_tot[t+1] += sum over the CTAs of the partials of step t+1 (fixed order); publish in operand order
+            for (int qb = 0; qb < q_n; qb += 128) {
+                const int w = min(128, q_n - qb);
+                if (n > 0) {
+                    // stage the [G][w] block of partials of this CTA's pairs
+                    if (((n_pairs | Q | w) & 3) == 0) {
+                        // 16-byte cp.async.cg pieces (no registers, every piece in flight at once); no divisions inside
+                        const int w4 = w >> 2;
+                        const int dcc = 128 / w4, dpc = 128 - dcc * w4;
+                        int cc = rt / w4, pc = rt - cc * w4;
+                        const float* src = f.part + q_lo + qb;
+                        while (cc < G) {
+                            cp_async16(sRed + cc * w + 4 * pc, src + (size_t)cc * n_pairs + 4 * pc, true);
+                            cc += dcc;
+                            pc += dpc;
+                            if (pc >= w4) {
+                                pc -= w4;
+                                ++cc;
+                            }
+                        }
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                    } else {
+                        const int RP = 128 / w;
+                        const int r0 = rt / w, qc = rt - r0 * w;
+                        if (r0 < RP) {
+                            const float* src = f.part + (size_t)r0 * n_pairs + q_lo + qb + qc;
+                            float* dstp = sRed + r0 * w + qc;
+                            for (int cc0 = 0; cc0 < G; cc0 += RP * LB) {
+                                float v[LB];
 #pragma unroll
-                            for (int k = 0; k < LB; ++k)
-                                if (cc0 + k * RP + r0 < G) v[k] = __ldcg(src + (size_t)(cc0 + k * RP) * n_pairs);
+                                for (int k = 0; k < LB; ++k)
+                                    if (cc0 + k * RP + r0 < G) v[k] = __ldcg(src + (size_t)(cc0 + k * RP) * n_pairs);
 #pragma unroll
-                            for (int k = 0; k < LB; ++k)
-                                if (cc0 + k * RP + r0 < G) dstp[(cc0 + k * RP) * w] = v[k];
+                                for (int k = 0; k < LB; ++k)
+                                    if (cc0 + k * RP + r0 < G) dstp[(cc0 + k * RP) * w] = v[k];
+                            }
                         }
                     }
+                    if (rt == 0) TB_TRACE(27);
                     named_bar_sync(2, 128);
-                    if (rt < w) {
+                }
+                if (rt < w) {
+                    const int qq = q_lo + qb + rt;
+                    const int o = qq / B, bb = qq - o * B;   // pair order of `part` is [o][b]
+                    float* dyp = dyt + (size_t)bb * out + o;
+                    float dyv = __ldcg(dyp);
+                    if (n > 0) {
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                         int cc = 0;
                         for (; cc + 3 < G; cc += 4) {
@@ -438,100 +548,39 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                             s3 += sRed[(cc + 3) * w + rt];
                         }
                         for (; cc < G; ++cc) s0 += sRed[cc * w + rt];
-                        const int qq = q_lo + qb + rt;
-                        const int o = qq / B, bb = qq - o * B;   // pair order of `part` is [o][b]
-                        float* dyp = dyt + (size_t)bb * out + o;
-                        *dyp = __ldcg(dyp) + ((s0 + s1) + (s2 + s3));
+                        dyv += (s0 + s1) + (s2 + s3);
+                        *dyp = dyv;
                     }
-                    if (qb + 128 < q_n) named_bar_sync(2, 128);
+                    if (t >= 0) {
+                        uint16_t hi, lo;
+                        split_bf16(dyv, hi, lo);
+                        const size_t off = (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8 + (size_t)(o & 7);
+                        dyx[off] = hi;
+                        dyx[dy_part + off] = lo;
+                    }
                 }
-                if (rt == 0) TB_TRACE(21);
-                __threadfence();
-                named_bar_sync(2, 128);
-                if (rt == 0) red_release_gpu_add(ctrB, 1u);
-                if (rt == 0) TB_TRACE(22);
+                if (qb + 128 < q_n) named_bar_sync(2, 128);
             }
+            if (rt == 0) TB_TRACE(21);
+            fence_proxy_async_all();
+            named_bar_sync(2, 128);
+            if (rt == 0) red_release_gpu_add(ctrB, 1u);
+            if (rt == 0) TB_TRACE(22);
             if (t < 0) break;
-            if (n > 0) {
-                if (rt == 0) spin_until(ctrB, (unsigned)G * (unsigned)n);
-                if (rt == 0) TB_TRACE(23);
-                named_bar_sync(2, 128);
-            }
-            // q[b][uu] = sum_o dy_t[b][o] W_o[o][u0+uu]
-            {
-                float qv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (rt < B) {
-                    const float* dy = f.dy_tot + (size_t)(t + 1) * n_pairs + (size_t)rt * out;
-                    auto fma8 = [&](float d, int o) {
-                        const float4 w0 = *reinterpret_cast<const float4*>(sWo + o * 8);
-                        const float4 w1 = *reinterpret_cast<const float4*>(sWo + o * 8 + 4);
-                        qv[0] = fmaf(d, w0.x, qv[0]); qv[1] = fmaf(d, w0.y, qv[1]);
-                        qv[2] = fmaf(d, w0.z, qv[2]); qv[3] = fmaf(d, w0.w, qv[3]);
-                        qv[4] = fmaf(d, w1.x, qv[4]); qv[5] = fmaf(d, w1.y, qv[5]);
-                        qv[6] = fmaf(d, w1.z, qv[6]); qv[7] = fmaf(d, w1.w, qv[7]);
-                    };
-                    if ((out & 3) == 0) {   // the row is 16-byte aligned: all loads in flight before the first use
-                        float4 d4[16];
-#pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                            if (4 * q < out) d4[q] = __ldcg(reinterpret_cast<const float4*>(dy) + q);
-#pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                            if (4 * q < out) {
-                                fma8(d4[q].x, 4 * q);
-                                fma8(d4[q].y, 4 * q + 1);
-                                fma8(d4[q].z, 4 * q + 2);
-                                fma8(d4[q].w, 4 * q + 3);
-                            }
-                    } else {
-                        for (int o0 = 0; o0 < out; o0 += 16) {
-                            float d1[16];
-#pragma unroll
-                            for (int o = 0; o < 16; ++o)
-                                if (o0 + o < out) d1[o] = __ldcg(dy + o0 + o);
-#pragma unroll
-                            for (int o = 0; o < 16; ++o)
-                                if (o0 + o < out) fma8(d1[o], o0 + o);
-                        }
-                    }
-                }
-                *reinterpret_cast<float4*>(sQ + rt * 8) = make_float4(qv[0], qv[1], qv[2], qv[3]);
-                *reinterpret_cast<float4*>(sQ + rt * 8 + 4) = make_float4(qv[4], qv[5], qv[6], qv[7]);
-            }
-            if (rt == 0) TB_TRACE(24);
-            named_bar_arrive(5, 256);
-            named_bar_sync(6, 256);   // sG = dgi of the own units
+            // drain D3 (partial of the y feedback of step t, this CTA's units) into part[c][o][b]
+            mbar_wait(part_full, (uint32_t)n & 1);
             if (rt == 0) TB_TRACE(25);
-            if (rt < B && out > 32) {
-                float gv[24];
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const float4 x = *reinterpret_cast<const float4*>(sG + rt * 24 + 4 * q);
-                    gv[4 * q] = x.x; gv[4 * q + 1] = x.y; gv[4 * q + 2] = x.z; gv[4 * q + 3] = x.w;
-                }
-                float* pd = f.part + (size_t)c * n_pairs + rt;
-                for (int o = 32; o < out; o += 4) {
-                    float p4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int rr = 0; rr < 24; ++rr) {
-                        const float4 w = *reinterpret_cast<const float4*>(sWy + rr * 64 + o);
-                        p4[0] = fmaf(gv[rr], w.x, p4[0]);
-                        p4[1] = fmaf(gv[rr], w.y, p4[1]);
-                        p4[2] = fmaf(gv[rr], w.z, p4[2]);
-                        p4[3] = fmaf(gv[rr], w.w, p4[3]);
-                    }
-                    for (int q = 0; q < 4 && o + q < out; ++q) pd[(size_t)(o + q) * B] = p4[q];
-                }
-            }
+            tc_fence_after();
+            drain_partial(taddr, f.part + (size_t)c * n_pairs + rt, 0, 32, out, B, rt < B);   // the finaliser warps take [32, 64)
+            tc_fence_before();
             if (rt == 0) TB_TRACE(26);
-            __threadfence();
             named_bar_arrive(7, 256);
         }
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();   // no CTA leaves while a peer may still store into its inbox
-    if (warp == 2) tmem_dealloc<64>(tmem);
+    cluster_sync_all();   // no CTA leaves while a peer may still copy into its inbox
+    if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -542,7 +591,8 @@ bool gru_tc_bwd_shape_ok(int B, int H, int out) {
 size_t gru_tc_bwd_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
     size_t gxh = (size_t)2 * 2 * (3 * H / TB_KC) * MB * 512 / 2;   // bf16 elements -> floats
-    return round_up_sz(gxh, 64) + 64;
+    size_t dyx = (size_t)2 * 2 * MB * 512 / 2;
+    return round_up_sz(gxh, 64) + round_up_sz(dyx, 64) + 64;
 }
 
 // picks the cluster size (8 preferred) whose clusters are all co-resident; 0 = not runnable
@@ -602,18 +652,22 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     GruTcBwdArgs a;
     a.f = f;
     const size_t gxh_f = round_up_sz((size_t)2 * 2 * (3 * f.H / TB_KC) * L.MB * 512 / 2, 64);
+    const size_t dyx_f = round_up_sz((size_t)2 * 2 * L.MB * 512 / 2, 64);
     a.gxh = reinterpret_cast<uint16_t*>(tc_scratch);
-    a.ctr = reinterpret_cast<unsigned*>(tc_scratch + gxh_f);
+    a.dyx = reinterpret_cast<uint16_t*>(tc_scratch + gxh_f);
+    a.ctr = reinterpret_cast<unsigned*>(tc_scratch + gxh_f + dyx_f);
     a.S = S;
     a.smem_max = di.max_smem_optin;
     a.trace = nullptr;
+    a.keepalive = 1;
+    if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     const char* trace_file = getenv("CVB_TRACE_FILE");
     const size_t trace_bytes = (size_t)(f.T + 1) * 64 * sizeof(long long);
     if (trace_file && trace_file[0]) {
         CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
         CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));
     }
-    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, 64 * sizeof(float), s));
+    CVB_CHECK(cudaMemsetAsync(a.dyx, 0, (dyx_f + 64) * sizeof(float), s));   // dy padding columns + both counters
     CVB_CHECK(cudaFuncSetAttribute(k_gru_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(f.H / 8);
@@ -628,7 +682,10 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 2;
+    // CVB_TC_NOCOOP=1 drops the cooperative attribute (profilers that cannot replay a cooperative cluster launch; the
+    // grid still fits one wave, but co-residency is then only true on an otherwise idle device)
+    const char* nocoop = getenv("CVB_TC_NOCOOP");
+    cfg.numAttrs = (nocoop && nocoop[0] == '1') ? 1 : 2;
     prof_begin(s, CVB_PROF_GRU_BWD);
     CVB_CHECK(cudaLaunchKernelEx(&cfg, k_gru_bwd_tc, a));
     prof_end(s, CVB_PROF_GRU_BWD);

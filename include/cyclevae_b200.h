@@ -190,6 +190,12 @@ int cvb_bench_allgather(int grid, int mode, int wmode, int bytes, int inflight, 
 int cvb_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* Bm, int ldb, float beta, float* C, int ldc, void* stream);
 
+/* the split-precision tcgen05 GEMM behind cvb_gemm's large products, exported for tests: C[M,N] = op(A) op(B)
+ * (+ C if beta1) (+ bias[N]); operands are split x = hi + lo into fp16 (f16 != 0, forward products) or bf16
+ * (gradient products) pairs, three products with fp32 accumulation in TMEM. */
+int cvb_gemm_tc(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb, int beta1,
+                const float* bias, float* C, int ldc, int f16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,14 +19,13 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 80
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 80
 MHZ = 1965.0
 
-NAMES_BWD = {0: "fin: step start", 1: "fin: accum_full seen", 2: "fin: exchange stores+arrive issued", 3: "fin: inbox complete",
-             4: "fin: partial sums added", 5: "fin: q ready (bar5)", 6: "fin: gate math + sG", 7: "fin: stores+partial issued",
-             8: "fin: fences done", 9: "fin: ctrA arrive", 14: "prod: ctrA seen", 15: "prod: last chunk slot free",
-             16: "mma: first chunk full", 17: "mma: last chunk full", 20: "aux: ctrA seen", 21: "aux: partials staged",
-             22: "aux: dy reduced, ctrB arrive", 23: "aux: ctrB seen", 24: "aux: q done", 25: "aux: sG ready (bar6)",
-             26: "aux: partial half done"}
+NAMES_BWD = {0: "fin: step start", 1: "fin: accum_full seen", 2: "fin: exchange copies issued", 3: "fin: inbox complete",
+             6: "fin: gate math + A2 staged", 7: "fin: dgh published", 8: "fin: fences done", 9: "fin: ctrA arrive",
+             13: "prod: ctrB seen", 14: "prod: ctrA seen", 20: "aux: ctrA seen", 27: "aux: partials staged",
+             21: "aux: dy summed + published", 22: "aux: ctrB arrive", 25: "aux: part_full seen", 26: "aux: D3 drained"}
 NAMES_BWD.update({32 + i: f"prod: chunk {i} slot free, issuing" for i in range(8)})
 NAMES_BWD.update({40 + i: f"mma: chunk {i} full" for i in range(8)})
+NAMES_BWD.update({48 + i: f"mma: chunk {i} issued+committed" for i in range(8)})
 
 
 def run(tag):
