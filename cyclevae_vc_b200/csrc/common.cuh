@@ -78,6 +78,23 @@ int zero_floats(cudaStream_t s, float* p, size_t n);
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// MUFU-based forms for the tensor-core recurrence kernels: |error| <~ 3e-7 absolute (ex2.approx: 2 ulp near 0)
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp, no slow-path subroutine (rcp(inf) = 0)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, sigmoid_fast(2.0f * x), -1.0f); }
+
+// 16-byte read-only load pinned in program order (asm volatile): prefetches issued at the top of a recurrence
+// step stay there instead of being sunk next to their first use (where they would expose the full HBM latency)
+__device__ __forceinline__ float4 ldg_nc_v4_pinned(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -1,219 +1,342 @@
-// Tensor-core (tcgen05) variant of the persistent AR-GRU forward recurrence (gru_vae.py:364-399).
+// Tensor-core (tcgen05) forward recurrence of the autoregressive GRU (gru_vae.py:364-399), one persistent
+// cooperative launch for all T steps.
 //
-// Work split: CTA c owns hidden units [8c, 8c+8): their r,z,n rows of W_hh / W_y and their columns of
-// W_o stay in shared memory for the whole sequence as bf16 hi+lo pairs (x = hi + lo).
-// Per step the gate pre-activations of ALL batch rows for those units are one MMA chain
-//     D[128 (batch rows), 32] += A[128, K] * B[32, K]^T,   K = H (h_{t-1} chunks) + 64 (y_{t-1} chunk)
-// with D columns [r(8) | z(8) | W_hn h (8) | W_yn y (8)], three MMAs per K-step (hi*hi, lo*hi, hi*lo),
-// fp32 accumulation in TMEM.  A (the batch side) is what every CTA must all-gather each step: the
-// owners publish h_t as bf16 hi/lo already arranged in the UMMA K-major core-matrix order, so each K
-// chunk is ONE contiguous cp.async.bulk into the ring (no tensor maps, no swizzle).
+// 2-D work split over thread-block clusters of S = 4 CTAs: cluster i owns the block of 32 hidden units
+// [32i, 32i+32); CTA j of the cluster owns the K-slice [j*H/4, (j+1)*H/4) of the contraction
+// gh[b, (g,u)] = sum_k h_{t-1}[b,k] W_hh[g*H+u, k]  (g = r, z, n) for ALL units of the block, and FINALISES the 8
+// units [32i + 8j, +8).  The W_hh rows of (block x K-slice) stay in shared memory for the whole sequence as fp16
+// hi+lo (x = hi + lo + O(2^-22 x)) stored [hi rows | lo rows], so per K step ONE MMA with N = 192 forms
+// A_hi B_hi (96 columns) and A_hi B_lo (96 columns) and a second with N = 96 adds A_lo B_hi; fp32 accumulation in
+// TMEM, the halves added in registers.  A CTA ingests only 1/4 of the all-gathered h_{t-1} per step.  The four
+// partial accumulators of a unit meet in the finaliser's shared memory through bulk DSMEM copies
+// (cp.async.bulk.shared::cluster, complete_tx on the receiver's mbarrier) and are summed in fixed order: the
+// accumulation chain inside the tensor core is H/64 steps long, the rest is fp32 round-to-nearest.
 //
-// Warp roles (384 threads): w0 bulk-copy producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue
-// (TMEM lane = batch row: gates, h_t, saved activations, partial y), w8-11 reducers (fixed-order sum
-// of the per-CTA partial y_t = W_o o_t, published in both fp32 and UMMA order).  Grid-wide sync is two
-// monotonic counters: A (h_t + partials published), B (y_t published); the y reduction of step t runs
-// concurrently with the h-chunk ingest of step t+1 and only the last K chunk waits for it.
+// The y feedback runs on the tensor core as well: W_y y_{t-1} for the own 8 units is one 64-deep MMA chain
+// (accumulator D2) on the y_{t-1} chunk every CTA pulls through its ring, and the partial of
+// y_t = W_o o_t + b_o over the own units is one MMA (accumulator D3) drained into part[c][o][b]; the per-pair
+// sums over the CTAs are formed in fixed order by the "aux" warps of the CTA that owns the pair (no float atomics:
+// run-to-run deterministic) and published in operand order for the next step.
+//
+// Roles (384 threads): w0 bulk-copy producer, w1 MMA issuer, w2 TMEM allocator, w4-7 exchange + gates
+// (TMEM lane == batch row), w8-11 aux (drain of D3, y reduction + publication).  Grid-wide ordering is two
+// monotonic counters: A (h_t / partials published), B (y_t published).
+#include <stdlib.h>
+
 #include "gru_ar.cuh"
 #include "umma.cuh"
 
 namespace cvb {
 using namespace umma;
 
-constexpr int TC_NT = 384;
-constexpr int TC_U = 8;
-constexpr int TC_N = 32;            // MMA N: r,z,ghn,gin x 8 units
-constexpr int TC_KC = 64;           // K per ring stage
-constexpr int TC_WH_PART = 65536;   // bytes of one part (hi or lo) of the W_hh operand at H = 1024 (scaled by H/1024)
-constexpr int TC_RED_FLOATS = 5120;
+constexpr int TF_NT = 384;
+constexpr int TF_KC = 64;             // K per ring stage
+constexpr int TF_S = 4;               // cluster size
+constexpr int TF_UB = 8 * TF_S;       // units per cluster
+constexpr int TF_NW = 3 * TF_UB;      // rows of the W_hh operand (r, z, n of the block) = 96
+constexpr uint32_t TF_COL_Y = 192;    // D2: W_y y for the own units, 2 x 32 columns
+constexpr uint32_t TF_COL_P = 256;    // D3: partial of y_t, 2 x 64 columns
+constexpr uint32_t TF_COL_DUMMY = 384;
 
-struct TcLayout {
-    int MB;          // batch row blocks of 8
-    int NS;          // ring stages
-    int nchunk;      // H / 64
-    uint32_t stage_bytes, ring_bytes, wh_part_bytes, off_wh, off_wy, off_wo, off_bh, off_red, off_bar, total;
+struct TfLayout {
+    int MB, nch, NS;
+    uint32_t half, stage_bytes, w_chunk_bytes, slot_bytes;
+    uint32_t off_ring, off_ybuf, off_w, off_b2, off_b3, off_a2, off_inbox, off_bias, off_bar, total;
 };
 
-__host__ __device__ inline TcLayout tc_layout(int B, int H, int smem_max) {
-    TcLayout L;
+__host__ __device__ inline TfLayout tf_layout(int B, int H, int G, int out, int smem_max) {
+    TfLayout L;
     L.MB = (B + 7) / 8;
-    L.nchunk = H / TC_KC;
-    L.stage_bytes = 2u * L.MB * 1024u;
-    L.wh_part_bytes = (uint32_t)L.nchunk * 4096u;
-    uint32_t fixed = 2 * L.wh_part_bytes + 8192 + 64 * TC_U * 4 + 128 + TC_RED_FLOATS * 4 + 256;
+    L.nch = H / TF_KC / TF_S;
+    L.half = (uint32_t)L.MB * 1024u;
+    L.stage_bytes = 2u * L.half;
+    L.w_chunk_bytes = 2u * (TF_NW / 8) * 1024u;                 // [hi: 12 row groups][lo: 12 row groups] x 1 KB
+    L.slot_bytes = (uint32_t)L.MB * 8u * 96u;                   // [rows][24 floats]
+    uint32_t inbox = (uint32_t)TF_S * L.slot_bytes;             // also the staging of the partials being reduced (see the step order)
+    const int Q = (B * out + G - 1) / G;
+    const uint32_t red = (uint32_t)(G * (Q < 128 ? Q : 128)) * 4u;
+    if (inbox < red) inbox = red;
+    inbox = (inbox + 127u) & ~127u;
+    const uint32_t fixed = L.stage_bytes + (uint32_t)L.nch * L.w_chunk_bytes + 8192u + 4096u + 8192u + inbox + 640u + 256u;
     int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
-    L.NS = ns > 8 ? 8 : ns;
-    L.ring_bytes = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
-    L.off_wh = L.ring_bytes;
-    L.off_wy = L.off_wh + 2 * L.wh_part_bytes;
-    L.off_wo = L.off_wy + 8192;
-    L.off_bh = L.off_wo + 64 * TC_U * 4;
-    L.off_red = L.off_bh + 128;
-    L.off_bar = L.off_red + TC_RED_FLOATS * 4;
-    L.total = L.off_bar + 256;
+    L.NS = ns > 6 ? 6 : ns;
+    const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
+    L.off_ring = 0;                       // h chunks only: idle between a step's last h chunk and the next step's first, when it
+                                          // doubles as the staging of the outgoing partial sums
+    L.off_ybuf = ring;                    // y_{t-1} operand (hi | lo), its own buffer: it lands while the exchange is under way
+    L.off_w = L.off_ybuf + L.stage_bytes;
+    L.off_b2 = L.off_w + (uint32_t)L.nch * L.w_chunk_bytes;   // W_y rows of the own units: [hi 4 groups][lo 4 groups] x 1 KB
+    L.off_b3 = L.off_b2 + 8192u;          // W_o columns of the own units: [hi 8 groups][lo 8 groups] x 256 B
+    L.off_a2 = L.off_b3 + 4096u;          // o_t of the own units: [2 parts][16 row groups][2 kblk][8][8]
+    L.off_inbox = L.off_a2 + 8192u;
+    L.off_bias = L.off_inbox + inbox;
+    L.off_bar = L.off_bias + 640u;   // [24] b_hh + [128] partial sums of the reducers
+    L.total = L.off_bar + 256u;
     return L;
 }
 
 struct GruTcArgs {
-    GruFwdArgs f;        // same tensors as the exact kernel
-    uint16_t* hx;        // [2 slots][2 parts][nchunk][MB][8 kblk][64] bf16 (UMMA order)
-    uint16_t* yx;        // [2 slots][2 parts][MB][8 kblk][64] bf16, zero-initialised
-    unsigned* ctr;       // [0] = A, [32] = B (separate 128B lines), zero-initialised
+    GruFwdArgs f;
+    uint16_t* hx;        // [2 slots][2 parts][H/64 chunks][MB][8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
+    uint16_t* yx;        // [2 slots][2 parts][MB][8 kblk][8 rows][8 k] fp16 of y_t, zero-initialised
+    unsigned* ctr;       // [0] = A, [32] = B (separate 128-B lines), zero-initialised
     int smem_max;
+    int keepalive;
+    long long* trace;    // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE_FWD), else null
 };
 
-__device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
+#define TF_TRACE(ev)                                                     \
+    do {                                                                 \
+        if (a.trace && c == 0) a.trace[(size_t)t * 64 + (ev)] = clock64(); \
+    } while (0)
+
+static __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
     while (ld_acquire_gpu(ctr) < target) {
     }
 }
+static __device__ __forceinline__ void split8_f16(const float* x, uint4& hi, uint4& lo) {
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) split_f16(x[q], h[q], l[q]);
+    hi = make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                    (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+    lo = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                    (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+}
+// drain columns [o_lo, o_hi) of D3 (main + correction halves) of this warp's 32 TMEM lanes into part[c][o][b]
+static __device__ __forceinline__ void drain_partial_y(uint32_t taddr_p, float* pd, int o_lo, int o_hi, int out, int B, bool row_ok) {
+    for (int o0 = o_lo; o0 < o_hi && o0 < out; o0 += 16) {
+        float v[16], v2[16];
+        tmem_ld_x16(taddr_p + o0, v);
+        tmem_ld_x16(taddr_p + 64 + o0, v2);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (o0 + q < out) pd[(size_t)(o0 + q) * B] = v[q] + v2[q];
+        }
+    }
+}
 
-__global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
+__global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const GruFwdArgs& f = a.f;
     const int B = f.B, T = f.T, H = f.H, out = f.out;
-    const int G = gridDim.x, c = blockIdx.x, u0 = c * TC_U;
-    const TcLayout L = tc_layout(B, H, a.smem_max);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* ring = smem;
-    uint8_t* sWh = smem + L.off_wh;
-    uint8_t* sWy = smem + L.off_wy;
-    float* sWo = reinterpret_cast<float*>(smem + L.off_wo);   // [64][8]
-    float* sBh = reinterpret_cast<float*>(smem + L.off_bh);   // [3][8]
-    float* sRed = reinterpret_cast<float*>(smem + L.off_red);
+    const int G = gridDim.x, c = blockIdx.x;
+    const int j = (int)cluster_ctarank();
+    const TfLayout L = tf_layout(B, H, G, out, a.smem_max);
+    const int ublk0 = (c / TF_S) * TF_UB;   // first unit of the cluster's block
+    const int u0 = ublk0 + 8 * j;           // first of the 8 units this CTA finalises
+    const int k0 = j * L.nch * TF_KC;       // first column of W_hh (= unit of h) of this CTA's K-slice
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    uint8_t* ring = smem + L.off_ring;
+    float* stage = reinterpret_cast<float*>(ring);                 // [S (to)][MB*8][24], aliases the (idle) ring
+    uint8_t* sW = smem + L.off_w;
+    uint8_t* sB2 = smem + L.off_b2;
+    uint8_t* sB3 = smem + L.off_b3;
+    uint8_t* sA2 = smem + L.off_a2;
+    float* inbox = reinterpret_cast<float*>(smem + L.off_inbox);   // [S (from)][MB*8][24]
+    float* sRed = inbox;                                           // [G][w], aliases the (idle) inbox
+    float* sBh = reinterpret_cast<float*>(smem + L.off_bias);      // [3][8] b_hh of the own units
+    float* sPs = sBh + 32;                                         // [128] partial sums of the reducers
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* empty = full + 8;
-    uint64_t* accum_full = empty + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
-    const size_t hx_part = (size_t)L.nchunk * L.MB * 512;   // elements per part
+    uint64_t* accum_full = empty + 8;   // D2 (W_y y) complete
+    uint64_t* d1_full = full + 24;      // D1 (K-slice of W_hh h) complete
+    uint64_t* y_full = full + 25;
+    uint64_t* y_empty = full + 26;
+    uint8_t* ybuf = smem + L.off_ybuf;
+    uint64_t* inbox_full = accum_full + 1;
+    uint64_t* a2_full = inbox_full + 1;
+    uint64_t* part_full = a2_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_full + 1);
+    const size_t hx_part = (size_t)(H / TF_KC) * L.MB * 512;   // elements per part
     const size_t yx_part = (size_t)L.MB * 512;
     unsigned* ctrA = a.ctr;
     unsigned* ctrB = a.ctr + 32;
+    const int n_pairs = B * out;
 
-    // ---- one-time setup: weights -> bf16 hi/lo in UMMA K-major core-matrix order -----------------
-    for (int i = threadIdx.x; i < TC_N * H; i += TC_NT) {
-        int n = i / H, k = i - n * H;
-        int g = n >> 3, uu = n & 7;
-        float w = (g < 3) ? f.Whh[(size_t)(g * H + u0 + uu) * H + k] : 0.f;
-        uint16_t hi, lo;
-        split_f16(w, hi, lo);
-        uint32_t off = (uint32_t)(k / TC_KC) * 4096u + (uint32_t)(n >> 3) * 1024u + (uint32_t)((k % TC_KC) >> 3) * 128u + (uint32_t)(n & 7) * 16u +
-                       (uint32_t)(k & 7) * 2u;
-        *reinterpret_cast<uint16_t*>(sWh + off) = hi;
-        *reinterpret_cast<uint16_t*>(sWh + L.wh_part_bytes + off) = lo;
-    }
-    for (int i = threadIdx.x; i < TC_N * TC_KC; i += TC_NT) {
-        int n = i / TC_KC, k = i - n * TC_KC;
-        int g = n >> 3, uu = n & 7;
-        int row = (g == 0) ? u0 + uu : (g == 1) ? H + u0 + uu : (g == 3) ? 2 * H + u0 + uu : -1;   // block 2 (W_hn h) gets no y term
-        float w = (row >= 0 && k < out) ? f.Wy[(size_t)row * f.ldwy + k] : 0.f;
-        uint16_t hi, lo;
-        split_f16(w, hi, lo);
-        uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
-        *reinterpret_cast<uint16_t*>(sWy + off) = hi;
-        *reinterpret_cast<uint16_t*>(sWy + 4096 + off) = lo;
-    }
-    for (int i = threadIdx.x; i < 64 * TC_U; i += TC_NT) {
-        int o = i / TC_U, uu = i - o * TC_U;
-        sWo[i] = (o < out) ? f.Wo[(size_t)o * H + u0 + uu] : 0.f;
-    }
-    if (threadIdx.x < 24) sBh[threadIdx.x] = f.bhh[(threadIdx.x >> 3) * H + u0 + (threadIdx.x & 7)];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < 8; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+    // ---- one-time setup: weights -> fp16 hi/lo in UMMA K-major core-matrix order -----------------
+    {
+        const int Kr = L.nch * TF_KC;
+        for (int i = threadIdx.x; i < TF_NW * Kr; i += TF_NT) {
+            const int n = i / Kr, kl = i - n * Kr;   // n = g*32 + unit of the block
+            const int g = n / TF_UB, ul = n - g * TF_UB;
+            const float w = f.Whh[(size_t)(g * H + ublk0 + ul) * H + k0 + kl];
+            uint16_t hi, lo;
+            split_f16(w, hi, lo);
+            const uint32_t off = (uint32_t)(kl / TF_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TF_KC) >> 3) * 128u +
+                                 (uint32_t)(n & 7) * 16u + (uint32_t)(kl & 7) * 2u;
+            *reinterpret_cast<uint16_t*>(sW + off) = hi;
+            *reinterpret_cast<uint16_t*>(sW + (TF_NW / 8) * 1024u + off) = lo;
         }
-        mbar_init(accum_full, 1);
-        mbar_fence_init();
+        for (int i = threadIdx.x; i < 32 * 64; i += TF_NT) {   // B2[n = g*8+uu][k] = W_y[g*H + u0 + uu][k]; rows 24..31 zero
+            const int n = i >> 6, k = i & 63;
+            const float w = (n < 24 && k < out) ? f.Wy[(size_t)((n >> 3) * H + u0 + (n & 7)) * f.ldwy + k] : 0.f;
+            uint16_t hi, lo;
+            split_f16(w, hi, lo);
+            const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+            *reinterpret_cast<uint16_t*>(sB2 + off) = hi;
+            *reinterpret_cast<uint16_t*>(sB2 + 4096 + off) = lo;
+        }
+        for (int i = threadIdx.x; i < 64 * 16; i += TF_NT) {   // B3[n = o][k = uu] = W_o[o][u0 + uu]; k 8..15 zero
+            const int n = i >> 4, k = i & 15;
+            const float w = (k < 8 && n < out) ? f.Wo[(size_t)n * H + u0 + k] : 0.f;
+            uint16_t hi, lo;
+            split_f16(w, hi, lo);
+            const uint32_t off = (uint32_t)(n >> 3) * 256u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+            *reinterpret_cast<uint16_t*>(sB3 + off) = hi;
+            *reinterpret_cast<uint16_t*>(sB3 + 2048 + off) = lo;
+        }
+        for (int i = threadIdx.x; i < 8192 / 16; i += TF_NT) reinterpret_cast<uint4*>(sA2)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x < 24) sBh[threadIdx.x] = f.bhh[(threadIdx.x >> 3) * H + u0 + (threadIdx.x & 7)];
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            mbar_init(accum_full, 1);
+            mbar_init(d1_full, 1);
+            mbar_init(y_full, 1);
+            mbar_init(y_empty, 1);
+            mbar_init(inbox_full, 1);   // armed with expect_tx(S slots) every step; the peers' bulk copies complete_tx
+            mbar_init(a2_full, 128);
+            mbar_init(part_full, 1);
+            mbar_fence_init();
+        }
+        fence_proxy_async_smem();
+        if (warp == 2) tmem_alloc<512>(tmem_slot);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
     }
-    fence_proxy_async_smem();
-    if (warp == 2) tmem_alloc<32>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    cluster_sync_all();   // every CTA's inbox barrier is initialised before any peer copies into it
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ================= bulk-copy producer =====================================================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int t = 0; t < T; ++t) {
-                const uint16_t* hsrc = a.hx + (size_t)(t & 1) * 2 * hx_part;
-                const uint16_t* ysrc = a.yx + (size_t)(t & 1) * 2 * yx_part;
-                spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));
-                fence_proxy_async_all();
-                for (int ch = 0; ch <= L.nchunk; ++ch, ++it) {
-                    const int s = it % L.NS;
-                    mbar_wait(&empty[s], ((it / L.NS) & 1) ^ 1);
+        // ================= producer: K-slice of h_{t-1} chunk by chunk, then y_{t-1} ====================
+        int s = 0;
+        uint32_t ph = 1;
+        for (int t = 0; t < T; ++t) {
+            const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
+            const uint16_t* srcy = a.yx + (size_t)(t & 1) * 2 * yx_part;
+            if (lane == 0) {
+                spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy before their release
+                TF_TRACE(14);
+            }
+            __syncwarp();
+            for (int ch = 0; ch < L.nch; ++ch) {
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph);
+                    if (ch < 8) TF_TRACE(32 + ch);
                     uint8_t* dst = ring + (size_t)s * L.stage_bytes;
-                    const uint32_t half = L.MB * 1024u;
-                    mbar_expect_tx(&full[s], 2 * half);
-                    if (ch < L.nchunk) {
-                        bulk_g2s(dst, hsrc + (size_t)ch * L.MB * 512, half, &full[s]);
-                        bulk_g2s(dst + half, hsrc + hx_part + (size_t)ch * L.MB * 512, half, &full[s]);
-                    } else {
-                        spin_until(ctrB, (unsigned)G * (unsigned)(t + 1));
-                        fence_proxy_async_all();
-                        bulk_g2s(dst, ysrc, half, &full[s]);
-                        bulk_g2s(dst + half, ysrc + yx_part, half, &full[s]);
-                    }
+                    mbar_expect_tx(&full[s], 2 * L.half);
+                    bulk_g2s(dst, src + (size_t)ch * L.MB * 512, L.half, &full[s]);
+                    bulk_g2s(dst + L.half, src + hx_part + (size_t)ch * L.MB * 512, L.half, &full[s]);
+                }
+                __syncwarp();
+                if (++s == L.NS) {
+                    s = 0;
+                    ph ^= 1;
                 }
             }
+            if (lane == 0) {
+                spin_until(ctrB, (unsigned)G * (unsigned)(t + 1));
+                TF_TRACE(13);
+                mbar_wait(y_empty, ((uint32_t)t & 1) ^ 1);
+                mbar_expect_tx(y_full, 2 * L.half);
+                bulk_g2s(ybuf, srcy, L.half, y_full);
+                bulk_g2s(ybuf + L.half, srcy + yx_part, L.half, y_full);
+            }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ================= MMA issuer ================================================================
-        if (lane == 0) {
-            const uint32_t idesc = idesc_f16_f32(128, TC_N);
-            const uint32_t half = L.MB * 1024u;
-            uint32_t it = 0;
-            for (int t = 0; t < T; ++t) {
-                for (int ch = 0; ch <= L.nchunk; ++ch, ++it) {
-                    const int s = it % L.NS;
-                    mbar_wait(&full[s], (it / L.NS) & 1);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(ring + (size_t)s * L.stage_bytes);
-                    const uint32_t a_lo = a_hi + half;
-                    const uint32_t b_hi = (ch < L.nchunk) ? smem_u32(sWh) + (uint32_t)ch * 4096u : smem_u32(sWy);
-                    const uint32_t b_lo = (ch < L.nchunk) ? b_hi + L.wh_part_bytes : b_hi + 4096u;
+        // ================= MMA issuer (descriptors stay warp-uniform; one elected lane issues) ===========
+        const uint32_t idesc1s = idesc_f16_f32(128, 2 * TF_NW), idesc1 = idesc_f16_f32(128, TF_NW);
+        const uint32_t idesc2s = idesc_f16_f32(128, 64), idesc2 = idesc_f16_f32(128, 32);
+        const uint32_t idesc3s = idesc_f16_f32(128, 128), idesc3 = idesc_f16_f32(128, 64);
+        const uint32_t idesc_dummy = idesc_f16_f32(128, 16);
+        const uint64_t dA0 = smem_desc(smem_u32(ring), 128, 1024);
+        const uint64_t dW0 = smem_desc(smem_u32(sW), 128, 1024);
+        const uint64_t dY0 = smem_desc(smem_u32(ybuf), 128, 1024);
+        const uint64_t dB2 = smem_desc(smem_u32(sB2), 128, 1024);
+        const uint64_t dA2 = smem_desc(smem_u32(sA2), 128, 256);
+        const uint64_t dB3 = smem_desc(smem_u32(sB3), 128, 256);
+        const uint32_t a_step = L.stage_bytes >> 4, half16 = L.half >> 4, w_step = L.w_chunk_bytes >> 4;
+        // poll an mbarrier; while idle keep the tensor pipe warm with a dummy MMA into scratch columns (the first MMA
+        // after a few microseconds of idleness was measured to stall ~3400 cycles at issue)
+        auto wait_warm = [&](uint64_t* bar, uint32_t parity) {
+            for (;;) {
+                uint32_t ok = (lane == 0) ? (mbar_test_wait(bar, parity) ? 1u : 0u) : 0u;
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) break;
+                if (a.keepalive) mma_bf16_ss_elect(tmem + TF_COL_DUMMY, dA2, dB2, idesc_dummy, false);
+            }
+        };
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = 0; t < T; ++t) {
+            for (int ch = 0; ch < L.nch; ++ch) {
+                wait_warm(&full[s], ph);
+                if (lane == 0 && ch < 8) TF_TRACE(40 + ch);
+                tc_fence_after();
+                const uint64_t da = dA0 + (uint64_t)((uint32_t)s * a_step);
+                const uint64_t db = dW0 + (uint64_t)((uint32_t)ch * w_step);
 #pragma unroll
-                    for (int k16 = 0; k16 < TC_KC / 16; ++k16) {
-                        const uint64_t dah = smem_desc(a_hi + k16 * 256, 128, 1024);
-                        const uint64_t dal = smem_desc(a_lo + k16 * 256, 128, 1024);
-                        const uint64_t dbh = smem_desc(b_hi + k16 * 256, 128, 1024);
-                        const uint64_t dbl = smem_desc(b_lo + k16 * 256, 128, 1024);
-                        mma_bf16_ss(tmem, dah, dbh, idesc, (ch | k16) != 0);
-                        mma_bf16_ss(tmem, dal, dbh, idesc, true);
-                        mma_bf16_ss(tmem, dah, dbl, idesc, true);
-                    }
-                    mma_commit(&empty[s]);
-                    if (ch == L.nchunk) mma_commit(accum_full);
+                for (int k16 = 0; k16 < TF_KC / 16; ++k16) {
+                    mma_bf16_ss_elect(tmem, da + 16u * k16, db + 16u * k16, idesc1s, (ch | k16) != 0);
+                    mma_bf16_ss_elect(tmem, da + half16 + 16u * k16, db + 16u * k16, idesc1, true);
+                }
+                mma_commit_elect(&empty[s]);
+                if (ch == L.nch - 1) mma_commit_elect(d1_full);   // the exchange of the partial sums does not wait for y_{t-1}
+                if (lane == 0 && ch < 8) TF_TRACE(48 + ch);
+                if (++s == L.NS) {
+                    s = 0;
+                    ph ^= 1;
                 }
             }
+            {   // W_y y_{t-1} of the own units
+                wait_warm(y_full, (uint32_t)t & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k16 = 0; k16 < TF_KC / 16; ++k16) {
+                    mma_bf16_ss_elect(tmem + TF_COL_Y, dY0 + 16u * k16, dB2 + 16u * k16, idesc2s, k16 != 0);
+                    mma_bf16_ss_elect(tmem + TF_COL_Y, dY0 + half16 + 16u * k16, dB2 + 16u * k16, idesc2, true);
+                }
+                mma_commit_elect(y_empty);
+                mma_commit_elect(accum_full);
+            }
+            // partial of y_t over the own units: D3[b][o] = sum_uu o_t[b][uu] W_o[o][u0+uu]
+            wait_warm(a2_full, (uint32_t)t & 1);
+            tc_fence_after();
+            mma_bf16_ss_elect(tmem + TF_COL_P, dA2, dB3, idesc3s, false);
+            mma_bf16_ss_elect(tmem + TF_COL_P, dA2 + 256u, dB3, idesc3, true);
+            mma_commit_elect(part_full);
         }
     } else if (warp >= 4 && warp < 8) {
-        // ================= epilogue: TMEM lane = batch row =============================================
+        // ================= exchange + gates: TMEM lane == batch row ======================================
         const int b = (warp - 4) * 32 + lane;
         const bool act = b < B;
         const int etid = threadIdx.x - 128;
+        const uint32_t inbox_addr = smem_u32(inbox);
+        const uint32_t inbox_bar_addr = smem_u32(inbox_full);
+        const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
+        const uint32_t slot_f = L.slot_bytes / 4;
         float hreg[8];
-        // prologue: publish h_in (slot 0) in UMMA order
+        // prologue: publish h_in (slot 0) in operand order
         {
-            uint32_t phi[4], plo[4];
+            const int t = 0;
+            (void)t;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hreg[j] = act ? f.hs[(size_t)b * H + u0 + j] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint16_t h0, l0, h1, l1;
-                split_f16(hreg[2 * j], h0, l0);
-                split_f16(hreg[2 * j + 1], h1, l1);
-                phi[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                plo[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-            }
+            for (int q = 0; q < 8; ++q) hreg[q] = act ? f.hs[(size_t)b * H + u0 + q] : 0.f;
+            uint4 hh, hl;
+            split8_f16(hreg, hh, hl);
             if (act) {
-                size_t off = ((size_t)(c >> 3) * L.MB + (b >> 3)) * 512 + (size_t)(c & 7) * 64 + (size_t)(b & 7) * 8;
-                *reinterpret_cast<uint4*>(a.hx + off) = make_uint4(phi[0], phi[1], phi[2], phi[3]);
-                *reinterpret_cast<uint4*>(a.hx + hx_part + off) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
+                const size_t off = ((size_t)(u0 >> 6) * L.MB + (b >> 3)) * 512 + (size_t)((u0 & 63) >> 3) * 64 + (size_t)(b & 7) * 8;
+                *reinterpret_cast<uint4*>(a.hx + off) = hh;
+                *reinterpret_cast<uint4*>(a.hx + hx_part + off) = hl;
             }
-            __threadfence();
             fence_proxy_async_all();
             named_bar_sync(1, 128);
             if (etid == 0) red_release_gpu_add(ctrA, 1u);
@@ -223,46 +346,146 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             float4 gxv[6];
             float4 mk[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
             if (act) {
-                const float* g = f.gx + row * 3 * H + u0;
+                const float* gp = f.gx + row * 3 * H + u0;
 #pragma unroll
                 for (int gi = 0; gi < 3; ++gi) {
-                    gxv[2 * gi] = *reinterpret_cast<const float4*>(g + (size_t)gi * H);
-                    gxv[2 * gi + 1] = *reinterpret_cast<const float4*>(g + (size_t)gi * H + 4);
+                    gxv[2 * gi] = ldg_nc_v4_pinned(gp + (size_t)gi * H);
+                    gxv[2 * gi + 1] = ldg_nc_v4_pinned(gp + (size_t)gi * H + 4);
                 }
                 if (f.mask) {
-                    mk[0] = *reinterpret_cast<const float4*>(f.mask + row * H + u0);
-                    mk[1] = *reinterpret_cast<const float4*>(f.mask + row * H + u0 + 4);
+                    mk[0] = ldg_nc_v4_pinned(f.mask + row * H + u0);
+                    mk[1] = ldg_nc_v4_pinned(f.mask + row * H + u0 + 4);
                 }
             }
-            mbar_wait(accum_full, t & 1);
+            if (etid == 0) TF_TRACE(0);
+            if (etid == 0) mbar_expect_tx(inbox_full, (uint32_t)TF_S * L.slot_bytes);
+            mbar_wait(d1_full, (uint32_t)t & 1);
+            if (etid == 0) TF_TRACE(1);
             tc_fence_after();
-            float v[32];
-            const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
-            tmem_ld_x16(taddr, v);
-            tmem_ld_x16(taddr + 16, v + 16);
-            tmem_ld_wait();
+            // partial sums (main + correction) of the block's units -> the finalisers' inboxes
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    float v[16], v2[16];
+                    tmem_ld_x16(taddr + g * TF_UB + 16 * k, v);
+                    tmem_ld_x16(taddr + TF_NW + g * TF_UB + 16 * k, v2);
+                    tmem_ld_wait();
+                    if (b < L.MB * 8) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            float* d = stage + (size_t)(2 * k + h2) * slot_f + b * 24 + g * 8;
+                            *reinterpret_cast<float4*>(d) = make_float4(v[8 * h2 + 0] + v2[8 * h2 + 0], v[8 * h2 + 1] + v2[8 * h2 + 1],
+                                                                        v[8 * h2 + 2] + v2[8 * h2 + 2], v[8 * h2 + 3] + v2[8 * h2 + 3]);
+                            *reinterpret_cast<float4*>(d + 4) = make_float4(v[8 * h2 + 4] + v2[8 * h2 + 4], v[8 * h2 + 5] + v2[8 * h2 + 5],
+                                                                            v[8 * h2 + 6] + v2[8 * h2 + 6], v[8 * h2 + 7] + v2[8 * h2 + 7]);
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            if (etid < TF_S)
+                bulk_s2c(mapa(inbox_addr + (uint32_t)j * L.slot_bytes, (uint32_t)etid), stage + (size_t)etid * slot_f, L.slot_bytes,
+                         mapa(inbox_bar_addr, (uint32_t)etid));
+            if (etid == 0) TF_TRACE(2);
+            // W_y y_{t-1} of the own units: columns [r 8 | z 8 | n 8 | pad 8] (+ correction half at +32)
+            float yr[8], yz[8], yn[8];
+            mbar_wait(accum_full, (uint32_t)t & 1);
+            if (etid == 0) TF_TRACE(4);
+            tc_fence_after();
+            {
+                float c2[8];
+                tmem_ld_x8(taddr + TF_COL_Y, yr);
+                tmem_ld_x8(taddr + TF_COL_Y + 32, c2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) yr[q] += c2[q];
+                tmem_ld_x8(taddr + TF_COL_Y + 8, yz);
+                tmem_ld_x8(taddr + TF_COL_Y + 40, c2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) yz[q] += c2[q];
+                tmem_ld_x8(taddr + TF_COL_Y + 16, yn);
+                tmem_ld_x8(taddr + TF_COL_Y + 48, c2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) yn[q] += c2[q];
+            }
             tc_fence_before();
-            float ov[8];
+            mbar_wait_cluster(inbox_full, (uint32_t)t & 1);
+            if (etid == 0) TF_TRACE(3);
+            float ar[8], az[8], an[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ar[q] = az[q] = an[q] = 0.f;
             if (act) {
+#pragma unroll
+                for (int p = 0; p < TF_S; ++p) {   // fixed order: deterministic
+                    const float4* x = reinterpret_cast<const float4*>(inbox + (size_t)p * slot_f + b * 24);
+                    const float4 x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3], x4 = x[4], x5 = x[5];
+                    ar[0] += x0.x; ar[1] += x0.y; ar[2] += x0.z; ar[3] += x0.w; ar[4] += x1.x; ar[5] += x1.y; ar[6] += x1.z; ar[7] += x1.w;
+                    az[0] += x2.x; az[1] += x2.y; az[2] += x2.z; az[3] += x2.w; az[4] += x3.x; az[5] += x3.y; az[6] += x3.z; az[7] += x3.w;
+                    an[0] += x4.x; an[1] += x4.y; an[2] += x4.z; an[3] += x4.w; an[4] += x5.x; an[5] += x5.y; an[6] += x5.z; an[7] += x5.w;
+                }
+            }
+            if (etid == 0) TF_TRACE(5);
+            float rr[8], zz[8], nn[8], gh[8], ov[8];
+            {
                 const float* gxr = reinterpret_cast<const float*>(&gxv[0]);
                 const float* gxz = reinterpret_cast<const float*>(&gxv[2]);
                 const float* gxn = reinterpret_cast<const float*>(&gxv[4]);
                 const float* mkf = reinterpret_cast<const float*>(&mk[0]);
-                float rr[8], zz[8], nn[8], gh[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    rr[j] = sigmoidf_(gxr[j] + v[j] + sBh[j]);
-                    zz[j] = sigmoidf_(gxz[j] + v[8 + j] + sBh[8 + j]);
-                    gh[j] = v[16 + j] + sBh[16 + j];
-                    nn[j] = tanhf(gxn[j] + v[24 + j] + rr[j] * gh[j]);
-                    hreg[j] = (1.0f - zz[j]) * nn[j] + zz[j] * hreg[j];
-                    ov[j] = hreg[j] * mkf[j];
+                for (int q = 0; q < 8; ++q) {
+                    if (act) {
+                        rr[q] = sigmoid_fast(gxr[q] + yr[q] + ar[q] + sBh[q]);
+                        zz[q] = sigmoid_fast(gxz[q] + yz[q] + az[q] + sBh[8 + q]);
+                        gh[q] = an[q] + sBh[16 + q];
+                        nn[q] = tanh_fast(gxn[q] + yn[q] + rr[q] * gh[q]);
+                        hreg[q] = (1.0f - zz[q]) * nn[q] + zz[q] * hreg[q];
+                        ov[q] = hreg[q] * mkf[q];
+                    } else {
+                        rr[q] = zz[q] = nn[q] = gh[q] = ov[q] = 0.f;
+                    }
                 }
+            }
+            if (etid == 0) TF_TRACE(10);
+            uint4 oh, ol, hh, hl;
+            split8_f16(ov, oh, ol);
+            split8_f16(hreg, hh, hl);
+            if (etid == 0) TF_TRACE(11);
+            if (act) {   // o_t of the own units as the A operand of the partial's MMA (k block 0; k block 1 stays zero)
+                uint8_t* a2 = sA2 + (uint32_t)(b >> 3) * 256u + (uint32_t)(b & 7) * 16u;
+                *reinterpret_cast<uint4*>(a2) = oh;
+                *reinterpret_cast<uint4*>(a2 + 4096) = ol;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(a2_full);
+            if (etid == 0) TF_TRACE(6);
+            if (act) {   // publish h_t (fp16 hi/lo, operand order) into the other exchange slot
+                uint16_t* hdst = a.hx + (size_t)((t + 1) & 1) * 2 * hx_part;
+                const size_t off = ((size_t)(u0 >> 6) * L.MB + (b >> 3)) * 512 + (size_t)((u0 & 63) >> 3) * 64 + (size_t)(b & 7) * 8;
+                *reinterpret_cast<uint4*>(hdst + off) = hh;
+                *reinterpret_cast<uint4*>(hdst + hx_part + off) = hl;
+            }
+            if (etid == 0) TF_TRACE(7);
+            fence_proxy_async_all();   // own generic writes of h_t -> visible to the peers' bulk copies (async proxy)
+            if (etid == 0) TF_TRACE(8);
+            if (out > 32) {   // second half of the partial accumulator (the aux warps drain [0, 32))
+                mbar_wait(part_full, (uint32_t)t & 1);
+                tc_fence_after();
+                drain_partial_y(taddr + TF_COL_P, f.part + (size_t)c * n_pairs + b, 32, 64, out, B, act);
+                tc_fence_before();
+            }
+            named_bar_sync(7, 256);    // every finaliser published; D3 is drained into `part`
+            if (etid == 0) red_release_gpu_add(ctrA, 1u);   // release is cumulative over the barrier: one gpu-scope fence per CTA
+            if (etid == 0) TF_TRACE(9);
+            if (act) {   // off the critical path: outputs / saved activations that only later kernels read
                 float* hd = f.hs + (size_t)(t + 1) * B * H + (size_t)b * H + u0;
                 *reinterpret_cast<float4*>(hd) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
                 *reinterpret_cast<float4*>(hd + 4) = make_float4(hreg[4], hreg[5], hreg[6], hreg[7]);
+                const size_t so = row * H + u0;
                 if (f.sv_r) {
-                    const size_t so = row * H + u0;
                     *reinterpret_cast<float4*>(f.sv_r + so) = make_float4(rr[0], rr[1], rr[2], rr[3]);
                     *reinterpret_cast<float4*>(f.sv_r + so + 4) = make_float4(rr[4], rr[5], rr[6], rr[7]);
                     *reinterpret_cast<float4*>(f.sv_z + so) = make_float4(zz[0], zz[1], zz[2], zz[3]);
@@ -273,151 +496,234 @@ __global__ void __launch_bounds__(TC_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                     *reinterpret_cast<float4*>(f.sv_ghn + so + 4) = make_float4(gh[4], gh[5], gh[6], gh[7]);
                 }
                 if (f.sv_o) {
-                    const size_t so = row * H + u0;
                     *reinterpret_cast<float4*>(f.sv_o + so) = make_float4(ov[0], ov[1], ov[2], ov[3]);
                     *reinterpret_cast<float4*>(f.sv_o + so + 4) = make_float4(ov[4], ov[5], ov[6], ov[7]);
                 }
-                // publish h_t (bf16 hi/lo, UMMA order) into the other exchange slot
-                uint32_t phi[4], plo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint16_t h0, l0, h1, l1;
-                    split_f16(hreg[2 * j], h0, l0);
-                    split_f16(hreg[2 * j + 1], h1, l1);
-                    phi[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    plo[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                }
-                uint16_t* hdst = a.hx + (size_t)((t + 1) & 1) * 2 * hx_part;
-                size_t off = ((size_t)(c >> 3) * L.MB + (b >> 3)) * 512 + (size_t)(c & 7) * 64 + (size_t)(b & 7) * 8;
-                *reinterpret_cast<uint4*>(hdst + off) = make_uint4(phi[0], phi[1], phi[2], phi[3]);
-                *reinterpret_cast<uint4*>(hdst + hx_part + off) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
-                // partial y_t = W_o[:, own units] o_t
-                float* pd = f.part + ((size_t)c * B + b) * out;
-                for (int o = 0; o < out; o += 4) {
-                    float p4[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 w0 = *reinterpret_cast<const float4*>(sWo + (o + q) * 8);
-                        const float4 w1 = *reinterpret_cast<const float4*>(sWo + (o + q) * 8 + 4);
-                        float s = w0.x * ov[0];
-                        s = fmaf(w0.y, ov[1], s);
-                        s = fmaf(w0.z, ov[2], s);
-                        s = fmaf(w0.w, ov[3], s);
-                        s = fmaf(w1.x, ov[4], s);
-                        s = fmaf(w1.y, ov[5], s);
-                        s = fmaf(w1.z, ov[6], s);
-                        s = fmaf(w1.w, ov[7], s);
-                        p4[q] = s;
-                    }
-                    if (o + 3 < out) {
-                        if ((out & 3) == 0) {
-                            *reinterpret_cast<float4*>(pd + o) = make_float4(p4[0], p4[1], p4[2], p4[3]);
-                        } else {
-                            pd[o] = p4[0]; pd[o + 1] = p4[1]; pd[o + 2] = p4[2]; pd[o + 3] = p4[3];
-                        }
-                    } else {
-                        for (int q = 0; q < 4 && o + q < out; ++q) pd[o + q] = p4[q];
-                    }
-                }
             }
-            __threadfence();
-            fence_proxy_async_all();
-            named_bar_sync(1, 128);
-            if (etid == 0) red_release_gpu_add(ctrA, 1u);
         }
     } else if (warp >= 8) {
-        // ================= reducers: y_t = b_o + sum_c partial_c, published fp32 + UMMA order ==========
-        const int rtid = threadIdx.x - 256;
-        const int n_pairs = B * out;
+        // ================= aux: drain of D3, y reduction + publication ===================================
+        const int rt = threadIdx.x - 256;
         const int Q = (n_pairs + G - 1) / G;
         const int q_lo = c * Q;
         const int q_n = max(0, min(Q, n_pairs - q_lo));
-        const int QB = max(1, min(128, TC_RED_FLOATS / G));   // pairs per pass through the scratch (one per reducer thread)
+        const uint32_t taddr = tmem + ((uint32_t)((warp - 8) * 32) << 16) + TF_COL_P;
+        constexpr int LB = 8;
+        // round 0 publishes y_in; round r >= 1 reduces the partials of step r-1 into y_{r-1}
         for (int round = 0; round <= T; ++round) {
-            // round 0 publishes y_in; round r >= 1 reduces the partials of step r-1 into y_{r-1}
+            const int t = round;   // trace row
             if (round > 0) {
-                if (rtid == 0) spin_until(ctrA, (unsigned)G * (unsigned)(round + 1));
+                // drain D3 of step round-1 (outputs [0, 32) of this CTA's partial)
+                mbar_wait(part_full, (uint32_t)(round - 1) & 1);
+                tc_fence_after();
+                drain_partial_y(taddr, f.part + (size_t)c * n_pairs + rt, 0, 32, out, B, rt < B);
+                tc_fence_before();
+                if (rt == 0) TF_TRACE(26);
+                named_bar_arrive(7, 256);
+                if (rt == 0) spin_until(ctrA, (unsigned)G * (unsigned)(round + 1));
+                if (rt == 0) TF_TRACE(20);
                 named_bar_sync(2, 128);
             }
             float* ydst = f.ys + (size_t)round * n_pairs;
             uint16_t* yx = a.yx + (size_t)(round & 1) * 2 * yx_part;
-            for (int qb = 0; qb < q_n; qb += QB) {
-                const int nq = min(QB, q_n - qb);
-                float yv = 0.f;
+            for (int qb = 0; qb < q_n; qb += 128) {
+                const int w = min(128, q_n - qb);
                 if (round > 0) {
-                    for (int i = rtid; i < nq * G; i += 128) {
-                        int cc = i / nq, q = i - cc * nq;
-                        sRed[cc * nq + q] = __ldcg(f.part + (size_t)cc * n_pairs + q_lo + qb + q);
+                    // stage the [G][w] block of partials of this CTA's pairs
+                    if (((n_pairs | Q | w) & 3) == 0) {
+                        const int w4 = w >> 2;
+                        const int dcc = 128 / w4, dpc = 128 - dcc * w4;
+                        int cc = rt / w4, pc = rt - cc * w4;
+                        const float* src = f.part + q_lo + qb;
+                        while (cc < G) {
+                            cp_async16(sRed + cc * w + 4 * pc, src + (size_t)cc * n_pairs + 4 * pc, true);
+                            cc += dcc;
+                            pc += dpc;
+                            if (pc >= w4) {
+                                pc -= w4;
+                                ++cc;
+                            }
+                        }
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                    } else {
+                        const int RP = 128 / w;
+                        const int r0 = rt / w, qc = rt - r0 * w;
+                        if (r0 < RP) {
+                            const float* src = f.part + (size_t)r0 * n_pairs + q_lo + qb + qc;
+                            float* dstp = sRed + r0 * w + qc;
+                            for (int cc0 = 0; cc0 < G; cc0 += RP * LB) {
+                                float v[LB];
+#pragma unroll
+                                for (int k = 0; k < LB; ++k)
+                                    if (cc0 + k * RP + r0 < G) v[k] = __ldcg(src + (size_t)(cc0 + k * RP) * n_pairs);
+#pragma unroll
+                                for (int k = 0; k < LB; ++k)
+                                    if (cc0 + k * RP + r0 < G) dstp[(cc0 + k * RP) * w] = v[k];
+                            }
+                        }
+                    }
+                    if (rt == 0) TF_TRACE(27);
+                    named_bar_sync(2, 128);
+                }
+                // sum over the CTAs: nsub threads per pair, each a fixed subset, combined in fixed order (deterministic)
+                const int nsub = 128 / w;
+                const int sub = rt / w, qi = rt - sub * w;
+                if (round > 0) {
+                    if (sub < nsub) {
+                        float s0 = 0.f, s1 = 0.f;
+                        int cc = sub;
+                        for (; cc + nsub < G; cc += 2 * nsub) {
+                            s0 += sRed[cc * w + qi];
+                            s1 += sRed[(cc + nsub) * w + qi];
+                        }
+                        if (cc < G) s0 += sRed[cc * w + qi];
+                        sPs[sub * w + qi] = s0 + s1;
                     }
                     named_bar_sync(2, 128);
-                    if (rtid < nq) {
-                        float s = 0.f;
-                        for (int cc = 0; cc < G; ++cc) s += sRed[cc * nq + rtid];
-                        yv = s + f.bo[(q_lo + qb + rtid) % out];
-                    }
-                } else if (rtid < nq) {
-                    yv = f.ys[q_lo + qb + rtid];
                 }
-                if (rtid < nq) {
-                    const int q = q_lo + qb + rtid;
-                    const int bb = q / out, o = q - bb * out;
-                    if (round > 0) ydst[q] = yv;
+                if (rt < w) {
+                    const int qq = q_lo + qb + rt;
+                    const int o = qq / B, bb = qq - o * B;   // pair order of `part` is [o][b]
+                    float yv;
+                    if (round > 0) {
+                        float sacc = sPs[rt];
+                        for (int k = 1; k < nsub; ++k) sacc += sPs[k * w + rt];
+                        yv = sacc + f.bo[o];
+                        ydst[(size_t)bb * out + o] = yv;
+                    } else {
+                        yv = f.ys[(size_t)bb * out + o];
+                    }
                     uint16_t hi, lo;
                     split_f16(yv, hi, lo);
-                    size_t off = (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8 + (size_t)(o & 7);
+                    const size_t off = (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8 + (size_t)(o & 7);
                     yx[off] = hi;
                     yx[yx_part + off] = lo;
                 }
-                named_bar_sync(2, 128);
+                if (qb + 128 < q_n) named_bar_sync(2, 128);
             }
-            __threadfence();
+            if (rt == 0) TF_TRACE(21);
             fence_proxy_async_all();
             named_bar_sync(2, 128);
-            if (rtid == 0) red_release_gpu_add(ctrB, 1u);
+            if (rt == 0) red_release_gpu_add(ctrB, 1u);
+            if (rt == 0) TF_TRACE(22);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<32>(tmem);
+    cluster_sync_all();   // no CTA leaves while a peer may still copy into its inbox
+    if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
-// eligibility of the tensor-core variant
-bool gru_tc_shape_ok(int B, int H, int out) { return H % TC_KC == 0 && H >= TC_KC && out <= 64 && B <= 128 && B >= 1; }
-bool gru_tc_supported(int B, int H, int out, const DeviceInfo& di) {
-    if (!gru_tc_shape_ok(B, H, out) || H / TC_U > di.n_sm) return false;
-    TcLayout L = tc_layout(B, H, di.max_smem_optin);
-    return L.NS >= 2;
+// ---- host side ----------------------------------------------------------------------------------------
+bool gru_tc_shape_ok(int B, int H, int out) {
+    return H % (TF_KC * TF_S) == 0 && H >= TF_KC * TF_S && out >= 1 && out <= 64 && B >= 1 && B <= 128;
 }
 
 size_t gru_tc_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
-    size_t hx = (size_t)2 * 2 * (H / TC_KC) * MB * 512 / 2;   // bf16 elements -> floats
+    size_t hx = (size_t)2 * 2 * (H / TF_KC) * MB * 512 / 2;   // fp16 elements -> floats
     size_t yx = (size_t)2 * 2 * MB * 512 / 2;
     return round_up_sz(hx, 64) + round_up_sz(yx, 64) + 64;
 }
+
+// are all G/4 clusters co-resident at this shape?  (cached per shape)
+static bool fwd_runnable(int B, int H, int out, const DeviceInfo& di, TfLayout* Lout) {
+    const int G = H / 8;
+    if (!gru_tc_shape_ok(B, H, out) || G > di.n_sm) return false;
+    struct Entry { int B, H, out, ok; };
+    static Entry cache[16];
+    static int n_cache = 0;
+    int ok = -1;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].B == B && cache[i].H == H && cache[i].out == out) ok = cache[i].ok;
+    TfLayout L = tf_layout(B, H, G, out, di.max_smem_optin);
+    if (ok < 0) {
+        ok = 0;
+        if (L.NS >= 2 && (int)L.total <= di.max_smem_optin && (uint32_t)L.NS * L.stage_bytes >= (uint32_t)TF_S * L.slot_bytes &&
+            cudaFuncSetAttribute(k_gru_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(TF_NT);
+            cfg.dynamicSmemBytes = L.total;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = TF_S;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k_gru_fwd_tc, &cfg) == cudaSuccess) {
+                if (getenv("CVB_DEBUG"))
+                    fprintf(stderr, "[cvb] k_gru_fwd_tc: %d co-resident clusters of %d (need %d), smem %u, ring %d\n", ncl, TF_S, G / TF_S, L.total, L.NS);
+                ok = ncl * TF_S >= G ? 1 : 0;
+            }
+        }
+        cudaGetLastError();
+        if (n_cache < 16) cache[n_cache++] = Entry{B, H, out, ok};
+    }
+    if (ok && Lout) *Lout = L;
+    return ok != 0;
+}
+
+bool gru_tc_supported(int B, int H, int out, const DeviceInfo& di) { return fwd_runnable(B, H, out, di, nullptr); }
 
 int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     if (f.T <= 0 || f.B <= 0) return 0;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
-    CVB_REQUIRE(gru_tc_supported(f.B, f.H, f.out, di), "gru_ar_fwd_tc: unsupported shape B=%d H=%d out=%d", f.B, f.H, f.out);
-    TcLayout L = tc_layout(f.B, f.H, di.max_smem_optin);
+    TfLayout L;
+    CVB_REQUIRE(fwd_runnable(f.B, f.H, f.out, di, &L), "gru_ar_fwd_tc: unsupported shape B=%d H=%d out=%d", f.B, f.H, f.out);
     GruTcArgs a;
     a.f = f;
-    size_t MB = L.MB;
-    size_t hx_f = round_up_sz((size_t)2 * 2 * L.nchunk * MB * 512 / 2, 64);
-    size_t yx_f = round_up_sz((size_t)2 * 2 * MB * 512 / 2, 64);
+    const size_t hx_f = round_up_sz((size_t)2 * 2 * (f.H / TF_KC) * L.MB * 512 / 2, 64);
+    const size_t yx_f = round_up_sz((size_t)2 * 2 * L.MB * 512 / 2, 64);
     a.hx = reinterpret_cast<uint16_t*>(tc_scratch);
     a.yx = reinterpret_cast<uint16_t*>(tc_scratch + hx_f);
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + hx_f + yx_f);
     a.smem_max = di.max_smem_optin;
+    a.keepalive = 1;
+    if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
+    a.trace = nullptr;
+    const char* trace_file = getenv("CVB_TRACE_FILE_FWD");
+    const size_t trace_bytes = (size_t)(f.T + 1) * 64 * sizeof(long long);
+    if (trace_file && trace_file[0]) {
+        CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
+        CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));
+    }
     CVB_CHECK(cudaMemsetAsync(a.yx, 0, (yx_f + 64) * sizeof(float), s));   // y padding columns + both counters
     CVB_CHECK(cudaFuncSetAttribute(k_gru_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    void* params[] = {&a};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(f.H / 8);
+    cfg.blockDim = dim3(TF_NT);
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TF_S;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    const char* nocoop = getenv("CVB_TC_NOCOOP");   // see gru_tc_bwd.cu
+    cfg.numAttrs = (nocoop && nocoop[0] == '1') ? 1 : 2;
     prof_begin(s, CVB_PROF_GRU_FWD);
-    CVB_CHECK(cudaLaunchCooperativeKernel((const void*)k_gru_fwd_tc, dim3(f.H / TC_U), dim3(TC_NT), params, L.total, s));
+    CVB_CHECK(cudaLaunchKernelEx(&cfg, k_gru_fwd_tc, a));
     prof_end(s, CVB_PROF_GRU_FWD);
     count_launch();
+    if (a.trace) {   // profiling hook only: synchronises
+        CVB_CHECK(cudaStreamSynchronize(s));
+        long long* h = (long long*)malloc(trace_bytes);
+        CVB_CHECK(cudaMemcpy(h, a.trace, trace_bytes, cudaMemcpyDeviceToHost));
+        if (FILE* fp = fopen(trace_file, "wb")) {
+            fwrite(h, 1, trace_bytes, fp);
+            fclose(fp);
+        }
+        free(h);
+        CVB_CHECK(cudaFree(a.trace));
+    }
     return 0;
 }
 

@@ -325,12 +325,12 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 const size_t so = row * H + u0;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    pr[q] = *reinterpret_cast<const float4*>(f.sv_r + so + 4 * q);
-                    pz[q] = *reinterpret_cast<const float4*>(f.sv_z + so + 4 * q);
-                    pn[q] = *reinterpret_cast<const float4*>(f.sv_n + so + 4 * q);
-                    pg[q] = *reinterpret_cast<const float4*>(f.sv_ghn + so + 4 * q);
-                    ph[q] = *reinterpret_cast<const float4*>(f.hs + so + 4 * q);   // hs slot t = h_{t-1}
-                    if (f.mask) pm[q] = *reinterpret_cast<const float4*>(f.mask + so + 4 * q);
+                    pr[q] = ldg_nc_v4_pinned(f.sv_r + so + 4 * q);
+                    pz[q] = ldg_nc_v4_pinned(f.sv_z + so + 4 * q);
+                    pn[q] = ldg_nc_v4_pinned(f.sv_n + so + 4 * q);
+                    pg[q] = ldg_nc_v4_pinned(f.sv_ghn + so + 4 * q);
+                    ph[q] = ldg_nc_v4_pinned(f.hs + so + 4 * q);   // hs slot t = h_{t-1}
+                    if (f.mask) pm[q] = ldg_nc_v4_pinned(f.mask + so + 4 * q);
                 }
             }
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

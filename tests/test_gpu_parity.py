@@ -411,7 +411,7 @@ def test_full_size_properties(cvb):
         assert torch.equal(o1, o2) and torch.equal(h1, h2) and torch.equal(y1, y2)
         for j in (0, 37, 79):
             oj, yj, hj = me(xg[j], y0[j:j + 1], clamp_vae=True, lat_dim=lat)
-            assert _maxabs(oj, o1[j]) < 1e-5 and _maxabs(hj[0, 0], h1[0, j]) < 1e-5
+            assert _maxabs(oj, o1[j]) < 5e-5 and _maxabs(hj[0, 0], h1[0, j]) < 5e-5   # batched gx: tensor-core GEMM, unbatched: cuBLAS
         ref, _, href = orc.gru_rnn_forward(Pe, enc, x[[3, 64]], torch.zeros(2, 1, 2 * lat), clamp_vae=True, lat_dim=lat)
     assert _maxabs(o1[[3, 64]], ref) < TOL
     assert _maxabs(h1[0, [3, 64]], href[0]) < TOL

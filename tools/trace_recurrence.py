@@ -28,6 +28,15 @@ NAMES_BWD.update({40 + i: f"mma: chunk {i} full" for i in range(8)})
 NAMES_BWD.update({48 + i: f"mma: chunk {i} issued+committed" for i in range(8)})
 
 
+NAMES_FWD = {0: "fin: step start", 1: "fin: accum_full seen", 2: "fin: exchange copies issued", 3: "fin: inbox complete",
+             4: "fin: accum_full (y part) seen", 5: "fin: partial sums added", 10: "fin: gates done", 11: "fin: splits done", 6: "fin: gates + A2 staged", 7: "fin: h published", 8: "fin: proxy fence done", 9: "fin: ctrA arrive",
+             13: "prod: ctrB seen", 14: "prod: ctrA seen", 20: "aux: ctrA seen", 27: "aux: partials staged",
+             21: "aux: y summed + published", 22: "aux: ctrB arrive", 26: "aux: D3 drained"}
+NAMES_FWD.update({32 + i: f"prod: chunk {i} slot free, issuing" for i in range(8)})
+NAMES_FWD.update({40 + i: f"mma: chunk {i} full" for i in range(8)})
+NAMES_FWD.update({48 + i: f"mma: chunk {i} issued+committed" for i in range(8)})
+
+
 def run(tag):
     enc = cvb.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, do_prob=0.5, scale_out_flag=False).cuda().train()
     enc.apply(cvb.initialize)
@@ -36,10 +45,12 @@ def run(tag):
     for i in range(3):
         path = os.path.join(ROOT, "gpurun_out", f"trace_{tag}_{i}.bin")
         os.environ["CVB_TRACE_FILE"] = path
+        os.environ["CVB_TRACE_FILE_FWD"] = path.replace("trace_bwd", "trace_fwd")
         o, y, h = enc(x, y0, do=True, clamp_vae=True, lat_dim=32)
         o.square().sum().backward()
         torch.cuda.synchronize()
     os.environ.pop("CVB_TRACE_FILE", None)
+    os.environ.pop("CVB_TRACE_FILE_FWD", None)
     return path
 
 
@@ -64,4 +75,5 @@ def report(path, names):
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     p = run("bwd")
+    report(p.replace("trace_bwd", "trace_fwd"), NAMES_FWD)
     report(p, NAMES_BWD)
