@@ -26,6 +26,7 @@ constexpr int GT_BM = 128, GT_BN = 128, GT_BK = 64;
 constexpr int GT_BLOCK_ELEMS = GT_BM * GT_BK;          // one part of one block
 constexpr int GT_STAGE_BYTES = 4 * GT_BLOCK_ELEMS * 2;  // A hi, A lo, B hi, B lo
 constexpr int GT_NS = 3;
+constexpr int GT_KD = 2;   // chunks (of 64) accumulated inside the tensor core before the slice is added in fp32 registers
 constexpr int GT_THREADS = 256;
 
 // ---- operand preparation ---------------------------------------------------------------------------------
@@ -135,37 +136,45 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
         }
     } else if (warp == 1) {
         // ================= MMA issuer =====================================================================
+        // The accumulation chain inside the tensor core rounds toward zero (measured: error grows ~K / 2^22), so a
+        // TMEM accumulator only ever sums GT_KD chunks (K = 128); the epilogue warps add the slices in fp32 registers
+        // with round-to-nearest while the other accumulator buffer receives the next slice.
         const uint32_t idesc_s = g.f16 ? idesc_f16_f32(128, 256) : idesc_bf16_f32(128, 256);   // B rows [hi | lo]
         const uint32_t idesc_h = g.f16 ? idesc_f16_f32(128, 128) : idesc_bf16_f32(128, 128);   // B hi rows only
         const uint64_t d0 = smem_desc(smem_u32(smem), 128, 1024);
         int s = 0, acc = 0;
         uint32_t ph = 0, acc_ph = 1;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            if (lane == 0) mbar_wait(&tmem_empty[acc], acc_ph);
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t d_tmem = tmem + (uint32_t)acc * 256u;
             for (int kc = 0; kc < g.KC; ++kc) {
+                const bool slice_start = (kc % GT_KD) == 0;
+                const bool slice_end = ((kc + 1) % GT_KD) == 0 || kc == g.KC - 1;
+                if (slice_start) {
+                    if (lane == 0) mbar_wait(&tmem_empty[acc], acc_ph);
+                    __syncwarp();
+                }
                 if (lane == 0) mbar_wait(&full[s], ph);
                 __syncwarp();
                 tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t)acc * 256u;
                 const uint64_t da = d0 + (uint64_t)((uint32_t)s * (GT_STAGE_BYTES >> 4));
                 const uint64_t db = da + (uint64_t)(GT_STAGE_BYTES >> 5);
 #pragma unroll
                 for (int k16 = 0; k16 < GT_BK / 16; ++k16) {
-                    mma_bf16_ss_elect(d_tmem, da + 16u * k16, db + 16u * k16, idesc_s, (kc | k16) != 0);
+                    mma_bf16_ss_elect(d_tmem, da + 16u * k16, db + 16u * k16, idesc_s, !(slice_start && k16 == 0));
                     mma_bf16_ss_elect(d_tmem, da + (uint32_t)(GT_BLOCK_ELEMS * 2 >> 4) + 16u * k16, db + 16u * k16, idesc_h, true);
                 }
                 mma_commit_elect(&empty[s]);
-                if (kc == g.KC - 1) mma_commit_elect(&tmem_full[acc]);
                 if (++s == GT_NS) {
                     s = 0;
                     ph ^= 1;
                 }
-            }
-            if (++acc == 2) {
-                acc = 0;
-                acc_ph ^= 1;
+                if (slice_end) {
+                    mma_commit_elect(&tmem_full[acc]);
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_ph ^= 1;
+                    }
+                }
             }
         }
     } else if (warp >= 4) {
@@ -173,51 +182,59 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
         int acc = 0;
         uint32_t acc_ph = 0;
         const bool vec_ok = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+        const int n_slices = (g.KC + GT_KD - 1) / GT_KD;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int nt = tile / g.MT, mt = tile - nt * g.MT;
             const int row = mt * GT_BM + (warp - 4) * 32 + lane;
             const int n0 = nt * GT_BN;
-            mbar_wait(&tmem_full[acc], acc_ph);
-            tc_fence_after();
-            const uint32_t taddr = tmem + (uint32_t)acc * 256u + ((uint32_t)((warp - 4) * 32) << 16);
-            float* crow = g.C + (size_t)row * g.ldc + n0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < GT_BN; c0 += 16) {
-                if (n0 + c0 >= g.N) break;   // warp-uniform
-                float v[16], v2[16];
-                tmem_ld_x16(taddr + c0, v);
-                tmem_ld_x16(taddr + 128 + c0, v2);
-                tmem_ld_wait();
-                if (row < g.M) {
+            float sum[GT_BN];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) v[q] += v2[q];
-                    if (g.bias) {
+            for (int q = 0; q < GT_BN; ++q) sum[q] = 0.f;
+            for (int sl = 0; sl < n_slices; ++sl) {
+                mbar_wait(&tmem_full[acc], acc_ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem + (uint32_t)acc * 256u + ((uint32_t)((warp - 4) * 32) << 16);
 #pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                            if (n0 + c0 + q < g.N) v[q] += g.bias[n0 + c0 + q];
-                    }
-                    if (vec_ok && n0 + c0 + 16 <= g.N) {
+                for (int c0 = 0; c0 < GT_BN; c0 += 16) {
+                    float v[16], v2[16];
+                    tmem_ld_x16(taddr + c0, v);
+                    tmem_ld_x16(taddr + 128 + c0, v2);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 16; q += 4) {
-                            float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-                            if (g.beta1) {
-                                const float4 old = *reinterpret_cast<const float4*>(crow + c0 + q);
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                            }
-                            *reinterpret_cast<float4*>(crow + c0 + q) = o;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                            if (n0 + c0 + q < g.N) crow[c0 + q] = g.beta1 ? crow[c0 + q] + v[q] : v[q];
-                    }
+                    for (int q = 0; q < 16; ++q) sum[c0 + q] += v[q] + v2[q];
+                }
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_ph ^= 1;
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) {
-                acc = 0;
-                acc_ph ^= 1;
+            if (row < g.M) {
+                float* crow = g.C + (size_t)row * g.ldc + n0;
+#pragma unroll
+                for (int c0 = 0; c0 < GT_BN; c0 += 4) {
+                    if (n0 + c0 < g.N) {
+                        float o[4] = {sum[c0], sum[c0 + 1], sum[c0 + 2], sum[c0 + 3]};
+                        if (g.bias) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (n0 + c0 + q < g.N) o[q] += g.bias[n0 + c0 + q];
+                        }
+                        if (vec_ok && n0 + c0 + 4 <= g.N) {
+                            float4 w = make_float4(o[0], o[1], o[2], o[3]);
+                            if (g.beta1) {
+                                const float4 old = *reinterpret_cast<const float4*>(crow + c0);
+                                w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(crow + c0) = w;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (n0 + c0 + q < g.N) crow[c0 + q] = g.beta1 ? crow[c0 + q] + o[q] : o[q];
+                        }
+                    }
+                }
             }
         }
     }

@@ -486,7 +486,8 @@ def test_split_precision_tensor_core_gemm(cvb, f16):
     all four transpose combinations, accumulate and bias epilogues, leading dimensions wider than the rows."""
     from cyclevae_vc_b200._lib import check, lib, ptr
     g = torch.Generator().manual_seed(3)
-    tol = 2e-5 if f16 else 1.5e-4   # x sqrt(K); the TMEM accumulation chain rounds toward zero (error grows ~K)
+    tol = 5e-6 if f16 else 6e-5   # x sqrt(K): operand split 2^-22 / 2^-17 per product, max over the outputs (~4 sigma);
+    #                             K-slices of 128 are summed in fp32 registers, so the error does not grow ~K
     shapes = [(128, 128, 64, 0, 1), (6400, 3072, 486, 0, 1), (3072, 1024, 6400, 1, 0), (6400, 306, 3072, 0, 0),
               (200, 50, 100, 1, 1), (130, 66, 31, 1, 1), (257, 129, 65, 0, 0), (64, 1030, 777, 1, 0)]
     for (M, N, K, ta, tb) in shapes:
