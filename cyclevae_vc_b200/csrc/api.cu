@@ -176,6 +176,31 @@ size_t cvb_scratch_floats(const cvb_net* net, int B, int T, int training) {
     return f;
 }
 
+int cvb_recurrence_max_rows(const cvb_net* net, int training) {
+    // largest batch-row count (multiple of 8, <= 128) one launch of the tensor-core recurrence kernels holds at this
+    // network shape; 128 when only the fp32-FMA kernels apply (they tile the batch themselves)
+    if (!net || !want_tc()) return 128;
+    DeviceInfo di;
+    if (get_device_info(&di)) return 128;
+    static int cache_key[8], cache_val[8], n_cache = 0;
+    const int key = (net->hidden * 131 + net->out_dim) * 2 + (training ? 1 : 0);
+    for (int i = 0; i < n_cache; ++i)
+        if (cache_key[i] == key) return cache_val[i];
+    int best = 128;
+    for (int B = 128; B >= 8; B -= 8) {
+        if (gru_tc_supported(B, net->hidden, net->out_dim, di) && (!training || gru_tc_bwd_supported(B, net->hidden, net->out_dim, di))) {
+            best = B;
+            break;
+        }
+        if (B == 8) best = 128;
+    }
+    if (n_cache < 8) {
+        cache_key[n_cache] = key;
+        cache_val[n_cache++] = best;
+    }
+    return best;
+}
+
 int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, const float* y_in, const float* h_in,
                         const float* mask_conv_tm, const float* mask_gru_tm, int head_mode, int lat_dim, int training,
                         float* trj_out_bm, float* y_last, float* h_last, float* fe_ws, float* rec_ws, float* scratch,

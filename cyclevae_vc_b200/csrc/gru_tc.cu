@@ -52,10 +52,7 @@ __host__ __device__ inline TfLayout tf_layout(int B, int H, int G, int out, int 
     L.stage_bytes = 2u * L.half;
     L.w_chunk_bytes = 2u * (TF_NW / 8) * 1024u;                 // [hi: 12 row groups][lo: 12 row groups] x 1 KB
     L.slot_bytes = (uint32_t)L.MB * 8u * 96u;                   // [rows][24 floats]
-    uint32_t inbox = (uint32_t)TF_S * L.slot_bytes;             // also the staging of the partials being reduced (see the step order)
-    const int Q = (B * out + G - 1) / G;
-    const uint32_t red = (uint32_t)(G * (Q < 128 ? Q : 128)) * 4u;
-    if (inbox < red) inbox = red;
+    uint32_t inbox = (uint32_t)TF_S * L.slot_bytes;
     inbox = (inbox + 127u) & ~127u;
     const uint32_t fixed = L.stage_bytes + (uint32_t)L.nch * L.w_chunk_bytes + 8192u + 4096u + 8192u + inbox + 640u + 256u;
     int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
@@ -137,7 +134,11 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     uint8_t* sB3 = smem + L.off_b3;
     uint8_t* sA2 = smem + L.off_a2;
     float* inbox = reinterpret_cast<float*>(smem + L.off_inbox);   // [S (from)][MB*8][24]
-    float* sRed = inbox;                                           // [G][w], aliases the (idle) inbox
+    // [G][w] staging of the partials being reduced: aliases the y operand buffer.  The reducers of round r work between
+    // "counter A >= G(r+1)" and their own arrival on counter B; the y copy of step r is issued only after counter B is
+    // complete, and its MMAs retire before this CTA's next arrival on counter A -- the two uses never overlap.  (The
+    // inbox must NOT be reused: the peers' exchange copies land as soon as THEIR h chunks are consumed.)
+    float* sRed = reinterpret_cast<float*>(smem + L.off_ybuf);
     float* sBh = reinterpret_cast<float*>(smem + L.off_bias);      // [3][8] b_hh of the own units
     float* sPs = sBh + 32;                                         // [128] partial sums of the reducers
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
@@ -640,7 +641,10 @@ static bool fwd_runnable(int B, int H, int out, const DeviceInfo& di, TfLayout* 
     TfLayout L = tf_layout(B, H, G, out, di.max_smem_optin);
     if (ok < 0) {
         ok = 0;
+        const int Q = (B * out + G - 1) / G;
+        const uint32_t red_bytes = (uint32_t)(G * (Q < 128 ? Q : 128)) * 4u;
         if (L.NS >= 2 && (int)L.total <= di.max_smem_optin && (uint32_t)L.NS * L.stage_bytes >= (uint32_t)TF_S * L.slot_bytes &&
+            red_bytes <= L.stage_bytes &&
             cudaFuncSetAttribute(k_gru_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(G);

@@ -34,6 +34,7 @@ __all__ = ["initialize", "TwoSidedDilConv1d", "GRU_RNN", "TWFSEloss", "sampling_
            "reparam_concat", "kl_per_utt", "mcd_l1_per_utt", "draw_dropout_masks", "LOG_VAR_FLOOR"]
 
 LOG_VAR_FLOOR = -13.815510557964274104107948728106  # gru_vae.py:412
+MAX_ROWS_PER_LAUNCH = 128   # batch rows of one persistent recurrence launch (= the M of a tcgen05 MMA)
 
 
 def _stream() -> int:
@@ -287,7 +288,25 @@ class GRU_RNN(nn.Module):
             head = _lib.HEAD_CLAMP
         else:
             head = _lib.HEAD_NONE
-        trj, y_last, h_last = _GruRnnFn.apply(self, head, int(lat_dim), xb, y0, h0, mc, mg, *self._param_list())
+        max_rows = MAX_ROWS_PER_LAUNCH
+        if B > 64:
+            params = self._param_list()
+            max_rows = int(lib.cvb_recurrence_max_rows(C.byref(self._net_struct(params)),
+                                                       1 if (torch.is_grad_enabled() and any(p.requires_grad for p in params)) else 0))
+        if B <= max_rows:
+            trj, y_last, h_last = _GruRnnFn.apply(self, head, int(lat_dim), xb, y0, h0, mc, mg, *self._param_list())
+        else:
+            # utterances never interact inside GRU_RNN.forward: wide batches (stage-6 conversion of many utterances at
+            # once) run as independent slices of the row count one persistent tensor-core launch holds
+            n_sl = -(-B // max_rows)
+            per = -(-B // n_sl)
+            outs = []
+            for lo in range(0, B, per):
+                hi = min(B, lo + per)
+                outs.append(_GruRnnFn.apply(self, head, int(lat_dim), xb[lo:hi], y0[lo:hi], None if h0 is None else h0[lo:hi],
+                                            None if mc is None else mc[:, lo:hi].contiguous(),
+                                            None if mg is None else mg[:, lo:hi].contiguous(), *self._param_list()))
+            trj, y_last, h_last = (torch.cat([o[i] for o in outs], 0) for i in range(3))
         if not batched:
             trj = trj.squeeze(0)
         return trj, y_last.unsqueeze(1), h_last.unsqueeze(0)

@@ -510,3 +510,25 @@ def test_split_precision_tensor_core_gemm(cvb, f16):
             err = (Cm[:, :N].double() - ref).abs().max().item()
             assert err < tol * scale, (M, N, K, ta, tb, beta1, err)
             assert torch.equal(Cm[:, N:], C0[:, N:])   # nothing written past the row
+
+
+def test_tensor_core_forward_any_row_count(cvb):
+    """Batch-row counts that are not multiples of the 8-row operand groups, the widest single launch, and a wide batch that
+    the host slices (cvb_recurrence_max_rows): tensor-core forward == fp32-FMA forward, eval mode, two passes each (the
+    exchange buffers are reused across launches, so stale contents must never leak into live rows)."""
+    torch.manual_seed(0)
+    enc = cvb.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, do_prob=0.5, scale_out_flag=False).cuda().eval()
+    enc.apply(cvb.initialize)
+    for B, T in ((17, 2), (17, 9), (43, 12), (86, 12), (128, 6), (300, 5)):
+        x = torch.randn(B, T, 54, device="cuda")
+        y0 = 0.1 * torch.randn(B, 1, 64, device="cuda")
+        h0 = 0.3 * torch.randn(1, B, 1024, device="cuda")
+        with torch.no_grad():
+            os.environ["CVB_RECURRENCE"] = "exact"
+            try:
+                o_e, y_e, h_e = enc(x, y0, h_in=h0, clamp_vae=True, lat_dim=32)
+            finally:
+                os.environ.pop("CVB_RECURRENCE", None)
+            for _ in range(2):
+                o_t, y_t, h_t = enc(x, y0, h_in=h0, clamp_vae=True, lat_dim=32)
+                assert _maxabs(o_t, o_e) < 2e-5 and _maxabs(h_t, h_e) < 2e-5 and _maxabs(y_t, y_e) < 2e-5, (B, T)
