@@ -299,7 +299,11 @@ def run_native(args):
                          "frac": achieved / peak_tf, "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": n_l,
                          "algorithmic_flops_per_launch": fl, "peak_source": peak_src,
                          "share_of_step": {k: v[0] / args.steps / ms for k, v in prof.items()},
-                         "note": "fp32 FMA variant of the recurrence kernel in this build; the denominator is the dense bf16 tensor peak"},
+                         "us_per_recurrent_step": avg_ms * 1e3 / T,
+                         "note": "split-precision tcgen05 recurrence (fp16/bf16 hi+lo operands, 2 MMAs per K step, fp32 TMEM "
+                                 "accumulation); `achieved` counts ALGORITHMIC fp32-equivalent FLOPs (the issued 16-bit MMA FLOPs are "
+                                 "3x) against the dense bf16 peak; the kernel is bound by the two grid-wide exchanges of every "
+                                 "recurrent step (us_per_recurrent_step), not by the tensor pipe"},
         }
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
