@@ -218,8 +218,13 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     float* xc = fe_ws + frontend_xc_offset(net, B, T);
     if (int rc = frontend_fwd(net, B, T, x_bm, mask_conv_tm, fe_ws, xc, s)) return rc;
     float* gx = scratch + FS.gx;
-    if (int rc = fill_rows(s, gx, TB, 3 * H, 3 * H, net->b_ih)) return rc;
-    if (int rc = gemm_rm(s, false, true, (int)TB, 3 * H, C, 1.f, xc, C, net->w_ih, TI, 1.f, gx, 3 * H)) return rc;
+    if (want_tc_gemm() && gemm_tc_eligible((int)TB, 3 * H, C)) {
+        // gx = xc W_x^T + b_ih: bias in the GEMM epilogue (no fill pass, no read-modify-write of the 3H-wide rows)
+        if (int rc = gemm_tc(s, false, true, (int)TB, 3 * H, C, xc, C, net->w_ih, TI, false, net->b_ih, gx, 3 * H, true)) return rc;
+    } else {
+        if (int rc = fill_rows(s, gx, TB, 3 * H, 3 * H, net->b_ih)) return rc;
+        if (int rc = gemm_rm(s, false, true, (int)TB, 3 * H, C, 1.f, xc, C, net->w_ih, TI, 1.f, gx, 3 * H)) return rc;
+    }
     float* hs = rec_ws + RL.hs;
     float* ys = rec_ws + RL.ys;
     if (h_in)
@@ -324,10 +329,17 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
     a.T = T;
     a.H = H;
     a.out = out;
+    bool db_in_kernel = false;
     {
         DeviceInfo di;
         if (int rc = get_device_info(&di)) return rc;
         if (want_tc() && gru_tc_bwd_supported(B, H, out, di)) {
+            if (gr) {   // the recurrence sums the GRU bias gradients itself (no colsum passes over dgi / dghn)
+                a.dbih = gr->b_ih;
+                a.dbhh = gr->b_hh;
+                a.db_accumulate = gr->accumulate;
+                db_in_kernel = true;
+            }
             if (int rc = gru_ar_bwd_tc(a, scratch + BS.tc, s)) return rc;
         } else {
             if (int rc = gru_ar_bwd_exact(a, s)) return rc;
@@ -344,15 +356,21 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
             if (int rc = gemm_rm(s, true, false, 2 * H, H, iTB, 1.f, dgi, 3 * H, hs, H, beta, gr->w_hh, H, true)) return rc;
             if (int rc = gemm_rm(s, true, false, H, H, iTB, 1.f, dghn, H, hs, H, beta, gr->w_hh + (size_t)2 * H * H, H, true)) return rc;
         }
-        if (gr->b_hh) {
+        if (gr->b_hh && !db_in_kernel) {
             if (int rc = colsum(s, dgi, iTB, 2 * H, 3 * H, gr->b_hh, acc)) return rc;
             if (int rc = colsum(s, dghn, iTB, H, H, gr->b_hh + 2 * H, acc)) return rc;
         }
         if (gr->w_ih) {
-            if (int rc = gemm_rm(s, true, false, 3 * H, C, iTB, 1.f, dgi, 3 * H, xc, C, beta, gr->w_ih, TI, true)) return rc;
-            if (int rc = gemm_rm(s, true, false, 3 * H, out, iTB, 1.f, dgi, 3 * H, ys, out, beta, gr->w_ih + C, TI, true)) return rc;
+            if (want_tc_gemm() && gemm_tc_eligible(3 * H, TI, iTB)) {
+                // dW_ih = dgi^T [xc | y_prev]: one product, the two sources meet in the operand pass
+                if (int rc = gemm_tc(s, true, false, 3 * H, TI, iTB, dgi, 3 * H, xc, C, beta == 1.f, nullptr, gr->w_ih, TI, false, ys, out, C))
+                    return rc;
+            } else {
+                if (int rc = gemm_rm(s, true, false, 3 * H, C, iTB, 1.f, dgi, 3 * H, xc, C, beta, gr->w_ih, TI, true)) return rc;
+                if (int rc = gemm_rm(s, true, false, 3 * H, out, iTB, 1.f, dgi, 3 * H, ys, out, beta, gr->w_ih + C, TI, true)) return rc;
+            }
         }
-        if (gr->b_ih)
+        if (gr->b_ih && !db_in_kernel)
             if (int rc = colsum(s, dgi, iTB, 3 * H, 3 * H, gr->b_ih, acc)) return rc;
         const float* o_tm = mask_gru_tm ? rec_ws + RL.o : hs + (size_t)B * H;
         const float* dy1 = dy_tot + (size_t)B * out;

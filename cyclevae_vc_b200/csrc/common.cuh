@@ -64,10 +64,11 @@ static inline int tot_in_dim(const cvb_net* n) { return conv_dim(n) + n->out_dim
 // (bf16 hi/lo).  Small products and CVB_GEMM=cublas go to cuBLAS fp32.
 int gemm_rm(cudaStream_t s, bool transA, bool transB, int M, int N, int K, float alpha,
             const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc, bool grad = false);
+bool want_tc_gemm();   // false under CVB_GEMM=cublas
 // split-precision tcgen05 GEMM, gemm_tc.cu
 bool gemm_tc_eligible(int M, int N, int K);
 int gemm_tc(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-            bool beta1, const float* bias, float* C, int ldc, bool f16);
+            bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2 = nullptr, int ldb2 = 0, int N1 = 0);
 
 // elementwise / small kernels, elementwise.cu
 int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out, bool accumulate);

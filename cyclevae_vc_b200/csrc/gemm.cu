@@ -66,7 +66,7 @@ static int get_handle(cublasHandle_t* out) {
     return 0;
 }
 
-static bool want_tc_gemm() {
+bool want_tc_gemm() {
     const char* e = getenv("CVB_GEMM");
     return !(e && (e[0] == 'c' || e[0] == 'C'));
 }

@@ -34,7 +34,8 @@ constexpr int GT_THREADS = 256;
 // out: [ceil(R/128)][ceil(K/64)][2 parts][16][8][8][8] 16-bit.
 template <bool F16>
 __global__ void __launch_bounds__(256) k_split_tiles(const float* __restrict__ X, int ld, int R, int K, int transposed, int KC,
-                                                     uint16_t* __restrict__ out) {
+                                                     uint16_t* __restrict__ out, const float* __restrict__ X2, int ld2, int R1) {
+    // transposed sources may be two matrices side by side: rows [0, R1) from X, rows [R1, R) from X2 (e.g. [xc | y] for dW_ih)
     __shared__ float T[GT_BM * (GT_BK + 1)];
     const int rt = blockIdx.y, kc = blockIdx.x;
     const int r0 = rt * GT_BM, k0 = kc * GT_BK;
@@ -48,7 +49,9 @@ __global__ void __launch_bounds__(256) k_split_tiles(const float* __restrict__ X
         for (int i = threadIdx.x; i < GT_BM * GT_BK; i += 256) {
             const int k = i >> 7, r = i & 127;
             const bool ok = (r0 + r < R) && (k0 + k < K);
-            T[r * (GT_BK + 1) + k] = ok ? X[(size_t)(k0 + k) * ld + r0 + r] : 0.f;
+            float v = 0.f;
+            if (ok) v = (r0 + r < R1) ? X[(size_t)(k0 + k) * ld + r0 + r] : X2[(size_t)(k0 + k) * ld2 + (r0 + r - R1)];
+            T[r * (GT_BK + 1) + k] = v;
         }
     }
     __syncthreads();
@@ -277,21 +280,23 @@ bool gemm_tc_eligible(int M, int N, int K) {
 
 // C[M,N] = op(A) op(B) (+ C if beta1) (+ bias[N]);  A: [M,K] (lda) or [K,M] if transA;  B: [N,K] (ldb) if transB else [K,N].
 int gemm_tc(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-            bool beta1, const float* bias, float* C, int ldc, bool f16) {
+            bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2, int ldb2, int N1) {
+    CVB_REQUIRE(!B2 || !transB, "gemm_tc: a second B source needs B stored [K,N]");
+    if (!B2) N1 = N;
     const int MT = ceil_div(M, GT_BM), NTl = ceil_div(N, GT_BN), KC = ceil_div(K, GT_BK);
     uint16_t *At, *Bt;
     if (int rc = ws_get(0, (size_t)MT * KC * 2 * GT_BLOCK_ELEMS, &At)) return rc;
     if (int rc = ws_get(1, (size_t)NTl * KC * 2 * GT_BLOCK_ELEMS, &Bt)) return rc;
     // A as [M rows, K]: stored [M,K] when !transA, [K,M] when transA.  B as [N rows, K]: stored [N,K] when transB.
     if (f16) {
-        k_split_tiles<true><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At);
+        k_split_tiles<true><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M);
         CVB_LAUNCH_CHECK();
-        k_split_tiles<true><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt);
+        k_split_tiles<true><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1);
         CVB_LAUNCH_CHECK();
     } else {
-        k_split_tiles<false><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At);
+        k_split_tiles<false><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M);
         CVB_LAUNCH_CHECK();
-        k_split_tiles<false><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt);
+        k_split_tiles<false><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1);
         CVB_LAUNCH_CHECK();
     }
     DeviceInfo di;

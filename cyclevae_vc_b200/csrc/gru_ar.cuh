@@ -37,6 +37,10 @@ struct GruBwdArgs {
     float* part;    // [G,B,out]
     unsigned* bar;
     int B, T, H, out;
+    // tensor-core kernel only: bias gradients summed inside the recurrence (db_ih = sum dgi, db_hh = sum dgh); null = not wanted
+    float* dbih = nullptr;
+    float* dbhh = nullptr;
+    int db_accumulate = 0;
 };
 
 int gru_exact_grid(int H);

@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 *reinterpret_cast<uint4*>(hdst + hx_part + off) = hl;
             }
             if (etid == 0) TF_TRACE(7);
-            fence_proxy_async_all();   // own generic writes of h_t -> visible to the peers' bulk copies (async proxy)
+            fence_proxy_async_global();   // own generic writes of h_t -> visible to the peers' bulk copies (async proxy)
             if (etid == 0) TF_TRACE(8);
             if (out > 32) {   // second half of the partial accumulator (the aux warps drain [0, 32))
                 mbar_wait(part_full, (uint32_t)t & 1);
@@ -510,6 +510,17 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         const int q_n = max(0, min(Q, n_pairs - q_lo));
         const uint32_t taddr = tmem + ((uint32_t)((warp - 8) * 32) << 16) + TF_COL_P;
         constexpr int LB = 8;
+        // per-thread constants of the first (normally the only) block of pairs: no division / bias load inside the rounds
+        const int w0 = min(128, q_n);
+        const int nsub0 = w0 > 0 ? 128 / w0 : 1;
+        const int sub0 = w0 > 0 ? rt / w0 : 0, qi0 = w0 > 0 ? rt - sub0 * w0 : 0;
+        int o0 = 0, bb0 = 0;
+        float bias0 = 0.f, y_deferred = 0.f;
+        if (rt < w0) {
+            o0 = (q_lo + rt) / B;
+            bb0 = (q_lo + rt) - o0 * B;
+            bias0 = f.bo[o0];
+        }
         // round 0 publishes y_in; round r >= 1 reduces the partials of step r-1 into y_{r-1}
         for (int round = 0; round <= T; ++round) {
             const int t = round;   // trace row
@@ -568,30 +579,46 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                     named_bar_sync(2, 128);
                 }
                 // sum over the CTAs: nsub threads per pair, each a fixed subset, combined in fixed order (deterministic)
-                const int nsub = 128 / w;
-                const int sub = rt / w, qi = rt - sub * w;
+                const bool hoisted = (qb == 0);
+                const int nsub = hoisted ? nsub0 : 128 / w;
+                const int sub = hoisted ? sub0 : rt / w, qi = hoisted ? qi0 : rt - (rt / w) * w;
                 if (round > 0) {
                     if (sub < nsub) {
-                        float s0 = 0.f, s1 = 0.f;
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                        const float* p = sRed + sub * w + qi;
+                        const int stp = nsub * w;
                         int cc = sub;
-                        for (; cc + nsub < G; cc += 2 * nsub) {
-                            s0 += sRed[cc * w + qi];
-                            s1 += sRed[(cc + nsub) * w + qi];
+                        for (; cc + 3 * nsub < G; cc += 4 * nsub, p += 4 * stp) {
+                            s0 += p[0];
+                            s1 += p[stp];
+                            s2 += p[2 * stp];
+                            s3 += p[3 * stp];
                         }
-                        if (cc < G) s0 += sRed[cc * w + qi];
-                        sPs[sub * w + qi] = s0 + s1;
+                        for (; cc < G; cc += nsub, p += stp) s0 += p[0];
+                        sPs[sub * w + qi] = (s0 + s1) + (s2 + s3);
                     }
                     named_bar_sync(2, 128);
                 }
                 if (rt < w) {
-                    const int qq = q_lo + qb + rt;
-                    const int o = qq / B, bb = qq - o * B;   // pair order of `part` is [o][b]
+                    int o, bb;
+                    float bias;
+                    if (hoisted) {
+                        o = o0;
+                        bb = bb0;
+                        bias = bias0;
+                    } else {
+                        const int qq = q_lo + qb + rt;
+                        o = qq / B;   // pair order of `part` is [o][b]
+                        bb = qq - o * B;
+                        bias = f.bo[o];
+                    }
                     float yv;
                     if (round > 0) {
                         float sacc = sPs[rt];
                         for (int k = 1; k < nsub; ++k) sacc += sPs[k * w + rt];
-                        yv = sacc + f.bo[o];
-                        ydst[(size_t)bb * out + o] = yv;
+                        yv = sacc + bias;
+                        if (hoisted) y_deferred = yv;   // the fp32 output is stored after the release (only later kernels read it)
+                        else ydst[(size_t)bb * out + o] = yv;
                     } else {
                         yv = f.ys[(size_t)bb * out + o];
                     }
@@ -604,9 +631,10 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 if (qb + 128 < q_n) named_bar_sync(2, 128);
             }
             if (rt == 0) TF_TRACE(21);
-            fence_proxy_async_all();
+            fence_proxy_async_global();
             named_bar_sync(2, 128);
             if (rt == 0) red_release_gpu_add(ctrB, 1u);
+            if (round > 0 && rt < w0) ydst[(size_t)bb0 * out + o0] = y_deferred;
             if (rt == 0) TF_TRACE(22);
         }
     }

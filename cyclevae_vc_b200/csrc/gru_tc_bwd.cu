@@ -56,7 +56,7 @@ __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int ou
     const uint32_t inbox = (uint32_t)S * L.slot_bytes;
     const int Q = (B * out + G - 1) / G;
     const uint32_t aux = (((uint32_t)(G * (Q < 128 ? Q : 128)) * 4u) + 127u) & ~127u;   // staging of the partials being reduced
-    const uint32_t fixed = 2u * L.w_part_bytes + 2u * inbox + 16384u + 4096u + 8192u + aux + 256u;
+    const uint32_t fixed = 2u * L.w_part_bytes + 2u * inbox + 16384u + 4096u + 8192u + aux + 768u;
     int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
     L.NS = ns > 6 ? 6 : ns;
     const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
@@ -69,7 +69,7 @@ __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int ou
     L.off_b3 = L.off_b2 + 4096u;        // [2 parts][8 n blocks][4 kblk][8][8] bf16: W_y rows of the own units
     L.off_aux = L.off_b3 + 8192u;
     L.off_bar = L.off_aux + aux;
-    L.total = L.off_bar + 256u;
+    L.total = L.off_bar + 256u + 512u;   // mbarriers + tmem slot | [128] partial sums of the reducers
     return L;
 }
 
@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
         float carry[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) carry[q] = act ? f.dhc[(size_t)b * H + u0 + q] : 0.f;
+        float bsum = 0.f;   // lane i: sum over (t, rows of this warp) of value i of [dar 8 | daz 8 | dan 8 | dan*r 8]
+        const bool want_db = f.dbih != nullptr || f.dbhh != nullptr;
         for (int n = 0; n <= T; ++n) {
             const int t = T - 1 - n;
             const size_t row = (size_t)(t < 0 ? 0 : t) * B + (act ? b : 0);
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 }
             }
             if (etid == 0) TB_TRACE(7);
-            fence_proxy_async_all();   // own generic writes of dgh_t -> visible to the peers' bulk copies (async proxy)
+            fence_proxy_async_global();   // own generic writes of dgh_t -> visible to the peers' bulk copies (async proxy)
             if (etid == 0) TB_TRACE(8);
             if (out > 32) {   // second half of the partial accumulator (the aux warps drain [0, 32))
                 mbar_wait(part_full, (uint32_t)n & 1);
@@ -473,6 +475,31 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 *reinterpret_cast<float4*>(gn) = make_float4(dgnr[0], dgnr[1], dgnr[2], dgnr[3]);
                 *reinterpret_cast<float4*>(gn + 4) = make_float4(dgnr[4], dgnr[5], dgnr[6], dgnr[7]);
             }
+            if (want_db) {   // bias gradients: butterfly sums over the rows of the warp, lane i keeps value i (fixed order)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float v = (i < 8) ? dgr[i & 7] : (i < 16) ? dgz[i & 7] : (i < 24) ? dgn[i & 7] : dgnr[i & 7];
+                    const float sres = warp_sum(v);   // inactive rows contribute zeros
+                    if (lane == i) bsum += sres;
+                }
+            }
+        }
+        if (want_db) {
+            // every CTA of the cluster is past its last exchange: the staging buffer is idle
+            stage[(warp - 4) * 32 + lane] = bsum;
+            named_bar_sync(3, 128);
+            if (etid < 32) {
+                const float tot = (stage[etid] + stage[32 + etid]) + (stage[64 + etid] + stage[96 + etid]);
+                const int grp = etid >> 3, u = u0 + (etid & 7);
+                if (f.dbih && grp < 3) {   // db_ih = sum [dar, daz, dan]
+                    float* d = f.dbih + (size_t)grp * H + u;
+                    *d = f.db_accumulate ? *d + tot : tot;
+                }
+                if (f.dbhh && grp != 2) {  // db_hh = sum [dar, daz, dan*r]
+                    float* d = f.dbhh + (size_t)(grp == 3 ? 2 : grp) * H + u;
+                    *d = f.db_accumulate ? *d + tot : tot;
+                }
+            }
         }
     } else if (warp >= 8) {
         // ================= aux: dy reduction + publication, drain of the partial accumulator ============
@@ -482,9 +509,22 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
         const int q_n = max(0, min(Q, n_pairs - q_lo));
         const uint32_t taddr = tmem + ((uint32_t)((warp - 8) * 32) << 16) + TB_COL_P;
         constexpr int LB = 8;   // independent loads in flight per thread
+        // per-thread constants of the first (normally the only) block of pairs: no division inside the steps
+        const int w0 = min(128, q_n);
+        const int nsub0 = w0 > 0 ? 128 / w0 : 1;
+        const int sub0 = w0 > 0 ? rt / w0 : 0, qi0 = w0 > 0 ? rt - sub0 * w0 : 0;
+        int o0 = 0, bb0 = 0;
+        if (rt < w0) {
+            o0 = (q_lo + rt) / B;
+            bb0 = (q_lo + rt) - o0 * B;
+        }
+        float* sPs = reinterpret_cast<float*>(smem + L.off_bar + 256);   // [128] partial sums (behind the mbarriers)
         for (int n = 0; n <= T; ++n) {
             const int t = T - 1 - n;
             float* dyt = f.dy_tot + (size_t)(t + 1) * n_pairs;
+            // the head's dY of this thread's pair: fetched before the wait, only this thread ever modifies it
+            float dy_base = (rt < w0) ? __ldcg(dyt + (size_t)bb0 * out + o0) : 0.f;
+            float dy_deferred = 0.f;
             uint16_t* dyx = a.dyx + (size_t)(n & 1) * 2 * dy_part;
             if (n > 0) {
                 if (rt == 0) spin_until(ctrA, (unsigned)G * (unsigned)n);
@@ -533,23 +573,46 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                     if (rt == 0) TB_TRACE(27);
                     named_bar_sync(2, 128);
                 }
-                if (rt < w) {
-                    const int qq = q_lo + qb + rt;
-                    const int o = qq / B, bb = qq - o * B;   // pair order of `part` is [o][b]
-                    float* dyp = dyt + (size_t)bb * out + o;
-                    float dyv = __ldcg(dyp);
-                    if (n > 0) {
+                // sum over the CTAs: nsub threads per pair, each a fixed subset, combined in fixed order (deterministic)
+                const bool hoisted = (qb == 0);
+                const int nsub = hoisted ? nsub0 : 128 / w;
+                const int sub = hoisted ? sub0 : rt / w, qi = hoisted ? qi0 : rt - (rt / w) * w;
+                if (n > 0) {
+                    if (sub < nsub) {
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        int cc = 0;
-                        for (; cc + 3 < G; cc += 4) {
-                            s0 += sRed[(cc + 0) * w + rt];
-                            s1 += sRed[(cc + 1) * w + rt];
-                            s2 += sRed[(cc + 2) * w + rt];
-                            s3 += sRed[(cc + 3) * w + rt];
+                        const float* p = sRed + sub * w + qi;
+                        const int stp = nsub * w;
+                        int cc = sub;
+                        for (; cc + 3 * nsub < G; cc += 4 * nsub, p += 4 * stp) {
+                            s0 += p[0];
+                            s1 += p[stp];
+                            s2 += p[2 * stp];
+                            s3 += p[3 * stp];
                         }
-                        for (; cc < G; ++cc) s0 += sRed[cc * w + rt];
-                        dyv += (s0 + s1) + (s2 + s3);
-                        *dyp = dyv;
+                        for (; cc < G; cc += nsub, p += stp) s0 += p[0];
+                        sPs[sub * w + qi] = (s0 + s1) + (s2 + s3);
+                    }
+                    named_bar_sync(2, 128);
+                }
+                if (rt < w) {
+                    int o, bb;
+                    float dyv;
+                    if (hoisted) {
+                        o = o0;
+                        bb = bb0;
+                        dyv = dy_base;
+                    } else {
+                        const int qq = q_lo + qb + rt;
+                        o = qq / B;   // pair order of `part` is [o][b]
+                        bb = qq - o * B;
+                        dyv = __ldcg(dyt + (size_t)bb * out + o);
+                    }
+                    if (n > 0) {
+                        float sacc = sPs[rt];
+                        for (int k = 1; k < nsub; ++k) sacc += sPs[k * w + rt];
+                        dyv += sacc;
+                        if (hoisted) dy_deferred = dyv;   // the fp32 total is stored after the release (only later kernels read it)
+                        else dyt[(size_t)bb * out + o] = dyv;
                     }
                     if (t >= 0) {
                         uint16_t hi, lo;
@@ -562,10 +625,11 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 if (qb + 128 < q_n) named_bar_sync(2, 128);
             }
             if (rt == 0) TB_TRACE(21);
-            fence_proxy_async_all();
+            fence_proxy_async_global();
             named_bar_sync(2, 128);
             if (rt == 0) red_release_gpu_add(ctrB, 1u);
             if (rt == 0) TB_TRACE(22);
+            if (n > 0 && rt < w0) dyt[(size_t)bb0 * out + o0] = dy_deferred;
             if (t < 0) break;
             // drain D3 (partial of the y feedback of step t, this CTA's units) into part[c][o][b]
             mbar_wait(part_full, (uint32_t)n & 1);
