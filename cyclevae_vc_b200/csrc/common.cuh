@@ -67,8 +67,15 @@ int gemm_rm(cudaStream_t s, bool transA, bool transB, int M, int N, int K, float
 bool want_tc_gemm();   // false under CVB_GEMM=cublas
 // split-precision tcgen05 GEMM, gemm_tc.cu
 bool gemm_tc_eligible(int M, int N, int K);
+// operand = virtual im2col of a dilated conv on the flattened padded grid: element (row r, column tap*ci + c) is
+// src[(r + tap*dshift)*ci + c] (src already offset to tap 0 of row 0)
+struct ConvGather {
+    int ci;
+    int dshift;
+};
 int gemm_tc(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-            bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2 = nullptr, int ldb2 = 0, int N1 = 0);
+            bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2 = nullptr, int ldb2 = 0, int N1 = 0,
+            const ConvGather* gA = nullptr, const ConvGather* gB = nullptr);
 
 // elementwise / small kernels, elementwise.cu
 int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out, bool accumulate);

@@ -52,8 +52,12 @@ size_t frontend_xc_offset(const cvb_net* n, int B, int T) { return fe_geom(n, B,
 size_t frontend_bwd_scratch_floats(const cvb_net* n, int B, int T) {
     FeGeom g = fe_geom(n, B, T);
     size_t mx = 0;
-    for (int i = 0; i < g.L; ++i) mx = mx > (size_t)g.k * g.C[i + 1] * g.C[i] ? mx : (size_t)g.k * g.C[i + 1] * g.C[i];
-    return g.wr_off[0] + round_up_sz(mx, 4);
+    size_t gmx = 0;   // G = dout Wcat of a tap-fused layer: [rows][k*ci]
+    for (int i = 0; i < g.L; ++i) {
+        mx = mx > (size_t)g.k * g.C[i + 1] * g.C[i] ? mx : (size_t)g.k * g.C[i + 1] * g.C[i];
+        gmx = gmx > g.R * g.k * g.C[i] ? gmx : g.R * g.k * g.C[i];
+    }
+    return g.wr_off[0] + round_up_sz(mx, 4) + round_up_sz(gmx, 4);
 }
 
 // xp[b, pad+t, i] = sum_j Ws[i, j] x[b, t, j] + bs[i]   (or a copy when there is no scale_in)
@@ -129,6 +133,49 @@ __global__ void k_unrepack_dw(int co, int ci, int k, const float* __restrict__ d
     }
 }
 
+// W [co][ci][k] -> Wcat [co][k*ci]  (column tap*ci + c): the B operand of the tap-fused product
+__global__ void k_repack_wcat(int co, int ci, int k, const float* __restrict__ W, float* __restrict__ Wc) {
+    size_t n = (size_t)co * ci * k;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t o = idx / ((size_t)k * ci);
+        int kk = (int)(idx - o * k * ci);
+        int j = kk / ci, c = kk - j * ci;
+        Wc[idx] = W[(o * ci + c) * k + j];
+    }
+}
+// dWcat [co][k*ci] -> dW [co][ci][k]
+__global__ void k_unrepack_dwcat(int co, int ci, int k, const float* __restrict__ dWc, float* __restrict__ dW, int accumulate) {
+    size_t n = (size_t)co * ci * k;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t rem = idx / k;   // o*ci + c
+        int j = (int)(idx - rem * k);
+        size_t o = rem / ci;
+        int c = (int)(rem - o * ci);
+        float v = dWc[o * k * ci + (size_t)j * ci + c];
+        dW[idx] = accumulate ? dW[idx] + v : v;
+    }
+}
+// din[m + r + (j-half)*d][c] += G[r][j*ci + c] over the taps, as a gather (no atomics): grid row p, channel c
+__global__ void k_col2im_add(size_t R, size_t rows, size_t m, int ci, int k, int d, const float* __restrict__ G, float* __restrict__ din) {
+    const int half = (k - 1) / 2;
+    size_t n = R * ci;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t p = idx / ci;
+        int c = (int)(idx - p * ci);
+        float v = 0.f;
+        for (int j = 0; j < k; ++j) {
+            long r = (long)p - (long)m - (long)(j - half) * d;
+            if (r >= 0 && (size_t)r < rows) v += G[(size_t)r * k * ci + (size_t)j * ci + c];
+        }
+        din[idx] += v;
+    }
+}
+
+// the k taps of a layer as ONE tensor-core product over the virtual im2col (K = k*ci) when that is the faster path
+static bool conv_fused(size_t rows, int co, int ci, int k) {
+    return want_tc_gemm() && rows >= 128 && co >= 128 && (double)rows * co * ci * k >= 5.0e8;
+}
+
 // xc_tm[t,b,c] = xcp[b,pad+t,c] * mask_tm[t,b,c]
 __global__ void k_compact_mask(int B, int T, int C, int pad, const float* __restrict__ xcp,
                                const float* __restrict__ mask, float* __restrict__ xc) {
@@ -183,11 +230,20 @@ int frontend_fwd(const cvb_net* net, int B, int T, const float* x_bm, const floa
         size_t m = (size_t)half * d;  // rows skipped at both ends of the flattened grid
         CVB_REQUIRE(g.R > 2 * m, "sequence too short for the receptive field");
         float* Wr = fe_ws + g.wr_off[i];
-        k_repack_w<<<grid1d((size_t)co * ci * g.k), 256, 0, s>>>(co, ci, g.k, net->conv_w[i], Wr);
-        CVB_LAUNCH_CHECK();
         const float* in = fe_ws + g.buf_off[i];
         float* out = fe_ws + g.buf_off[i + 1];
         size_t rows = g.R - 2 * m;
+        if (conv_fused(rows, co, ci, g.k)) {
+            k_repack_wcat<<<grid1d((size_t)co * ci * g.k), 256, 0, s>>>(co, ci, g.k, net->conv_w[i], Wr);
+            CVB_LAUNCH_CHECK();
+            ConvGather ga{ci, d};
+            if (int rc = gemm_tc(s, false, true, (int)rows, co, g.k * ci, in + (m - (size_t)half * d) * ci, ci, Wr, g.k * ci, false,
+                                 net->conv_b[i], out + m * co, co, true, nullptr, 0, 0, &ga, nullptr))
+                return rc;
+            continue;
+        }
+        k_repack_w<<<grid1d((size_t)co * ci * g.k), 256, 0, s>>>(co, ci, g.k, net->conv_w[i], Wr);
+        CVB_LAUNCH_CHECK();
         if (int rc = fill_rows(s, out + m * co, rows, co, co, net->conv_b[i])) return rc;
         for (int j = 0; j < g.k; ++j) {
             long shift = (long)(j - half) * d;
@@ -210,6 +266,8 @@ int frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const floa
     int acc = gr ? gr->accumulate : 0;
     float* dbuf = scratch;  // same offsets as buf_i
     float* dWr = scratch + g.wr_off[0];
+    size_t dwr_floats = 0;
+    for (int i = 0; i < g.L; ++i) dwr_floats = dwr_floats > (size_t)g.k * g.C[i + 1] * g.C[i] ? dwr_floats : (size_t)g.k * g.C[i + 1] * g.C[i];
     if (int rc = zero_floats(s, dbuf, g.wr_off[0])) return rc;
     int CL = g.C[g.L];
     k_expand_mask<<<grid1d((size_t)B * T * CL), 256, 0, s>>>(B, T, CL, g.pad, dxc_tm, mask_conv_tm, dbuf + g.buf_off[g.L]);
@@ -224,6 +282,23 @@ int frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const floa
         float* din = dbuf + g.buf_off[i];
         bool want_w = gr && gr->conv_w[i];
         bool need_din = (i > 0) || dx_bm || (gr && (gr->scale_in_w || gr->scale_in_b));
+        if (conv_fused(rows, co, ci, g.k)) {   // Wr holds Wcat [co][k*ci] (written by the forward)
+            ConvGather gb{ci, d};
+            if (want_w) {   // dWcat = dout^T im2col(in)
+                if (int rc = gemm_tc(s, true, false, co, g.k * ci, (int)rows, dout, co, in + (m - (size_t)half * d) * ci, ci, false, nullptr,
+                                     dWr, g.k * ci, false, nullptr, 0, 0, nullptr, &gb))
+                    return rc;
+                k_unrepack_dwcat<<<grid1d((size_t)co * ci * g.k), 256, 0, s>>>(co, ci, g.k, dWr, gr->conv_w[i], acc);
+                CVB_LAUNCH_CHECK();
+            }
+            if (need_din) {   // G = dout Wcat, then the taps are gathered back onto the grid
+                float* G = dWr + round_up_sz(dwr_floats, 4);
+                if (int rc = gemm_tc(s, false, false, (int)rows, g.k * ci, co, dout, co, Wr, g.k * ci, false, nullptr, G, g.k * ci, false))
+                    return rc;
+                k_col2im_add<<<grid1d(g.R * ci), 256, 0, s>>>(g.R, rows, m, ci, g.k, d, G, din);
+                CVB_LAUNCH_CHECK();
+            }
+        } else {
         for (int j = 0; j < g.k; ++j) {
             long shift = (long)(j - half) * d;
             if (want_w)
@@ -238,6 +313,7 @@ int frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const floa
         if (want_w) {
             k_unrepack_dw<<<grid1d((size_t)co * ci * g.k), 256, 0, s>>>(co, ci, g.k, dWr, gr->conv_w[i], acc);
             CVB_LAUNCH_CHECK();
+        }
         }
         if (gr && gr->conv_b[i])
             if (int rc = colsum(s, dout, (int)rows, co, co, gr->conv_b[i], acc != 0)) return rc;

@@ -34,8 +34,12 @@ constexpr int GT_THREADS = 256;
 // out: [ceil(R/128)][ceil(K/64)][2 parts][16][8][8][8] 16-bit.
 template <bool F16>
 __global__ void __launch_bounds__(256) k_split_tiles(const float* __restrict__ X, int ld, int R, int K, int transposed, int KC,
-                                                     uint16_t* __restrict__ out, const float* __restrict__ X2, int ld2, int R1) {
-    // transposed sources may be two matrices side by side: rows [0, R1) from X, rows [R1, R) from X2 (e.g. [xc | y] for dW_ih)
+                                                     uint16_t* __restrict__ out, const float* __restrict__ X2, int ld2, int R1,
+                                                     int conv_ci, int conv_dshift) {
+    // transposed sources may be two matrices side by side: rows [0, R1) from X, rows [R1, R) from X2 (e.g. [xc | y] for dW_ih).
+    // conv_ci > 0: the operand is the virtual im2col of a dilated conv on the flattened padded grid (frontend.cu): logical
+    // element (row r, column kk = tap*ci + c) lives at X[(r + tap*conv_dshift)*ci + c]; `transposed` then only says which of
+    // (r, kk) is the tile's row index.
     __shared__ float T[GT_BM * (GT_BK + 1)];
     const int rt = blockIdx.y, kc = blockIdx.x;
     const int r0 = rt * GT_BM, k0 = kc * GT_BK;
@@ -43,14 +47,30 @@ __global__ void __launch_bounds__(256) k_split_tiles(const float* __restrict__ X
         for (int i = threadIdx.x; i < GT_BM * GT_BK; i += 256) {
             const int r = i >> 6, k = i & 63;
             const bool ok = (r0 + r < R) && (k0 + k < K);
-            T[r * (GT_BK + 1) + k] = ok ? X[(size_t)(r0 + r) * ld + k0 + k] : 0.f;
+            float v = 0.f;
+            if (ok) {
+                if (conv_ci > 0) {
+                    const int kk = k0 + k, tap = kk / conv_ci, cch = kk - tap * conv_ci;
+                    v = X[((size_t)(r0 + r) + (size_t)tap * conv_dshift) * conv_ci + cch];
+                } else {
+                    v = X[(size_t)(r0 + r) * ld + k0 + k];
+                }
+            }
+            T[r * (GT_BK + 1) + k] = v;
         }
     } else {
         for (int i = threadIdx.x; i < GT_BM * GT_BK; i += 256) {
             const int k = i >> 7, r = i & 127;
             const bool ok = (r0 + r < R) && (k0 + k < K);
             float v = 0.f;
-            if (ok) v = (r0 + r < R1) ? X[(size_t)(k0 + k) * ld + r0 + r] : X2[(size_t)(k0 + k) * ld2 + (r0 + r - R1)];
+            if (ok) {
+                if (conv_ci > 0) {   // tile row = kk (tap, channel), tile k = grid row
+                    const int kk = r0 + r, tap = kk / conv_ci, cch = kk - tap * conv_ci;
+                    v = X[((size_t)(k0 + k) + (size_t)tap * conv_dshift) * conv_ci + cch];
+                } else {
+                    v = (r0 + r < R1) ? X[(size_t)(k0 + k) * ld + r0 + r] : X2[(size_t)(k0 + k) * ld2 + (r0 + r - R1)];
+                }
+            }
             T[r * (GT_BK + 1) + k] = v;
         }
     }
@@ -280,23 +300,27 @@ bool gemm_tc_eligible(int M, int N, int K) {
 
 // C[M,N] = op(A) op(B) (+ C if beta1) (+ bias[N]);  A: [M,K] (lda) or [K,M] if transA;  B: [N,K] (ldb) if transB else [K,N].
 int gemm_tc(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-            bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2, int ldb2, int N1) {
+            bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2, int ldb2, int N1, const ConvGather* gA,
+            const ConvGather* gB) {
     CVB_REQUIRE(!B2 || !transB, "gemm_tc: a second B source needs B stored [K,N]");
+    CVB_REQUIRE(!gA || !transA, "gemm_tc: a conv-gathered A is addressed as [M,K]");
+    CVB_REQUIRE(!gB || (!transB && !B2), "gemm_tc: a conv-gathered B is addressed as [K,N]");
     if (!B2) N1 = N;
+    const int a_ci = gA ? gA->ci : 0, a_ds = gA ? gA->dshift : 0, b_ci = gB ? gB->ci : 0, b_ds = gB ? gB->dshift : 0;
     const int MT = ceil_div(M, GT_BM), NTl = ceil_div(N, GT_BN), KC = ceil_div(K, GT_BK);
     uint16_t *At, *Bt;
     if (int rc = ws_get(0, (size_t)MT * KC * 2 * GT_BLOCK_ELEMS, &At)) return rc;
     if (int rc = ws_get(1, (size_t)NTl * KC * 2 * GT_BLOCK_ELEMS, &Bt)) return rc;
     // A as [M rows, K]: stored [M,K] when !transA, [K,M] when transA.  B as [N rows, K]: stored [N,K] when transB.
     if (f16) {
-        k_split_tiles<true><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M);
+        k_split_tiles<true><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M, a_ci, a_ds);
         CVB_LAUNCH_CHECK();
-        k_split_tiles<true><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1);
+        k_split_tiles<true><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1, b_ci, b_ds);
         CVB_LAUNCH_CHECK();
     } else {
-        k_split_tiles<false><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M);
+        k_split_tiles<false><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M, a_ci, a_ds);
         CVB_LAUNCH_CHECK();
-        k_split_tiles<false><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1);
+        k_split_tiles<false><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1, b_ci, b_ds);
         CVB_LAUNCH_CHECK();
     }
     DeviceInfo di;

@@ -82,6 +82,16 @@ struct GruTcArgs {
     long long* trace;    // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE_FWD), else null
 };
 
+static __device__ __forceinline__ long long globaltimer_ns() {
+    long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+// cross-CTA skew probe: globaltimer of every CTA at a few events of step 40 (trace rows behind the per-step table)
+#define TF_SKEW(slot)                                                                                       \
+    do {                                                                                                    \
+        if (a.trace && t == 40) a.trace[(size_t)(T + 1) * 64 + (size_t)(slot) * 256 + c] = globaltimer_ns(); \
+    } while (0)
 #define TF_TRACE(ev)                                                     \
     do {                                                                 \
         if (a.trace && c == 0) a.trace[(size_t)t * 64 + (ev)] = clock64(); \
@@ -158,6 +168,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     unsigned* ctrB = a.ctr + 32;
     const int n_pairs = B * out;
 
+    if (a.trace && c == 0 && threadIdx.x == 0) a.trace[60] = clock64();
     // ---- one-time setup: weights -> fp16 hi/lo in UMMA K-major core-matrix order -----------------
     {
         const int Kr = L.nch * TF_KC;
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     }
     cluster_sync_all();   // every CTA's inbox barrier is initialised before any peer copies into it
     const uint32_t tmem = *tmem_slot;
+    if (a.trace && c == 0 && threadIdx.x == 0) a.trace[61] = clock64();
 
     if (warp == 0) {
         // ================= producer: K-slice of h_{t-1} chunk by chunk, then y_{t-1} ====================
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             if (lane == 0) {
                 spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy before their release
                 TF_TRACE(14);
+                TF_SKEW(4);
             }
             __syncwarp();
             for (int ch = 0; ch < L.nch; ++ch) {
@@ -245,6 +258,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             if (lane == 0) {
                 spin_until(ctrB, (unsigned)G * (unsigned)(t + 1));
                 TF_TRACE(13);
+                TF_SKEW(5);
                 mbar_wait(y_empty, ((uint32_t)t & 1) ^ 1);
                 mbar_expect_tx(y_full, 2 * L.half);
                 bulk_g2s(ybuf, srcy, L.half, y_full);
@@ -479,8 +493,10 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 tc_fence_before();
             }
             named_bar_sync(7, 256);    // every finaliser published; D3 is drained into `part`
+            if (etid == 0) TF_SKEW(0);
             if (etid == 0) red_release_gpu_add(ctrA, 1u);   // release is cumulative over the barrier: one gpu-scope fence per CTA
             if (etid == 0) TF_TRACE(9);
+            if (etid == 0) TF_SKEW(1);
             if (act) {   // off the critical path: outputs / saved activations that only later kernels read
                 float* hd = f.hs + (size_t)(t + 1) * B * H + (size_t)b * H + u0;
                 *reinterpret_cast<float4*>(hd) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
@@ -631,9 +647,11 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 if (qb + 128 < q_n) named_bar_sync(2, 128);
             }
             if (rt == 0) TF_TRACE(21);
+            if (rt == 0) TF_SKEW(2);
             fence_proxy_async_global();
             named_bar_sync(2, 128);
             if (rt == 0) red_release_gpu_add(ctrB, 1u);
+            if (rt == 0) TF_SKEW(3);
             if (round > 0 && rt < w0) ydst[(size_t)bb0 * out + o0] = y_deferred;
             if (rt == 0) TF_TRACE(22);
         }
@@ -641,6 +659,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();   // no CTA leaves while a peer may still copy into its inbox
+    if (a.trace && c == 0 && threadIdx.x == 0) a.trace[62] = clock64();
     if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
@@ -719,7 +738,7 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     a.trace = nullptr;
     const char* trace_file = getenv("CVB_TRACE_FILE_FWD");
-    const size_t trace_bytes = (size_t)(f.T + 1) * 64 * sizeof(long long);
+    const size_t trace_bytes = ((size_t)(f.T + 1) * 64 + 8 * 256) * sizeof(long long);
     if (trace_file && trace_file[0]) {
         CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
         CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest(int mode, int N, int K
         lboA = 128; sboA = KB * 128;
         lboB = 128; sboB = KB * 128;
     }
-    if (mode == 2) {
+    if (mode == 2 || mode == 3) {
         if (tid == 0) {
             uint32_t bytesA = (uint32_t)M * K * 2, bytesB = (uint32_t)N * K * 2;
             mbar_expect_tx(&bars[0], bytesA + bytesB);
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest(int mode, int N, int K
         }
         fence_proxy_async_smem();
     }
-    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -75,7 +75,12 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest(int mode, int N, int K
         for (int k16 = 0; k16 < K / 16; ++k16) {
             uint64_t da = smem_desc(smem_u32(sA) + k16 * kstepA, lboA, sboA);
             uint64_t db = smem_desc(smem_u32(sB) + k16 * kstepB, lboB, sboB);
-            mma_bf16_ss(tmem, da, db, idesc, k16 > 0);
+            if (mode == 3) {   // A staged into TMEM columns [64 + 8*k16, +8) by tcgen05.cp, then a TS-mode MMA
+                tmem_cp_128x256b(tmem + 64 + 8 * k16, da);
+                mma_bf16_ts(tmem, tmem + 64 + 8 * k16, db, idesc, k16 > 0);
+            } else {
+                mma_bf16_ss(tmem, da, db, idesc, k16 > 0);
+            }
         }
         mma_commit(&bars[1]);
     }
@@ -89,14 +94,14 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest(int mode, int N, int K
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<64>(tmem);
+    if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace cvb
 
 extern "C" int cvb_selftest_umma(int mode, int N, int K, const void* A, const void* B, float* D, void* stream) {
     using namespace cvb;
-    CVB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0..2");
+    CVB_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0..3");
     CVB_REQUIRE(N % 16 == 0 && N >= 16 && N <= 64 && K % 16 == 0 && K >= 16 && K <= 512, "unsupported N=%d K=%d", N, K);
     size_t smem = (size_t)128 * K * 2 + (size_t)N * K * 2 + 64;
     CVB_CHECK(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

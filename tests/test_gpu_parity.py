@@ -452,10 +452,14 @@ def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B):
     w_h = torch.randn(1, B, 1024, generator=g).cuda()
 
     def run(mode):
+        # "exact" = the all-fp32 path: fp32-FMA recurrence kernels AND cuBLAS fp32 for every dense product (so the
+        # split-precision GEMM, the tap-fused conv products and the in-kernel bias gradients are A/B-checked too)
         if mode:
             os.environ["CVB_RECURRENCE"] = mode
+            os.environ["CVB_GEMM"] = "cublas"
         else:
             os.environ.pop("CVB_RECURRENCE", None)
+            os.environ.pop("CVB_GEMM", None)
         try:
             xs, ys, hs = (t.clone().requires_grad_(True) for t in (x, y0, h0))
             for p in m.parameters():
@@ -468,11 +472,12 @@ def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B):
             return (o.detach(), yl.detach(), hl.detach()), (xs.grad, ys.grad, hs.grad), grads
         finally:
             os.environ.pop("CVB_RECURRENCE", None)
+            os.environ.pop("CVB_GEMM", None)
 
     out_e, gin_e, gp_e = run("exact")
     out_t, gin_t, gp_t = run(None)
     for a, b in zip(out_t, out_e):
-        assert _maxabs(a, b) < 2e-5 * max(1.0, float(b.abs().max()))
+        assert _maxabs(a, b) < 5e-5 * max(1.0, float(b.abs().max()))
     for a, b in zip(gin_t, gin_e):
         assert _maxabs(a, b) < 1e-4 * max(1e-3, float(b.abs().max())), (float(b.abs().max()))
     assert set(gp_t) == set(gp_e)

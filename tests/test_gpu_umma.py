@@ -11,7 +11,7 @@ def _arrange(X):
     return X.to(torch.bfloat16).reshape(R // 8, 8, K // 8, 8).permute(0, 2, 1, 3).contiguous()
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("N,K", [(32, 64), (16, 256), (64, 128)])
 def test_umma_selftest(mode, N, K):
     from cyclevae_vc_b200._lib import check, lib, ptr
@@ -20,7 +20,7 @@ def test_umma_selftest(mode, N, K):
     B = torch.randn(N, K, generator=g).cuda()
     D = torch.full((128, N), float("nan"), device="cuda")
     ref = A.to(torch.bfloat16).double() @ B.to(torch.bfloat16).double().t()
-    if mode == 2:
+    if mode >= 2:   # 2: bulk-copied operands, SS MMA; 3: A staged smem -> TMEM (tcgen05.cp), TS MMA
         a, b = _arrange(A), _arrange(B)
         check(lib.cvb_selftest_umma(mode, N, K, a.data_ptr(), b.data_ptr(), ptr(D), torch.cuda.current_stream().cuda_stream))
     else:

@@ -55,14 +55,30 @@ def run(tag):
 
 
 def report(path, names):
-    tr = np.fromfile(path, dtype=np.int64).reshape(-1, 64)
+    raw = np.fromfile(path, dtype=np.int64)
+    n_rows = (raw.size - (8 * 256 if raw.size % 64 == 0 and (raw.size - 8 * 256) % 64 == 0 and "fwd" in path else 0)) // 64
+    tr = raw[:n_rows * 64].reshape(-1, 64)
+    if "fwd" in path and raw.size > n_rows * 64:
+        sk = raw[n_rows * 64:].reshape(8, 256)[:, :128].astype(np.float64)
+        sk_names = ["fin: before ctrA release", "fin: after ctrA release", "aux: y published", "aux: after ctrB release", "prod: ctrA seen (t=40)",
+                 "prod: ctrB seen (t=40)"]
+        ref = sk[0].min()
+        print("  cross-CTA skew at step 40 (globaltimer ns relative to the earliest CTA reaching its ctrA release):")
+        for i, nm in enumerate(sk_names):
+            v = sk[i][sk[i] > 0]
+            if v.size:
+                print(f"    {nm:28s} min {v.min() - ref:8.0f}  median {np.median(v) - ref:8.0f}  max {v.max() - ref:8.0f} ns")
     n_it = tr.shape[0]
     base = tr[:, 0].astype(np.float64)
     sel = slice(5, n_it - 2)
     period = np.diff(base[sel]).mean()
     print(f"{path}: {n_it} iterations, mean step period {period:.0f} cycles = {period / MHZ:.2f} us")
+    if tr[0, 60] and tr[0, 62]:
+        setup, first, total = tr[0, 61] - tr[0, 60], tr[0, 0] - tr[0, 60], tr[0, 62] - tr[0, 60]
+        print(f"  kernel: setup {setup / MHZ:.1f} us, entry -> first step {first / MHZ:.1f} us, whole kernel {total / MHZ:.1f} us, "
+              f"steps {period * (n_it - 1) / MHZ:.1f} us")
     rows = []
-    for ev in range(64):
+    for ev in range(60):
         v = tr[sel, ev].astype(np.float64)
         if (v == 0).all():
             continue
