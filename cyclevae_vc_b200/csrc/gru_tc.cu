@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
             const uint16_t* srcy = a.yx + (size_t)(t & 1) * 2 * yx_part;
             if (lane == 0) {
-                spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy before their release
+                spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));
+                fence_proxy_async_global();   // acquire (generic proxy) -> the bulk copies below (async proxy)
                 TF_TRACE(14);
                 TF_SKEW(4);
             }
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             }
             if (lane == 0) {
                 spin_until(ctrB, (unsigned)G * (unsigned)(t + 1));
+                fence_proxy_async_global();
                 TF_TRACE(13);
                 TF_SKEW(5);
                 mbar_wait(y_empty, ((uint32_t)t & 1) ^ 1);
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 drain_partial_y(taddr, f.part + (size_t)c * n_pairs + rt, 0, 32, out, B, rt < B);
                 tc_fence_before();
                 if (rt == 0) TF_TRACE(26);
-                named_bar_arrive(7, 256);
+                named_bar_sync(7, 256);   // a full barrier, not an arrive: thread 0's release after it must cover these warps' stores to `part`
                 if (rt == 0) spin_until(ctrA, (unsigned)G * (unsigned)(round + 1));
                 if (rt == 0) TF_TRACE(20);
                 named_bar_sync(2, 128);

@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             const uint16_t* srcy = a.dyx + (size_t)(n & 1) * 2 * dy_part;
             if (n >= 1) {
                 if (lane == 0) {
-                    spin_until(ctrA, (unsigned)G * (unsigned)n);   // the writers fenced generic -> async proxy before their release
+                    spin_until(ctrA, (unsigned)G * (unsigned)n);
+                    fence_proxy_async_global();   // acquire (generic proxy) -> the bulk copies below (async proxy)
                     TB_TRACE(14);
                 }
                 __syncwarp();
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 if (lane == 0) {
                     if (is_dy) {
                         spin_until(ctrB, (unsigned)G * (unsigned)(n + 1));
+                        fence_proxy_async_global();
                         TB_TRACE(13);
                     }
                     mbar_wait(&empty[s], ph);
@@ -485,11 +487,13 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             }
         }
         if (want_db) {
-            // every CTA of the cluster is past its last exchange: the staging buffer is idle
-            stage[(warp - 4) * 32 + lane] = bsum;
+            // scratch = this CTA's own inbox: its last incoming copies were waited for and summed above.  (NOT the staging
+            // buffer: the peers may still be pulling this CTA's last outgoing partial sums from it.)
+            named_bar_sync(3, 128);   // every finaliser thread is done reading the inbox
+            inbox[(warp - 4) * 32 + lane] = bsum;
             named_bar_sync(3, 128);
             if (etid < 32) {
-                const float tot = (stage[etid] + stage[32 + etid]) + (stage[64 + etid] + stage[96 + etid]);
+                const float tot = (inbox[etid] + inbox[32 + etid]) + (inbox[64 + etid] + inbox[96 + etid]);
                 const int grp = etid >> 3, u = u0 + (etid & 7);
                 if (f.dbih && grp < 3) {   // db_ih = sum [dar, daz, dan]
                     float* d = f.dbih + (size_t)grp * H + u;
@@ -638,7 +642,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             drain_partial(taddr, f.part + (size_t)c * n_pairs + rt, 0, 32, out, B, rt < B);   // the finaliser warps take [32, 64)
             tc_fence_before();
             if (rt == 0) TB_TRACE(26);
-            named_bar_arrive(7, 256);
+            named_bar_sync(7, 256);   // a full barrier, not an arrive: thread 0's release after it must cover these warps' stores to `part`
         }
     }
     tc_fence_before();
@@ -663,15 +667,19 @@ size_t gru_tc_bwd_scratch_floats(int B, int H) {
 static int pick_cluster(int B, int H, int out, const DeviceInfo& di, TbLayout* Lout) {
     const int G = H / 8;
     if (!gru_tc_bwd_shape_ok(B, H, out) || G > di.n_sm) return 0;
-    struct Entry { int B, H, out, S; };
+    // clusters of 8 halve the MMA count per step but need 16 co-resident clusters at H = 1024 (this pool's B200s hold 15);
+    // the 4-CTA shape is the one every measurement and parity run of this round used, so 8 is opt-in (CVB_TC_CLUSTER8=1)
+    const char* e8 = getenv("CVB_TC_CLUSTER8");
+    const int first = (e8 && e8[0] == '1') ? 8 : 4;
+    struct Entry { int B, H, out, first, S; };
     static Entry cache[16];
     static int n_cache = 0;
     int S = -1;
     for (int i = 0; i < n_cache; ++i)
-        if (cache[i].B == B && cache[i].H == H && cache[i].out == out) S = cache[i].S;
+        if (cache[i].B == B && cache[i].H == H && cache[i].out == out && cache[i].first == first) S = cache[i].S;
     if (S < 0) {
         S = 0;
-        for (int cand = 8; cand >= 4 && S == 0; cand >>= 1) {
+        for (int cand = first; cand >= 4 && S == 0; cand >>= 1) {
             if (H % (8 * cand) != 0 || (3 * H / TB_KC) % cand != 0) continue;
             TbLayout L = tb_layout(B, H, cand, G, out, di.max_smem_optin);
             if (L.NS < 2 || (int)L.total > di.max_smem_optin) continue;
@@ -698,7 +706,7 @@ static int pick_cluster(int B, int H, int out, const DeviceInfo& di, TbLayout* L
             if (getenv("CVB_DEBUG")) fprintf(stderr, "[cvb] k_gru_bwd_tc: cluster %d: %d co-resident clusters (need %d), smem %u, ring %d\n", cand, ncl, G / cand, L.total, L.NS);
             if (ncl * cand >= G) S = cand;
         }
-        if (n_cache < 16) cache[n_cache++] = Entry{B, H, out, S};
+        if (n_cache < 16) cache[n_cache++] = Entry{B, H, out, first, S};
     }
     if (S && Lout) *Lout = tb_layout(B, H, S, G, out, di.max_smem_optin);
     return S;

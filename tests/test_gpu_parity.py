@@ -412,17 +412,21 @@ def test_full_size_properties(cvb):
         for j in (0, 37, 79):
             oj, yj, hj = me(xg[j], y0[j:j + 1], clamp_vae=True, lat_dim=lat)
             assert _maxabs(oj, o1[j]) < 5e-5 and _maxabs(hj[0, 0], h1[0, j]) < 5e-5   # batched gx: tensor-core GEMM, unbatched: cuBLAS
-        ref, _, href = orc.gru_rnn_forward(Pe, enc, x[[3, 64]], torch.zeros(2, 1, 2 * lat), clamp_vae=True, lat_dim=lat)
-    assert _maxabs(o1[[3, 64]], ref) < TOL
-    assert _maxabs(h1[0, [3, 64]], href[0]) < TOL
+        # live oracle calls run in float64 (torch's CPU float32 kernels occasionally return ~1e-4 less accurate results on the
+        # GPU boxes' hosts; the fixtures under tests/golden were generated once and are not affected)
+        Pe64 = {k: v.double() for k, v in Pe.items()}
+        ref, _, href = orc.gru_rnn_forward(Pe64, enc, x[[3, 64]].double(), torch.zeros(2, 1, 2 * lat, dtype=torch.float64), clamp_vae=True,
+                                           lat_dim=lat)
+    assert _maxabs(o1[[3, 64]].double(), ref) < TOL
+    assert _maxabs(h1[0, [3, 64]].double(), href[0]) < TOL
     # decode-side wide batch: 256 utterances x 200 frames (two batch tiles of the persistent kernel)
     Bd, Td = 256, 200
     xd, _, _, _ = orc.synth_batch(Bd, Td, 8)
     with torch.no_grad():
         od, _, hd = me(xd.cuda(), torch.zeros(Bd, 1, 2 * lat).cuda(), clamp_vae=True, lat_dim=lat)
-        refd, _, hrefd = orc.gru_rnn_forward(Pe, enc, xd[[0, 127, 128, 255]], torch.zeros(4, 1, 2 * lat), clamp_vae=True,
-                                             lat_dim=lat)
-    assert _maxabs(od[[0, 127, 128, 255]], refd) < TOL
+        refd, _, hrefd = orc.gru_rnn_forward(Pe64, enc, xd[[0, 127, 128, 255]].double(), torch.zeros(4, 1, 2 * lat, dtype=torch.float64),
+                                             clamp_vae=True, lat_dim=lat)
+    assert _maxabs(od[[0, 127, 128, 255]].double(), refd) < TOL
     assert torch.isfinite(od).all()
 
 
@@ -537,3 +541,43 @@ def test_tensor_core_forward_any_row_count(cvb):
             for _ in range(2):
                 o_t, y_t, h_t = enc(x, y0, h_in=h0, clamp_vae=True, lat_dim=32)
                 assert _maxabs(o_t, o_e) < 2e-5 and _maxabs(h_t, h_e) < 2e-5 and _maxabs(y_t, y_e) < 2e-5, (B, T)
+
+
+@pytest.mark.parametrize("cluster8", ["0", "1"])
+def test_tensor_core_recurrence_hu512_both_cluster_shapes(cvb, cluster8):
+    """hidden_units = 512 (64 CTAs): the BPTT kernel's 8-CTA cluster shape is co-resident here (8 clusters), so both K-split
+    shapes are checked against the all-fp32 path, forward and gradients."""
+    lat, T, B = 16, 24, 40
+    spec = orc.NetSpec(in_dim=20, out_dim=2 * lat, hidden_units=512, do_prob=0.5, scale_in=True, scale_out=False)
+    rng = np.random.default_rng(3)
+    P = orc.init_params(spec, 77, gain=1.5, bias_std=0.02, mean=rng.normal(size=20), scale=rng.uniform(0.5, 2.0, size=20))
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, 20, generator=g).cuda()
+    y0 = (0.3 * torch.randn(B, 1, 2 * lat, generator=g)).cuda()
+    h0 = (0.5 * torch.randn(1, B, 512, generator=g)).cuda()
+    mc = ((torch.rand(B, T, spec.conv_dim, generator=g) >= 0.5).float() * 2).cuda()
+    mg = ((torch.rand(B, T, 512, generator=g) >= 0.5).float() * 2).cuda()
+    w_o = torch.randn(B, T, 2 * lat, generator=g).cuda()
+
+    def run(exact):
+        env = {"CVB_RECURRENCE": "exact", "CVB_GEMM": "cublas"} if exact else {"CVB_TC_CLUSTER8": cluster8}
+        os.environ.update(env)
+        try:
+            m = _module(cvb, spec, P).train()   # fresh module: the cluster shape is chosen once per shape and process-cached
+            xs, ys, hs = (t.clone().requires_grad_(True) for t in (x, y0, h0))
+            m.inject_dropout_masks(mc, mg)
+            o, yl, hl = m(xs, ys, h_in=hs, do=True, clamp_vae=True, lat_dim=lat)
+            ((o * w_o).sum() + hl.sum()).backward()
+            torch.cuda.synchronize()
+            return o.detach(), hl.detach(), xs.grad, hs.grad, {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+    o_e, h_e, dx_e, dh_e, gp_e = run(True)
+    o_t, h_t, dx_t, dh_t, gp_t = run(False)
+    assert _maxabs(o_t, o_e) < 5e-5 * max(1.0, float(o_e.abs().max())) and _maxabs(h_t, h_e) < 5e-5
+    for a, b in ((dx_t, dx_e), (dh_t, dh_e)):
+        assert _maxabs(a, b) < 1e-4 * max(1e-3, float(b.abs().max()))
+    for k in gp_e:
+        assert _maxabs(gp_t[k], gp_e[k]) < 1e-4 * max(1e-3, float(gp_e[k].abs().max())), k
