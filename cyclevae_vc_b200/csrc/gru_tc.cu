@@ -235,8 +235,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
             const uint16_t* srcy = a.yx + (size_t)(t & 1) * 2 * yx_part;
             if (lane == 0) {
-                spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));
-                fence_proxy_async_global();   // acquire (generic proxy) -> the bulk copies below (async proxy)
+                spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy before their release
                 TF_TRACE(14);
                 TF_SKEW(4);
             }
@@ -258,7 +257,6 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             }
             if (lane == 0) {
                 spin_until(ctrB, (unsigned)G * (unsigned)(t + 1));
-                fence_proxy_async_global();
                 TF_TRACE(13);
                 TF_SKEW(5);
                 mbar_wait(y_empty, ((uint32_t)t & 1) ^ 1);

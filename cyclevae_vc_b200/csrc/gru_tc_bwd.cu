@@ -217,8 +217,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             if (n >= 1) {
                 if (lane == 0) {
                     spin_until(ctrA, (unsigned)G * (unsigned)n);
-                    fence_proxy_async_global();   // acquire (generic proxy) -> the bulk copies below (async proxy)
-                    TB_TRACE(14);
+                        TB_TRACE(14);
                 }
                 __syncwarp();
             }
@@ -227,7 +226,6 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 if (lane == 0) {
                     if (is_dy) {
                         spin_until(ctrB, (unsigned)G * (unsigned)(n + 1));
-                        fence_proxy_async_global();
                         TB_TRACE(13);
                     }
                     mbar_wait(&empty[s], ph);
