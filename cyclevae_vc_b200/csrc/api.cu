@@ -50,9 +50,18 @@ static FwdScratch fwd_scratch(const cvb_net* net, int B, int T) {
     S.part = off; off += r4((size_t)gru_exact_grid(net->hidden) * B * out);
     S.bar = off; off += 16;
     S.tc = off;
-    if (gru_tc_shape_ok(B, net->hidden, net->out_dim)) off += r4(gru_tc_scratch_floats(B, net->hidden));
+    if (gru_tc_shape_ok(B, net->hidden, net->out_dim)) {
+        size_t a = gru_tc_scratch_floats(B, net->hidden);
+        size_t e = gru_tc_eval_scratch_floats(B, net->hidden) + r4((size_t)3 * H);   // folded inference path: W_fb | hx | ctr | c_fb
+        off += r4(a > e ? a : e);
+    }
     S.total = off;
     return S;
+}
+// CVB_EVAL_FOLD=0 keeps the two-exchange kernel for inference too (A/B testing)
+static bool want_fold() {
+    const char* e = getenv("CVB_EVAL_FOLD");
+    return !(e && e[0] == '0');
 }
 // CVB_RECURRENCE=exact forces the fp32-FMA kernels; default = tensor-core variant where the shape allows
 static bool want_tc() {
@@ -257,7 +266,11 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     {
         DeviceInfo di;
         if (int rc = get_device_info(&di)) return rc;
-        if (want_tc() && gru_tc_supported(B, H, out, di)) {
+        if (want_tc() && !training && !mask_gru_tm && want_fold() && gru_tc_eval_supported(B, H, out, di)) {
+            // inference (no dropout): feedback folded into the recurrent matrix, all y_t from one product afterwards
+            float* esc = scratch + FS.tc;
+            if (int rc = gru_ar_fwd_tc_eval(a, esc, esc + gru_tc_eval_scratch_floats(B, H), s)) return rc;
+        } else if (want_tc() && gru_tc_supported(B, H, out, di)) {
             if (int rc = gru_ar_fwd_tc(a, scratch + FS.tc, s)) return rc;
         } else {
             if (int rc = gru_ar_fwd_exact(a, s)) return rc;

@@ -53,6 +53,11 @@ bool gru_tc_supported(int B, int H, int out, const DeviceInfo& di);
 size_t gru_tc_scratch_floats(int B, int H);
 int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s);
 
+// inference-only forward with the y feedback folded into the recurrent matrix (one exchange per step), gru_tc_eval.cu
+bool gru_tc_eval_supported(int B, int H, int out, const DeviceInfo& di);
+size_t gru_tc_eval_scratch_floats(int B, int H);
+int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, float* cfb, cudaStream_t s);
+
 // tensor-core BPTT over thread-block clusters, gru_tc_bwd.cu
 bool gru_tc_bwd_shape_ok(int B, int H, int out);
 bool gru_tc_bwd_supported(int B, int H, int out, const DeviceInfo& di);

@@ -1,0 +1,480 @@
+// Inference-only tensor-core forward recurrence of the autoregressive GRU (gru_vae.py:364-399 with do=False: the
+// eval / stage-6 conversion path, decode_*.py:303-323), with the y feedback FOLDED into the recurrent matrix
+// (SURVEY.md Appendix A.4):  without dropout o_t = h_t, so
+//     W_y y_{t-1} = (W_y W_o) h_{t-1} + W_y b_o =: W_fb h_{t-1} + c_fb      (t >= 1)
+// and one step needs only h_{t-1}:
+//     a_r = gx_r + b_hr + (W_hr + W_fb,r) h      a_z likewise      gh_n = W_hn h + b_hn      gi_n = gx_n + W_fb,n h
+// (c_fb is added to gx[t >= 1] by the host before the launch; the first step's feedback is the caller's y_in, so
+// gx[0] += W_y y_in - W_fb h_in cancels the folded term there; all y_t come from ONE product Y = H W_o^T + b_o after
+// the launch).  Per step there is a single grid-wide exchange (h_t) instead of two.
+//
+// Same 2-D split over clusters of 4 CTAs as gru_tc.cu: cluster = 32 hidden units, CTA j = K-slice j of the
+// contraction for the block's 4 x 32 rows [r' | z' | hn | in'], finaliser of 8 units; operands fp16 hi+lo with B
+// stored [hi rows | lo rows] (one MMA with N = 256 and one with N = 128 per K step), fp32 accumulation in TMEM,
+// DSMEM bulk-copy exchange of the partial sums, fixed-order fp32 sums, MUFU gates.
+// Roles (256 threads): w0 bulk-copy producer, w1 MMA issuer, w2 TMEM allocator, w4-7 exchange + gates.
+#include <stdlib.h>
+
+#include "gru_ar.cuh"
+#include "umma.cuh"
+
+namespace cvb {
+using namespace umma;
+
+constexpr int TE_NT = 256;
+constexpr int TE_KC = 64;
+constexpr int TE_S = 4;
+constexpr int TE_UB = 8 * TE_S;     // units per cluster
+constexpr int TE_NW = 4 * TE_UB;    // rows of the folded operand: r', z', hn, in' of the block = 128
+
+struct TeLayout {
+    int MB, nch, NS;
+    uint32_t half, stage_bytes, w_chunk_bytes, slot_bytes;
+    uint32_t off_ring, off_w, off_inbox, off_bias, off_bar, total;
+};
+
+__host__ __device__ inline TeLayout te_layout(int B, int H, int smem_max) {
+    TeLayout L;
+    L.MB = (B + 7) / 8;
+    L.nch = H / TE_KC / TE_S;
+    L.half = (uint32_t)L.MB * 1024u;
+    L.stage_bytes = 2u * L.half;
+    L.w_chunk_bytes = 2u * (TE_NW / 8) * 1024u;   // [hi: 16 row groups][lo: 16 row groups] x 1 KB
+    L.slot_bytes = (uint32_t)L.MB * 8u * 128u;    // [rows][32 floats]
+    const uint32_t inbox = ((uint32_t)TE_S * L.slot_bytes + 127u) & ~127u;
+    const uint32_t fixed = (uint32_t)L.nch * L.w_chunk_bytes + inbox + 128u + 256u;
+    int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
+    L.NS = ns > 6 ? 6 : ns;
+    const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
+    L.off_ring = 0;   // idle between a step's last chunk and the next step's first: doubles as the staging of the outgoing sums
+    L.off_w = ring;
+    L.off_inbox = L.off_w + (uint32_t)L.nch * L.w_chunk_bytes;
+    L.off_bias = L.off_inbox + inbox;
+    L.off_bar = L.off_bias + 128u;
+    L.total = L.off_bar + 256u;
+    return L;
+}
+
+struct GruTcEvalArgs {
+    const float* gx;     // [T,B,3H]: W_x xc + b_ih + (t >= 1: W_y b_o; t == 0: W_y y_in)
+    const float* Whh;    // [3H,H]
+    const float* Wfb;    // [3H,H] = W_y W_o
+    const float* bhh;    // [3H]
+    float* hs;           // [T+1,B,H], slot 0 = h_in
+    uint16_t* hx;        // [2 slots][2 parts][H/64 chunks][MB][8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
+    unsigned* ctr;       // zero-initialised
+    int B, T, H;
+    int smem_max;
+    int keepalive;
+    long long* trace;    // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE_EVAL), else null
+};
+
+#define TE_TRACE(ev)                                                     \
+    do {                                                                 \
+        if (a.trace && c == 0) a.trace[(size_t)t * 64 + (ev)] = clock64(); \
+    } while (0)
+
+static __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
+    while (ld_acquire_gpu(ctr) < target) {
+    }
+}
+static __device__ __forceinline__ void split8_f16(const float* x, uint4& hi, uint4& lo) {
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) split_f16(x[q], h[q], l[q]);
+    hi = make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                    (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+    lo = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                    (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+}
+
+__global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int B = a.B, T = a.T, H = a.H;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int j = (int)cluster_ctarank();
+    const TeLayout L = te_layout(B, H, a.smem_max);
+    const int ublk0 = (c / TE_S) * TE_UB;
+    const int u0 = ublk0 + 8 * j;
+    const int k0 = j * L.nch * TE_KC;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    uint8_t* ring = smem + L.off_ring;
+    float* stage = reinterpret_cast<float*>(ring);                 // [S (to)][MB*8][32], aliases the (idle) ring
+    uint8_t* sW = smem + L.off_w;
+    float* inbox = reinterpret_cast<float*>(smem + L.off_inbox);   // [S (from)][MB*8][32]
+    float* sBh = reinterpret_cast<float*>(smem + L.off_bias);      // [3][8] b_hh of the own units
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    uint64_t* empty = full + 8;
+    uint64_t* d1_full = empty + 8;
+    uint64_t* inbox_full = d1_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbox_full + 1);
+    const size_t hx_part = (size_t)(H / TE_KC) * L.MB * 512;
+
+    // ---- one-time setup: folded weights -> fp16 hi/lo in UMMA K-major core-matrix order ------------------
+    {
+        const int Kr = L.nch * TE_KC;
+        for (int i = threadIdx.x; i < TE_NW * Kr; i += TE_NT) {
+            const int n = i / Kr, kl = i - n * Kr;   // n = g*32 + unit of the block; g: 0 r', 1 z', 2 hn, 3 in'
+            const int g = n / TE_UB, ul = n - g * TE_UB;
+            const size_t col = (size_t)k0 + kl;
+            const int u = ublk0 + ul;
+            float w;
+            if (g < 2) w = a.Whh[(size_t)(g * H + u) * H + col] + a.Wfb[(size_t)(g * H + u) * H + col];
+            else if (g == 2) w = a.Whh[(size_t)(2 * H + u) * H + col];
+            else w = a.Wfb[(size_t)(2 * H + u) * H + col];
+            uint16_t hi, lo;
+            split_f16(w, hi, lo);
+            const uint32_t off = (uint32_t)(kl / TE_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TE_KC) >> 3) * 128u +
+                                 (uint32_t)(n & 7) * 16u + (uint32_t)(kl & 7) * 2u;
+            *reinterpret_cast<uint16_t*>(sW + off) = hi;
+            *reinterpret_cast<uint16_t*>(sW + (TE_NW / 8) * 1024u + off) = lo;
+        }
+        if (threadIdx.x < 24) sBh[threadIdx.x] = a.bhh[(threadIdx.x >> 3) * H + u0 + (threadIdx.x & 7)];
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            mbar_init(d1_full, 1);
+            mbar_init(inbox_full, 1);
+            mbar_fence_init();
+        }
+        fence_proxy_async_smem();
+        if (warp == 2) tmem_alloc<512>(tmem_slot);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    cluster_sync_all();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= producer: K-slice of h_{t-1} ====================================================
+        int s = 0;
+        uint32_t ph = 1;
+        for (int t = 0; t < T; ++t) {
+            const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
+            if (lane == 0) {
+                spin_until(a.ctr, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy
+                TE_TRACE(14);
+            }
+            __syncwarp();
+            for (int ch = 0; ch < L.nch; ++ch) {
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph);
+                    uint8_t* dst = ring + (size_t)s * L.stage_bytes;
+                    mbar_expect_tx(&full[s], 2 * L.half);
+                    bulk_g2s(dst, src + (size_t)ch * L.MB * 512, L.half, &full[s]);
+                    bulk_g2s(dst + L.half, src + hx_part + (size_t)ch * L.MB * 512, L.half, &full[s]);
+                }
+                __syncwarp();
+                if (++s == L.NS) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =========================================================================
+        const uint32_t idesc_s = idesc_f16_f32(128, 2 * TE_NW), idesc_h = idesc_f16_f32(128, TE_NW), idesc_dummy = idesc_f16_f32(128, 16);
+        const uint64_t dA0 = smem_desc(smem_u32(ring), 128, 1024);
+        const uint64_t dW0 = smem_desc(smem_u32(sW), 128, 1024);
+        const uint32_t a_step = L.stage_bytes >> 4, half16 = L.half >> 4, w_step = L.w_chunk_bytes >> 4;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = 0; t < T; ++t) {
+            for (int ch = 0; ch < L.nch; ++ch) {
+                for (;;) {   // poll; while idle keep the tensor pipe warm (see gru_tc.cu)
+                    uint32_t ok = (lane == 0) ? (mbar_test_wait(&full[s], ph) ? 1u : 0u) : 0u;
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    if (ok) break;
+                    if (a.keepalive) mma_bf16_ss_elect(tmem + 384u, dW0, dW0, idesc_dummy, false);
+                }
+                if (lane == 0 && ch < 8) TE_TRACE(40 + ch);
+                tc_fence_after();
+                const uint64_t da = dA0 + (uint64_t)((uint32_t)s * a_step);
+                const uint64_t db = dW0 + (uint64_t)((uint32_t)ch * w_step);
+#pragma unroll
+                for (int k16 = 0; k16 < TE_KC / 16; ++k16) {
+                    mma_bf16_ss_elect(tmem, da + 16u * k16, db + 16u * k16, idesc_s, (ch | k16) != 0);
+                    mma_bf16_ss_elect(tmem, da + half16 + 16u * k16, db + 16u * k16, idesc_h, true);
+                }
+                mma_commit_elect(&empty[s]);
+                if (ch == L.nch - 1) mma_commit_elect(d1_full);
+                if (++s == L.NS) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= exchange + gates: TMEM lane == batch row ==========================================
+        const int b = (warp - 4) * 32 + lane;
+        const bool act = b < B;
+        const int etid = threadIdx.x - 128;
+        const uint32_t inbox_addr = smem_u32(inbox);
+        const uint32_t inbox_bar_addr = smem_u32(inbox_full);
+        const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
+        const uint32_t slot_f = L.slot_bytes / 4;
+        float hreg[8];
+        {   // prologue: publish h_in (slot 0) in operand order
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hreg[q] = act ? a.hs[(size_t)b * H + u0 + q] : 0.f;
+            uint4 hh, hl;
+            split8_f16(hreg, hh, hl);
+            if (act) {
+                const size_t off = ((size_t)(u0 >> 6) * L.MB + (b >> 3)) * 512 + (size_t)((u0 & 63) >> 3) * 64 + (size_t)(b & 7) * 8;
+                *reinterpret_cast<uint4*>(a.hx + off) = hh;
+                *reinterpret_cast<uint4*>(a.hx + hx_part + off) = hl;
+            }
+            fence_proxy_async_global();
+            named_bar_sync(1, 128);
+            if (etid == 0) red_release_gpu_add(a.ctr, 1u);
+        }
+        for (int t = 0; t < T; ++t) {
+            const size_t row = (size_t)t * B + (act ? b : 0);
+            float4 gxv[6];
+            if (act) {
+                const float* gp = a.gx + row * 3 * H + u0;
+#pragma unroll
+                for (int gi = 0; gi < 3; ++gi) {
+                    gxv[2 * gi] = ldg_nc_v4_pinned(gp + (size_t)gi * H);
+                    gxv[2 * gi + 1] = ldg_nc_v4_pinned(gp + (size_t)gi * H + 4);
+                }
+            }
+            if (etid == 0) TE_TRACE(0);
+            if (etid == 0) mbar_expect_tx(inbox_full, (uint32_t)TE_S * L.slot_bytes);
+            mbar_wait(d1_full, (uint32_t)t & 1);
+            if (etid == 0) TE_TRACE(1);
+            tc_fence_after();
+            // partial sums (main + correction halves) of the block's units -> the finalisers' inboxes
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    float v[16], v2[16];
+                    tmem_ld_x16(taddr + g * TE_UB + 16 * k, v);
+                    tmem_ld_x16(taddr + TE_NW + g * TE_UB + 16 * k, v2);
+                    tmem_ld_wait();
+                    if (b < L.MB * 8) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            // a row is 8 x 16 B; slot q of row b sits at q ^ (b & 7) so that a quarter warp covers all 32 banks
+                            float* row = stage + (size_t)(2 * k + h2) * slot_f + b * 32;
+                            float* d = row + (((2 * g) ^ (b & 7)) << 2);
+                            float* d1 = row + (((2 * g + 1) ^ (b & 7)) << 2);
+                            *reinterpret_cast<float4*>(d) = make_float4(v[8 * h2 + 0] + v2[8 * h2 + 0], v[8 * h2 + 1] + v2[8 * h2 + 1],
+                                                                        v[8 * h2 + 2] + v2[8 * h2 + 2], v[8 * h2 + 3] + v2[8 * h2 + 3]);
+                            *reinterpret_cast<float4*>(d1) = make_float4(v[8 * h2 + 4] + v2[8 * h2 + 4], v[8 * h2 + 5] + v2[8 * h2 + 5],
+                                                                            v[8 * h2 + 6] + v2[8 * h2 + 6], v[8 * h2 + 7] + v2[8 * h2 + 7]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            if (etid < TE_S)
+                bulk_s2c(mapa(inbox_addr + (uint32_t)j * L.slot_bytes, (uint32_t)etid), stage + (size_t)etid * slot_f, L.slot_bytes,
+                         mapa(inbox_bar_addr, (uint32_t)etid));
+            if (etid == 0) TE_TRACE(2);
+            mbar_wait_cluster(inbox_full, (uint32_t)t & 1);
+            if (etid == 0) TE_TRACE(3);
+            float ar[8], az[8], ahn[8], ain[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ar[q] = az[q] = ahn[q] = ain[q] = 0.f;
+            if (act) {
+#pragma unroll
+                for (int p = 0; p < TE_S; ++p) {   // fixed order: deterministic
+                    const float4* x = reinterpret_cast<const float4*>(inbox + (size_t)p * slot_f + b * 32);
+                    const int sw = b & 7;
+                    const float4 x0 = x[0 ^ sw], x1 = x[1 ^ sw], x2 = x[2 ^ sw], x3 = x[3 ^ sw], x4 = x[4 ^ sw], x5 = x[5 ^ sw], x6 = x[6 ^ sw],
+                                 x7 = x[7 ^ sw];
+                    ar[0] += x0.x; ar[1] += x0.y; ar[2] += x0.z; ar[3] += x0.w; ar[4] += x1.x; ar[5] += x1.y; ar[6] += x1.z; ar[7] += x1.w;
+                    az[0] += x2.x; az[1] += x2.y; az[2] += x2.z; az[3] += x2.w; az[4] += x3.x; az[5] += x3.y; az[6] += x3.z; az[7] += x3.w;
+                    ahn[0] += x4.x; ahn[1] += x4.y; ahn[2] += x4.z; ahn[3] += x4.w; ahn[4] += x5.x; ahn[5] += x5.y; ahn[6] += x5.z; ahn[7] += x5.w;
+                    ain[0] += x6.x; ain[1] += x6.y; ain[2] += x6.z; ain[3] += x6.w; ain[4] += x7.x; ain[5] += x7.y; ain[6] += x7.z; ain[7] += x7.w;
+                }
+            }
+            if (etid == 0) TE_TRACE(5);
+            {
+                const float* gxr = reinterpret_cast<const float*>(&gxv[0]);
+                const float* gxz = reinterpret_cast<const float*>(&gxv[2]);
+                const float* gxn = reinterpret_cast<const float*>(&gxv[4]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (act) {
+                        const float r = sigmoid_fast(gxr[q] + ar[q] + sBh[q]);
+                        const float z = sigmoid_fast(gxz[q] + az[q] + sBh[8 + q]);
+                        const float n = tanh_fast(gxn[q] + ain[q] + r * (ahn[q] + sBh[16 + q]));
+                        hreg[q] = (1.0f - z) * n + z * hreg[q];
+                    }
+                }
+            }
+            if (etid == 0) TE_TRACE(10);
+            uint4 hh, hl;
+            split8_f16(hreg, hh, hl);
+            if (act) {
+                uint16_t* hdst = a.hx + (size_t)((t + 1) & 1) * 2 * hx_part;
+                const size_t off = ((size_t)(u0 >> 6) * L.MB + (b >> 3)) * 512 + (size_t)((u0 & 63) >> 3) * 64 + (size_t)(b & 7) * 8;
+                *reinterpret_cast<uint4*>(hdst + off) = hh;
+                *reinterpret_cast<uint4*>(hdst + hx_part + off) = hl;
+            }
+            if (etid == 0) TE_TRACE(7);
+            fence_proxy_async_global();
+            if (etid == 0) TE_TRACE(8);
+            named_bar_sync(1, 128);
+            if (etid == 0) red_release_gpu_add(a.ctr, 1u);
+            if (etid == 0) TE_TRACE(9);
+            if (act) {   // off the critical path: the state trajectory (the y product after the launch reads it)
+                float* hd = a.hs + (size_t)(t + 1) * B * H + (size_t)b * H + u0;
+                *reinterpret_cast<float4*>(hd) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
+                *reinterpret_cast<float4*>(hd + 4) = make_float4(hreg[4], hreg[5], hreg[6], hreg[7]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+static bool eval_runnable(int B, int H, const DeviceInfo& di, TeLayout* Lout) {
+    const int G = H / 8;
+    if (!(H % (TE_KC * TE_S) == 0 && H >= TE_KC * TE_S && B >= 1 && B <= 128) || G > di.n_sm) return false;
+    struct Entry { int B, H, ok; };
+    static Entry cache[16];
+    static int n_cache = 0;
+    int ok = -1;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].B == B && cache[i].H == H) ok = cache[i].ok;
+    TeLayout L = te_layout(B, H, di.max_smem_optin);
+    if (ok < 0) {
+        ok = 0;
+        if (L.NS >= 2 && (int)L.total <= di.max_smem_optin && (uint32_t)L.NS * L.stage_bytes >= (uint32_t)TE_S * L.slot_bytes &&
+            cudaFuncSetAttribute(k_gru_fwd_tc_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(TE_NT);
+            cfg.dynamicSmemBytes = L.total;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = TE_S;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k_gru_fwd_tc_eval, &cfg) == cudaSuccess) ok = ncl * TE_S >= G ? 1 : 0;
+            if (getenv("CVB_DEBUG")) fprintf(stderr, "[cvb] k_gru_fwd_tc_eval: %d co-resident clusters of %d (need %d), smem %u, ring %d\n", ncl, TE_S, G / TE_S, L.total, L.NS);
+        } else if (getenv("CVB_DEBUG")) {
+            fprintf(stderr, "[cvb] k_gru_fwd_tc_eval: not runnable at B=%d H=%d: ring %d stages, smem %u of %d\n", B, H, L.NS, L.total, di.max_smem_optin);
+        }
+        cudaGetLastError();
+        if (n_cache < 16) cache[n_cache++] = Entry{B, H, ok};
+    }
+    if (ok && Lout) *Lout = L;
+    return ok != 0;
+}
+
+bool gru_tc_eval_supported(int B, int H, int out, const DeviceInfo& di) { return out >= 1 && eval_runnable(B, H, di, nullptr); }
+
+// scratch (floats): W_fb [3H,H] | hx | counter
+size_t gru_tc_eval_scratch_floats(int B, int H) {
+    size_t MB = (B + 7) / 8;
+    size_t hx = (size_t)2 * 2 * (H / TE_KC) * MB * 512 / 2;
+    return round_up_sz((size_t)3 * H * H, 64) + round_up_sz(hx, 64) + 64;
+}
+
+__global__ void k_add_rowvec(float* __restrict__ dst, size_t rows, int cols, const float* __restrict__ v) {
+    const size_t n = rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += v[i % cols];
+}
+
+// Inference forward of the recurrence with the folded feedback.  f.gx must hold W_x xc + b_ih; it is modified in place.
+// Fills hs[1..T] and ys[1..T]; `cfb` is a 3H-float scratch.
+int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, float* cfb, cudaStream_t s) {
+    if (f.T <= 0 || f.B <= 0) return 0;
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+    TeLayout L;
+    CVB_REQUIRE(eval_runnable(f.B, f.H, di, &L), "gru_ar_fwd_tc_eval: unsupported shape B=%d H=%d", f.B, f.H);
+    const int B = f.B, T = f.T, H = f.H, out = f.out;
+    float* Wfb = scratch;
+    const size_t wfb_f = round_up_sz((size_t)3 * H * H, 64);
+    const size_t hx_f = round_up_sz((size_t)2 * 2 * (H / TE_KC) * L.MB * 512 / 2, 64);
+    // W_fb = W_y W_o  ([3H,out] x [out,H]), c_fb = W_y b_o, gx[0] += y_in W_y^T, gx[t >= 1] += c_fb   (cuBLAS fp32, exact products)
+    if (int rc = gemm_rm(s, false, false, 3 * H, H, out, 1.f, f.Wy, f.ldwy, f.Wo, H, 0.f, Wfb, H)) return rc;
+    if (int rc = gemm_rm(s, false, false, 3 * H, 1, out, 1.f, f.Wy, f.ldwy, f.bo, 1, 0.f, cfb, 1)) return rc;
+    if (int rc = gemm_rm(s, false, true, B, 3 * H, out, 1.f, f.ys, out, f.Wy, f.ldwy, 1.f, const_cast<float*>(f.gx), 3 * H)) return rc;
+    // the first step's feedback is the CALLER's y_in, not W_o h_in + b_o: take the folded term the kernel will add back out
+    if (int rc = gemm_rm(s, false, true, B, 3 * H, H, -1.f, f.hs, H, Wfb, H, 1.f, const_cast<float*>(f.gx), 3 * H)) return rc;
+    if (T > 1) {
+        const size_t rows = (size_t)(T - 1) * B;
+        size_t g = ceil_div_sz(rows * 3 * H, 256);
+        if (g > 148 * 8) g = 148 * 8;
+        k_add_rowvec<<<(int)g, 256, 0, s>>>(const_cast<float*>(f.gx) + (size_t)B * 3 * H, rows, 3 * H, cfb);
+        CVB_LAUNCH_CHECK();
+    }
+    GruTcEvalArgs a;
+    a.gx = f.gx;
+    a.Whh = f.Whh;
+    a.Wfb = Wfb;
+    a.bhh = f.bhh;
+    a.hs = f.hs;
+    a.hx = reinterpret_cast<uint16_t*>(scratch + wfb_f);
+    a.ctr = reinterpret_cast<unsigned*>(scratch + wfb_f + hx_f);
+    a.B = B;
+    a.T = T;
+    a.H = H;
+    a.smem_max = di.max_smem_optin;
+    a.keepalive = 1;
+    if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
+    a.trace = nullptr;
+    const char* trace_file = getenv("CVB_TRACE_FILE_EVAL");
+    const size_t trace_bytes = (size_t)(T + 1) * 64 * sizeof(long long);
+    if (trace_file && trace_file[0]) {
+        CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
+        CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));
+    }
+    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, 64 * sizeof(float), s));
+    CVB_CHECK(cudaFuncSetAttribute(k_gru_fwd_tc_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(H / 8);
+    cfg.blockDim = dim3(TE_NT);
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TE_S;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    const char* nocoop = getenv("CVB_TC_NOCOOP");
+    cfg.numAttrs = (nocoop && nocoop[0] == '1') ? 1 : 2;
+    prof_begin(s, CVB_PROF_GRU_FWD);
+    CVB_CHECK(cudaLaunchKernelEx(&cfg, k_gru_fwd_tc_eval, a));
+    prof_end(s, CVB_PROF_GRU_FWD);
+    count_launch();
+    if (a.trace) {   // profiling hook only: synchronises
+        CVB_CHECK(cudaStreamSynchronize(s));
+        long long* h = (long long*)malloc(trace_bytes);
+        CVB_CHECK(cudaMemcpy(h, a.trace, trace_bytes, cudaMemcpyDeviceToHost));
+        if (FILE* fp = fopen(trace_file, "wb")) {
+            fwrite(h, 1, trace_bytes, fp);
+            fclose(fp);
+        }
+        free(h);
+        CVB_CHECK(cudaFree(a.trace));
+    }
+    // all outputs at once: ys[1..T] = hs[1..T] W_o^T + b_o
+    if (int rc = fill_rows(s, f.ys + (size_t)B * out, (size_t)T * B, out, out, f.bo)) return rc;
+    if (int rc = gemm_rm(s, false, true, T * B, out, H, 1.f, f.hs + (size_t)B * H, H, f.Wo, H, 1.f, f.ys + (size_t)B * out, out)) return rc;
+    return 0;
+}
+
+}  // namespace cvb

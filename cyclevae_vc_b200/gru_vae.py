@@ -98,11 +98,13 @@ class _GruRnnFn(torch.autograd.Function):
     h_in [B,H] | None, masks (time-major) | None, then the parameters in `mod._param_order`."""
 
     @staticmethod
-    def forward(ctx, mod, head_mode, lat_dim, x, y_in, h_in, mask_conv_tm, mask_gru_tm, *params):
+    def forward(ctx, mod, head_mode, lat_dim, want_grad, x, y_in, h_in, mask_conv_tm, mask_gru_tm, *params):
         B, T, _ = x.shape
         dev = x.device
         net = mod._net_struct(params)
-        needs_grad = any(ctx.needs_input_grad)   # False under torch.no_grad()
+        # decided by the caller from torch.is_grad_enabled(): inside Function.forward grad mode is always off and
+        # ctx.needs_input_grad stays True for parameters even under torch.no_grad()
+        needs_grad = bool(want_grad) and any(ctx.needs_input_grad)
         training = 1 if needs_grad else 0
         netp = C.byref(net)
         fe_n = lib.cvb_frontend_ws_floats(netp, B, T)
@@ -134,13 +136,13 @@ class _GruRnnFn(torch.autograd.Function):
         d_trj = _f32c(d_trj) if d_trj is not None else torch.zeros(B, T, mod.out_dim, device=dev)
         d_y_last = _f32c(d_y_last) if d_y_last is not None else None
         d_h_last = _f32c(d_h_last) if d_h_last is not None else None
-        need = ctx.needs_input_grad  # (mod, head, lat, x, y_in, h_in, mc, mg, *params)
-        dx = torch.empty_like(x) if need[3] else None
-        dy_in = torch.empty(B, mod.out_dim, device=dev) if need[4] else None
-        dh_in = torch.empty(B, mod.hidden_units, device=dev) if (ctx.has_h and need[5]) else None
+        need = ctx.needs_input_grad  # (mod, head, lat, want_grad, x, y_in, h_in, mc, mg, *params)
+        dx = torch.empty_like(x) if need[4] else None
+        dy_in = torch.empty(B, mod.out_dim, device=dev) if need[5] else None
+        dh_in = torch.empty(B, mod.hidden_units, device=dev) if (ctx.has_h and need[6]) else None
         grads = CvbNetGrads()
         gts = []
-        for (field, idx), p, nd in zip(mod._param_fields, params, need[8:]):
+        for (field, idx), p, nd in zip(mod._param_fields, params, need[9:]):
             g = torch.empty_like(p) if nd else None
             gts.append(g)
             if g is not None:
@@ -153,7 +155,7 @@ class _GruRnnFn(torch.autograd.Function):
         check(lib.cvb_gru_rnn_backward(netp, B, T, ptr(x), ptr(mask_conv_tm), ptr(mask_gru_tm), ctx.head_mode, ctx.lat_dim,
                                        None, ptr(d_trj), ptr(d_y_last), ptr(d_h_last), ptr(fe_ws), ptr(rec_ws), ptr(scratch),
                                        ptr(dx), ptr(dy_in), ptr(dh_in), C.byref(grads), _stream()), "cvb_gru_rnn_backward")
-        return (None, None, None, dx, dy_in, dh_in, None, None, *gts)
+        return (None, None, None, None, dx, dy_in, dh_in, None, None, *gts)
 
 
 class GRU_RNN(nn.Module):
@@ -288,13 +290,14 @@ class GRU_RNN(nn.Module):
             head = _lib.HEAD_CLAMP
         else:
             head = _lib.HEAD_NONE
+        params = self._param_list()
+        want_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or xb.requires_grad or y0.requires_grad
+                                                 or (h0 is not None and h0.requires_grad))
         max_rows = MAX_ROWS_PER_LAUNCH
         if B > 64:
-            params = self._param_list()
-            max_rows = int(lib.cvb_recurrence_max_rows(C.byref(self._net_struct(params)),
-                                                       1 if (torch.is_grad_enabled() and any(p.requires_grad for p in params)) else 0))
+            max_rows = int(lib.cvb_recurrence_max_rows(C.byref(self._net_struct(params)), 1 if want_grad else 0))
         if B <= max_rows:
-            trj, y_last, h_last = _GruRnnFn.apply(self, head, int(lat_dim), xb, y0, h0, mc, mg, *self._param_list())
+            trj, y_last, h_last = _GruRnnFn.apply(self, head, int(lat_dim), want_grad, xb, y0, h0, mc, mg, *params)
         else:
             # utterances never interact inside GRU_RNN.forward: wide batches (stage-6 conversion of many utterances at
             # once) run as independent slices of the row count one persistent tensor-core launch holds
@@ -303,9 +306,9 @@ class GRU_RNN(nn.Module):
             outs = []
             for lo in range(0, B, per):
                 hi = min(B, lo + per)
-                outs.append(_GruRnnFn.apply(self, head, int(lat_dim), xb[lo:hi], y0[lo:hi], None if h0 is None else h0[lo:hi],
+                outs.append(_GruRnnFn.apply(self, head, int(lat_dim), want_grad, xb[lo:hi], y0[lo:hi], None if h0 is None else h0[lo:hi],
                                             None if mc is None else mc[:, lo:hi].contiguous(),
-                                            None if mg is None else mg[:, lo:hi].contiguous(), *self._param_list()))
+                                            None if mg is None else mg[:, lo:hi].contiguous(), *params))
             trj, y_last, h_last = (torch.cat([o[i] for o in outs], 0) for i in range(3))
         if not batched:
             trj = trj.squeeze(0)

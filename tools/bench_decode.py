@@ -27,6 +27,10 @@ def run():
 for _ in range(2):
     out = run()
 torch.cuda.synchronize()
+import ctypes as C  # noqa: E402
+from cyclevae_vc_b200._lib import lib  # noqa: E402
+lib.cvb_profile_reset()
+lib.cvb_profile_enable(2)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(3):
@@ -34,5 +38,11 @@ for _ in range(3):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
+lib.cvb_profile_enable(0)
+prof = {}
+for kind, name in ((0, "recurrence"), (2, "gemm")):
+    tot, n = C.c_float(0), C.c_int(0)
+    lib.cvb_profile_summary(kind, C.byref(tot), C.byref(n))
+    prof[name] = {"ms_per_run": tot.value / 3, "launches_per_run": n.value // 3}
 print(json.dumps({"workload": f"stage-6 conversion, {N_UTT} utterances x {T} frames, hu1024 ld32, 1 ENC + 1 DEC pass, eval",
-                  "ms": ms, "frames_per_s": N_UTT * T / (ms * 1e-3), "finite": bool(torch.isfinite(out).all())}))
+                  "ms": ms, "frames_per_s": N_UTT * T / (ms * 1e-3), "finite": bool(torch.isfinite(out).all()), "profile": prof}))

@@ -88,8 +88,31 @@ def report(path, names):
         print(f"  ev{ev:2d} {names.get(ev, '?'):40s} {off:9.0f} cyc  {off / MHZ:7.2f} us")
 
 
+NAMES_EVAL = {0: "fin: step start", 1: "fin: d1_full seen", 2: "fin: exchange copies issued", 3: "fin: inbox complete", 5: "fin: partial sums added",
+              10: "fin: gates done", 7: "fin: h published", 8: "fin: proxy fence done", 9: "fin: counter arrive", 14: "prod: counter seen"}
+NAMES_EVAL.update({40 + i: f"mma: chunk {i} full" for i in range(8)})
+
+
+def run_eval():
+    enc = cvb.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, do_prob=0.5, scale_out_flag=False).cuda().eval()
+    enc.apply(cvb.initialize)
+    x = torch.randn(B, T, 54, device="cuda")
+    y0 = torch.zeros(B, 1, 64, device="cuda")
+    path = os.path.join(ROOT, "gpurun_out", "trace_eval.bin")
+    with torch.no_grad():
+        for i in range(3):
+            os.environ["CVB_TRACE_FILE_EVAL"] = path
+            enc(x, y0, clamp_vae=True, lat_dim=32)
+            torch.cuda.synchronize()
+    os.environ.pop("CVB_TRACE_FILE_EVAL", None)
+    return path
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    if len(sys.argv) > 3 and sys.argv[3] == "eval":
+        report(run_eval(), NAMES_EVAL)
+        sys.exit(0)
     p = run("bwd")
     report(p.replace("trace_bwd", "trace_fwd"), NAMES_FWD)
     report(p, NAMES_BWD)
