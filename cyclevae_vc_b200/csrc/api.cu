@@ -52,7 +52,7 @@ static FwdScratch fwd_scratch(const cvb_net* net, int B, int T) {
     S.tc = off;
     if (gru_tc_shape_ok(B, net->hidden, net->out_dim)) {
         size_t a = gru_tc_scratch_floats(B, net->hidden);
-        size_t e = gru_tc_eval_scratch_floats(B, net->hidden) + r4((size_t)3 * H);   // folded inference path: W_fb | hx | ctr | c_fb
+        size_t e = gru_tc_eval_scratch_floats(B, net->hidden) + r4((size_t)6 * H);   // folded inference path: W_fb | hx | ctr | c_fb | b_ih + c_fb
         off += r4(a > e ? a : e);
     }
     S.total = off;
@@ -227,11 +227,29 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     float* xc = fe_ws + frontend_xc_offset(net, B, T);
     if (int rc = frontend_fwd(net, B, T, x_bm, mask_conv_tm, fe_ws, xc, s)) return rc;
     float* gx = scratch + FS.gx;
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+    GruFwdArgs a;
+    a.H = H;
+    a.out = out;
+    a.Wy = net->w_ih + C;
+    a.ldwy = TI;
+    a.Wo = net->out_w;
+    a.bo = net->out_b;
+    // inference (no dropout): feedback folded into the recurrent matrix, all y_t from one product afterwards
+    const bool fold = want_tc() && !training && !mask_gru_tm && want_fold() && gru_tc_eval_supported(B, H, out, di);
+    float* esc = scratch + FS.tc;
+    float* cfb = esc + gru_tc_eval_scratch_floats(B, H);   // c_fb | b_ih + c_fb
+    const float* gx_bias = net->b_ih;
+    if (fold) {
+        if (int rc = gru_tc_eval_prepare(a, net->b_ih, esc, cfb, s)) return rc;
+        gx_bias = cfb + 3 * H;
+    }
     if (want_tc_gemm() && gemm_tc_eligible((int)TB, 3 * H, C)) {
         // gx = xc W_x^T + b_ih: bias in the GEMM epilogue (no fill pass, no read-modify-write of the 3H-wide rows)
-        if (int rc = gemm_tc(s, false, true, (int)TB, 3 * H, C, xc, C, net->w_ih, TI, false, net->b_ih, gx, 3 * H, true)) return rc;
+        if (int rc = gemm_tc(s, false, true, (int)TB, 3 * H, C, xc, C, net->w_ih, TI, false, gx_bias, gx, 3 * H, true)) return rc;
     } else {
-        if (int rc = fill_rows(s, gx, TB, 3 * H, 3 * H, net->b_ih)) return rc;
+        if (int rc = fill_rows(s, gx, TB, 3 * H, 3 * H, gx_bias)) return rc;
         if (int rc = gemm_rm(s, false, true, (int)TB, 3 * H, C, 1.f, xc, C, net->w_ih, TI, 1.f, gx, 3 * H)) return rc;
     }
     float* hs = rec_ws + RL.hs;
@@ -241,14 +259,9 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     else if (int rc = zero_floats(s, hs, (size_t)B * H))
         return rc;
     CVB_CHECK(cudaMemcpyAsync(ys, y_in, (size_t)B * out * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    GruFwdArgs a;
     a.gx = gx;
     a.Whh = net->w_hh;
     a.bhh = net->b_hh;
-    a.Wy = net->w_ih + C;
-    a.ldwy = TI;
-    a.Wo = net->out_w;
-    a.bo = net->out_b;
     a.mask = mask_gru_tm;
     a.hs = hs;
     a.ys = ys;
@@ -261,20 +274,12 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     a.bar = reinterpret_cast<unsigned*>(scratch + FS.bar);
     a.B = B;
     a.T = T;
-    a.H = H;
-    a.out = out;
-    {
-        DeviceInfo di;
-        if (int rc = get_device_info(&di)) return rc;
-        if (want_tc() && !training && !mask_gru_tm && want_fold() && gru_tc_eval_supported(B, H, out, di)) {
-            // inference (no dropout): feedback folded into the recurrent matrix, all y_t from one product afterwards
-            float* esc = scratch + FS.tc;
-            if (int rc = gru_ar_fwd_tc_eval(a, esc, esc + gru_tc_eval_scratch_floats(B, H), s)) return rc;
-        } else if (want_tc() && gru_tc_supported(B, H, out, di)) {
-            if (int rc = gru_ar_fwd_tc(a, scratch + FS.tc, s)) return rc;
-        } else {
-            if (int rc = gru_ar_fwd_exact(a, s)) return rc;
-        }
+    if (fold) {
+        if (int rc = gru_ar_fwd_tc_eval(a, esc, cfb, s)) return rc;
+    } else if (want_tc() && gru_tc_supported(B, H, out, di)) {
+        if (int rc = gru_ar_fwd_tc(a, scratch + FS.tc, s)) return rc;
+    } else {
+        if (int rc = gru_ar_fwd_exact(a, s)) return rc;
     }
     size_t smem = head_mode == CVB_HEAD_SCALE_OUT ? (size_t)(out * out + out) * sizeof(float) : 0;
     CVB_REQUIRE(smem <= 48 * 1024, "scale_out matrix too large (out_dim=%d)", out);

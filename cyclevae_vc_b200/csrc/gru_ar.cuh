@@ -56,7 +56,9 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s);
 // inference-only forward with the y feedback folded into the recurrent matrix (one exchange per step), gru_tc_eval.cu
 bool gru_tc_eval_supported(int B, int H, int out, const DeviceInfo& di);
 size_t gru_tc_eval_scratch_floats(int B, int H);
-int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, float* cfb, cudaStream_t s);
+// prepare (weights only; cfb = 6H floats: c_fb | b_ih + c_fb)  ->  caller's gx product with bias cfb + 3H  ->  launch
+int gru_tc_eval_prepare(const GruFwdArgs& f, const float* bih, float* scratch, float* cfb, cudaStream_t s);
+int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStream_t s);
 
 // tensor-core BPTT over thread-block clusters, gru_tc_bwd.cu
 bool gru_tc_bwd_shape_ok(int B, int H, int out);

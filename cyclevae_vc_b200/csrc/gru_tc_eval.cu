@@ -388,14 +388,29 @@ size_t gru_tc_eval_scratch_floats(int B, int H) {
     return round_up_sz((size_t)3 * H * H, 64) + round_up_sz(hx, 64) + 64;
 }
 
-__global__ void k_add_rowvec(float* __restrict__ dst, size_t rows, int cols, const float* __restrict__ v) {
-    const size_t n = rows * cols;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += v[i % cols];
+__global__ void k_add_rowvec(float* __restrict__ dst, int rows, int cols, float alpha, const float* __restrict__ v) {
+    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < cols; col += gridDim.x * blockDim.x) {
+        const float x = alpha * v[col];
+        for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(size_t)r * cols + col] += x;
+    }
 }
 
-// Inference forward of the recurrence with the folded feedback.  f.gx must hold W_x xc + b_ih; it is modified in place.
-// Fills hs[1..T] and ys[1..T]; `cfb` is a 3H-float scratch.
-int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, float* cfb, cudaStream_t s) {
+// Weight-only prologue of the folded inference path, BEFORE the input-side product:  W_fb = W_y W_o (scratch),
+// cfb[0..3H) = c_fb = W_y b_o,  cfb[3H..6H) = b_ih + c_fb = the bias the caller gives its gx product so that every row
+// of gx already carries c_fb (no extra pass over the [T,B,3H] buffer).  cuBLAS fp32, exact products.
+int gru_tc_eval_prepare(const GruFwdArgs& f, const float* bih, float* scratch, float* cfb, cudaStream_t s) {
+    const int H = f.H, out = f.out;
+    if (int rc = gemm_rm(s, false, false, 3 * H, H, out, 1.f, f.Wy, f.ldwy, f.Wo, H, 0.f, scratch, H)) return rc;
+    if (int rc = gemm_rm(s, false, false, 3 * H, 1, out, 1.f, f.Wy, f.ldwy, f.bo, 1, 0.f, cfb, 1)) return rc;
+    CVB_CHECK(cudaMemcpyAsync(cfb + 3 * H, bih, (size_t)3 * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    k_add_rowvec<<<dim3(ceil_div_sz((size_t)3 * H, 256), 1), 256, 0, s>>>(cfb + 3 * H, 1, 3 * H, 1.f, cfb);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Inference forward of the recurrence with the folded feedback, after gru_tc_eval_prepare and the caller's
+// gx = W_x xc + (b_ih + c_fb); gx[0] is modified in place.  Fills hs[1..T] and ys[1..T].
+int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStream_t s) {
     if (f.T <= 0 || f.B <= 0) return 0;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
@@ -405,19 +420,13 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, float* cfb, cudaStream_t s
     float* Wfb = scratch;
     const size_t wfb_f = round_up_sz((size_t)3 * H * H, 64);
     const size_t hx_f = round_up_sz((size_t)2 * 2 * (H / TE_KC) * L.MB * 512 / 2, 64);
-    // W_fb = W_y W_o  ([3H,out] x [out,H]), c_fb = W_y b_o, gx[0] += y_in W_y^T, gx[t >= 1] += c_fb   (cuBLAS fp32, exact products)
-    if (int rc = gemm_rm(s, false, false, 3 * H, H, out, 1.f, f.Wy, f.ldwy, f.Wo, H, 0.f, Wfb, H)) return rc;
-    if (int rc = gemm_rm(s, false, false, 3 * H, 1, out, 1.f, f.Wy, f.ldwy, f.bo, 1, 0.f, cfb, 1)) return rc;
-    if (int rc = gemm_rm(s, false, true, B, 3 * H, out, 1.f, f.ys, out, f.Wy, f.ldwy, 1.f, const_cast<float*>(f.gx), 3 * H)) return rc;
-    // the first step's feedback is the CALLER's y_in, not W_o h_in + b_o: take the folded term the kernel will add back out
-    if (int rc = gemm_rm(s, false, true, B, 3 * H, H, -1.f, f.hs, H, Wfb, H, 1.f, const_cast<float*>(f.gx), 3 * H)) return rc;
-    if (T > 1) {
-        const size_t rows = (size_t)(T - 1) * B;
-        size_t g = ceil_div_sz(rows * 3 * H, 256);
-        if (g > 148 * 8) g = 148 * 8;
-        k_add_rowvec<<<(int)g, 256, 0, s>>>(const_cast<float*>(f.gx) + (size_t)B * 3 * H, rows, 3 * H, cfb);
-        CVB_LAUNCH_CHECK();
-    }
+    // the first step's feedback is the CALLER's y_in, not W_o h_in + b_o:  gx[0] += W_y y_in - c_fb - W_fb h_in  takes
+    // the folded terms (the bias above, the product the kernel will add) back out
+    float* gx0 = const_cast<float*>(f.gx);
+    if (int rc = gemm_rm(s, false, true, B, 3 * H, out, 1.f, f.ys, out, f.Wy, f.ldwy, 1.f, gx0, 3 * H)) return rc;
+    if (int rc = gemm_rm(s, false, true, B, 3 * H, H, -1.f, f.hs, H, Wfb, H, 1.f, gx0, 3 * H)) return rc;
+    k_add_rowvec<<<dim3(ceil_div_sz((size_t)3 * H, 256), B < 16 ? B : 16), 256, 0, s>>>(gx0, B, 3 * H, -1.f, cfb);
+    CVB_LAUNCH_CHECK();
     GruTcEvalArgs a;
     a.gx = f.gx;
     a.Whh = f.Whh;
