@@ -185,25 +185,30 @@ size_t cvb_scratch_floats(const cvb_net* net, int B, int T, int training) {
     return f;
 }
 
-int cvb_recurrence_max_rows(const cvb_net* net, int training) {
+int cvb_recurrence_max_rows(const cvb_net* net, int mode) {
     // largest batch-row count (multiple of 8, <= 128) one launch of the tensor-core recurrence kernels holds at this
-    // network shape; 128 when only the fp32-FMA kernels apply (they tile the batch themselves)
+    // network shape; 128 when only the fp32-FMA kernels apply (they tile the batch themselves).
+    // mode 0: inference without recurrent dropout (folded kernel), 1: forward + BPTT, 2: forward only, with dropout masks
     if (!net || !want_tc()) return 128;
     DeviceInfo di;
     if (get_device_info(&di)) return 128;
-    static int cache_key[8], cache_val[8], n_cache = 0;
-    const int key = (net->hidden * 131 + net->out_dim) * 2 + (training ? 1 : 0);
+    static int cache_key[12], cache_val[12], n_cache = 0;
+    const bool fold = mode == 0 && want_fold();
+    const int key = (net->hidden * 131 + net->out_dim) * 4 + (fold ? 3 : mode == 1 ? 1 : 0);
     for (int i = 0; i < n_cache; ++i)
         if (cache_key[i] == key) return cache_val[i];
     int best = 128;
     for (int B = 128; B >= 8; B -= 8) {
-        if (gru_tc_supported(B, net->hidden, net->out_dim, di) && (!training || gru_tc_bwd_supported(B, net->hidden, net->out_dim, di))) {
+        const bool ok = fold ? gru_tc_eval_supported(B, net->hidden, net->out_dim, di)
+                             : gru_tc_supported(B, net->hidden, net->out_dim, di) &&
+                                   (mode != 1 || gru_tc_bwd_supported(B, net->hidden, net->out_dim, di));
+        if (ok) {
             best = B;
             break;
         }
         if (B == 8) best = 128;
     }
-    if (n_cache < 8) {
+    if (n_cache < 12) {
         cache_key[n_cache] = key;
         cache_val[n_cache++] = best;
     }

@@ -29,6 +29,7 @@ constexpr int TE_NW = 4 * TE_UB;    // rows of the folded operand: r', z', hn, i
 
 struct TeLayout {
     int MB, nch, NS;
+    int KCA, nsub;       // K extent of one ring stage of the h operand (64, or 32 when 64 leaves < 3 stages) and stages per step
     uint32_t half, stage_bytes, w_chunk_bytes, slot_bytes;
     uint32_t off_ring, off_w, off_inbox, off_bias, off_bar, total;
 };
@@ -37,13 +38,21 @@ __host__ __device__ inline TeLayout te_layout(int B, int H, int smem_max) {
     TeLayout L;
     L.MB = (B + 7) / 8;
     L.nch = H / TE_KC / TE_S;
-    L.half = (uint32_t)L.MB * 1024u;
-    L.stage_bytes = 2u * L.half;
     L.w_chunk_bytes = 2u * (TE_NW / 8) * 1024u;   // [hi: 16 row groups][lo: 16 row groups] x 1 KB
     L.slot_bytes = (uint32_t)L.MB * 8u * 128u;    // [rows][32 floats]
-    const uint32_t inbox = ((uint32_t)TE_S * L.slot_bytes + 127u) & ~127u;
+    // the own partial sums stay in registers (TMEM lane == batch row on both sides): S-1 slots travel
+    const uint32_t inbox = ((uint32_t)(TE_S - 1) * L.slot_bytes + 127u) & ~127u;
     const uint32_t fixed = (uint32_t)L.nch * L.w_chunk_bytes + inbox + 128u + 256u;
-    int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
+    L.KCA = 64;
+    int ns = 0;
+    for (;;) {
+        L.half = (uint32_t)L.MB * (uint32_t)L.KCA * 16u;   // [MB row groups][KCA/8 k blocks][8 rows][8 k] fp16
+        L.stage_bytes = 2u * L.half;
+        ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
+        if (ns >= 3 || L.KCA == 32) break;
+        L.KCA = 32;
+    }
+    L.nsub = L.nch * TE_KC / L.KCA;
     L.NS = ns > 6 ? 6 : ns;
     const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
     L.off_ring = 0;   // idle between a step's last chunk and the next step's first: doubles as the staging of the outgoing sums
@@ -61,7 +70,7 @@ struct GruTcEvalArgs {
     const float* Wfb;    // [3H,H] = W_y W_o
     const float* bhh;    // [3H]
     float* hs;           // [T+1,B,H], slot 0 = h_in
-    uint16_t* hx;        // [2 slots][2 parts][H/64 chunks][MB][8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
+    uint16_t* hx;        // [2 slots][2 parts][H/KCA chunks][MB][KCA/8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
     unsigned* ctr;       // zero-initialised
     int B, T, H;
     int smem_max;
@@ -100,16 +109,17 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     uint8_t* ring = smem + L.off_ring;
-    float* stage = reinterpret_cast<float*>(ring);                 // [S (to)][MB*8][32], aliases the (idle) ring
+    float* stage = reinterpret_cast<float*>(ring);                 // [S-1 (to)][MB*8][32], aliases the (idle) ring
     uint8_t* sW = smem + L.off_w;
-    float* inbox = reinterpret_cast<float*>(smem + L.off_inbox);   // [S (from)][MB*8][32]
+    float* inbox = reinterpret_cast<float*>(smem + L.off_inbox);   // [S-1 (from)][MB*8][32]
     float* sBh = reinterpret_cast<float*>(smem + L.off_bias);      // [3][8] b_hh of the own units
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* empty = full + 8;
     uint64_t* d1_full = empty + 8;
     uint64_t* inbox_full = d1_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbox_full + 1);
-    const size_t hx_part = (size_t)(H / TE_KC) * L.MB * 512;
+    const size_t hx_part = (size_t)H * L.MB * 8;
+    const uint32_t kca_sh = L.KCA == 64 ? 6u : 5u;   // log2(KCA)
 
     // ---- one-time setup: folded weights -> fp16 hi/lo in UMMA K-major core-matrix order ------------------
     {
@@ -154,19 +164,20 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
         int s = 0;
         uint32_t ph = 1;
         for (int t = 0; t < T; ++t) {
-            const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
+            const size_t sub_elems = (size_t)L.MB * L.KCA * 8;
+            const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nsub) * sub_elems;
             if (lane == 0) {
                 spin_until(a.ctr, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy
                 TE_TRACE(14);
             }
             __syncwarp();
-            for (int ch = 0; ch < L.nch; ++ch) {
+            for (int ch = 0; ch < L.nsub; ++ch) {
                 if (lane == 0) {
                     mbar_wait(&empty[s], ph);
                     uint8_t* dst = ring + (size_t)s * L.stage_bytes;
                     mbar_expect_tx(&full[s], 2 * L.half);
-                    bulk_g2s(dst, src + (size_t)ch * L.MB * 512, L.half, &full[s]);
-                    bulk_g2s(dst + L.half, src + hx_part + (size_t)ch * L.MB * 512, L.half, &full[s]);
+                    bulk_g2s(dst, src + (size_t)ch * sub_elems, L.half, &full[s]);
+                    bulk_g2s(dst + L.half, src + hx_part + (size_t)ch * sub_elems, L.half, &full[s]);
                 }
                 __syncwarp();
                 if (++s == L.NS) {
@@ -178,13 +189,14 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
     } else if (warp == 1) {
         // ================= MMA issuer =========================================================================
         const uint32_t idesc_s = idesc_f16_f32(128, 2 * TE_NW), idesc_h = idesc_f16_f32(128, TE_NW), idesc_dummy = idesc_f16_f32(128, 16);
-        const uint64_t dA0 = smem_desc(smem_u32(ring), 128, 1024);
+        const uint64_t dA0 = smem_desc(smem_u32(ring), 128, (uint32_t)L.KCA * 16u);
         const uint64_t dW0 = smem_desc(smem_u32(sW), 128, 1024);
         const uint32_t a_step = L.stage_bytes >> 4, half16 = L.half >> 4, w_step = L.w_chunk_bytes >> 4;
+        const int kca16 = L.KCA >> 4;
         int s = 0;
         uint32_t ph = 0;
         for (int t = 0; t < T; ++t) {
-            for (int ch = 0; ch < L.nch; ++ch) {
+            for (int ch = 0; ch < L.nsub; ++ch) {
                 for (;;) {   // poll; while idle keep the tensor pipe warm (see gru_tc.cu)
                     uint32_t ok = (lane == 0) ? (mbar_test_wait(&full[s], ph) ? 1u : 0u) : 0u;
                     ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -194,14 +206,15 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                 if (lane == 0 && ch < 8) TE_TRACE(40 + ch);
                 tc_fence_after();
                 const uint64_t da = dA0 + (uint64_t)((uint32_t)s * a_step);
-                const uint64_t db = dW0 + (uint64_t)((uint32_t)ch * w_step);
-#pragma unroll
-                for (int k16 = 0; k16 < TE_KC / 16; ++k16) {
+                // weights stay in 64-wide K chunks; stage ch covers k = [ch*KCA, +KCA) of the slice
+                const uint32_t kq = (uint32_t)ch << kca_sh;
+                const uint64_t db = dW0 + (uint64_t)((kq >> 6) * w_step + ((kq & 63u) >> 4) * 16u);
+                for (int k16 = 0; k16 < kca16; ++k16) {
                     mma_bf16_ss_elect(tmem, da + 16u * k16, db + 16u * k16, idesc_s, (ch | k16) != 0);
                     mma_bf16_ss_elect(tmem, da + half16 + 16u * k16, db + 16u * k16, idesc_h, true);
                 }
                 mma_commit_elect(&empty[s]);
-                if (ch == L.nch - 1) mma_commit_elect(d1_full);
+                if (ch == L.nsub - 1) mma_commit_elect(d1_full);
                 if (++s == L.NS) {
                     s = 0;
                     ph ^= 1;
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             uint4 hh, hl;
             split8_f16(hreg, hh, hl);
             if (act) {
-                const size_t off = ((size_t)(u0 >> 6) * L.MB + (b >> 3)) * 512 + (size_t)((u0 & 63) >> 3) * 64 + (size_t)(b & 7) * 8;
+                const size_t off = (((size_t)(u0 >> kca_sh) * L.MB + (b >> 3)) << (kca_sh + 3)) + (size_t)((u0 & (L.KCA - 1)) >> 3) * 64 + (size_t)(b & 7) * 8;
                 *reinterpret_cast<uint4*>(a.hx + off) = hh;
                 *reinterpret_cast<uint4*>(a.hx + hx_part + off) = hl;
             }
@@ -244,11 +257,12 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                 }
             }
             if (etid == 0) TE_TRACE(0);
-            if (etid == 0) mbar_expect_tx(inbox_full, (uint32_t)TE_S * L.slot_bytes);
+            if (etid == 0) mbar_expect_tx(inbox_full, (uint32_t)(TE_S - 1) * L.slot_bytes);
             mbar_wait(d1_full, (uint32_t)t & 1);
             if (etid == 0) TE_TRACE(1);
             tc_fence_after();
-            // partial sums (main + correction halves) of the block's units -> the finalisers' inboxes
+            // partial sums (main + correction halves) of the block's units -> the finalisers' inboxes; the own ones stay here
+            float own[32];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
 #pragma unroll
@@ -257,11 +271,15 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                     tmem_ld_x16(taddr + g * TE_UB + 16 * k, v);
                     tmem_ld_x16(taddr + TE_NW + g * TE_UB + 16 * k, v2);
                     tmem_ld_wait();
-                    if (b < L.MB * 8) {
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int p = 2 * k + h2;   // destination CTA of the cluster
+                        if (p == j) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) own[g * 8 + q] = v[8 * h2 + q] + v2[8 * h2 + q];
+                        } else if (b < L.MB * 8) {
                             // a row is 8 x 16 B; slot q of row b sits at q ^ (b & 7) so that a quarter warp covers all 32 banks
-                            float* row = stage + (size_t)(2 * k + h2) * slot_f + b * 32;
+                            float* row = stage + (size_t)(p - (p > j ? 1 : 0)) * slot_f + b * 32;
                             float* d = row + (((2 * g) ^ (b & 7)) << 2);
                             float* d1 = row + (((2 * g + 1) ^ (b & 7)) << 2);
                             *reinterpret_cast<float4*>(d) = make_float4(v[8 * h2 + 0] + v2[8 * h2 + 0], v[8 * h2 + 1] + v2[8 * h2 + 1],
@@ -275,18 +293,23 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             tc_fence_before();
             fence_proxy_async_smem();
             named_bar_sync(3, 128);
-            if (etid < TE_S)
-                bulk_s2c(mapa(inbox_addr + (uint32_t)j * L.slot_bytes, (uint32_t)etid), stage + (size_t)etid * slot_f, L.slot_bytes,
-                         mapa(inbox_bar_addr, (uint32_t)etid));
+            if (etid < TE_S && etid != j)   // slot order on both sides: the other CTAs by rank
+                bulk_s2c(mapa(inbox_addr + (uint32_t)(j - (j > etid ? 1 : 0)) * L.slot_bytes, (uint32_t)etid),
+                         stage + (size_t)(etid - (etid > j ? 1 : 0)) * slot_f, L.slot_bytes, mapa(inbox_bar_addr, (uint32_t)etid));
             if (etid == 0) TE_TRACE(2);
             mbar_wait_cluster(inbox_full, (uint32_t)t & 1);
             if (etid == 0) TE_TRACE(3);
             float ar[8], az[8], ahn[8], ain[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) ar[q] = az[q] = ahn[q] = ain[q] = 0.f;
+            for (int q = 0; q < 8; ++q) {
+                ar[q] = own[q];
+                az[q] = own[8 + q];
+                ahn[q] = own[16 + q];
+                ain[q] = own[24 + q];
+            }
             if (act) {
 #pragma unroll
-                for (int p = 0; p < TE_S; ++p) {   // fixed order: deterministic
+                for (int p = 0; p < TE_S - 1; ++p) {   // fixed order: deterministic
                     const float4* x = reinterpret_cast<const float4*>(inbox + (size_t)p * slot_f + b * 32);
                     const int sw = b & 7;
                     const float4 x0 = x[0 ^ sw], x1 = x[1 ^ sw], x2 = x[2 ^ sw], x3 = x[3 ^ sw], x4 = x[4 ^ sw], x5 = x[5 ^ sw], x6 = x[6 ^ sw],
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             split8_f16(hreg, hh, hl);
             if (act) {
                 uint16_t* hdst = a.hx + (size_t)((t + 1) & 1) * 2 * hx_part;
-                const size_t off = ((size_t)(u0 >> 6) * L.MB + (b >> 3)) * 512 + (size_t)((u0 & 63) >> 3) * 64 + (size_t)(b & 7) * 8;
+                const size_t off = (((size_t)(u0 >> kca_sh) * L.MB + (b >> 3)) << (kca_sh + 3)) + (size_t)((u0 & (L.KCA - 1)) >> 3) * 64 + (size_t)(b & 7) * 8;
                 *reinterpret_cast<uint4*>(hdst + off) = hh;
                 *reinterpret_cast<uint4*>(hdst + hx_part + off) = hl;
             }
@@ -353,7 +376,7 @@ static bool eval_runnable(int B, int H, const DeviceInfo& di, TeLayout* Lout) {
     TeLayout L = te_layout(B, H, di.max_smem_optin);
     if (ok < 0) {
         ok = 0;
-        if (L.NS >= 2 && (int)L.total <= di.max_smem_optin && (uint32_t)L.NS * L.stage_bytes >= (uint32_t)TE_S * L.slot_bytes &&
+        if (L.NS >= 2 && (int)L.total <= di.max_smem_optin && (uint32_t)L.NS * L.stage_bytes >= (uint32_t)(TE_S - 1) * L.slot_bytes &&
             cudaFuncSetAttribute(k_gru_fwd_tc_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(G);
@@ -384,7 +407,7 @@ bool gru_tc_eval_supported(int B, int H, int out, const DeviceInfo& di) { return
 // scratch (floats): W_fb [3H,H] | hx | counter
 size_t gru_tc_eval_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
-    size_t hx = (size_t)2 * 2 * (H / TE_KC) * MB * 512 / 2;
+    size_t hx = (size_t)2 * 2 * H * MB * 8 / 2;
     return round_up_sz((size_t)3 * H * H, 64) + round_up_sz(hx, 64) + 64;
 }
 
@@ -419,7 +442,7 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStre
     const int B = f.B, T = f.T, H = f.H, out = f.out;
     float* Wfb = scratch;
     const size_t wfb_f = round_up_sz((size_t)3 * H * H, 64);
-    const size_t hx_f = round_up_sz((size_t)2 * 2 * (H / TE_KC) * L.MB * 512 / 2, 64);
+    const size_t hx_f = round_up_sz((size_t)2 * 2 * H * L.MB * 8 / 2, 64);
     // the first step's feedback is the CALLER's y_in, not W_o h_in + b_o:  gx[0] += W_y y_in - c_fb - W_fb h_in  takes
     // the folded terms (the bias above, the product the kernel will add) back out
     float* gx0 = const_cast<float*>(f.gx);

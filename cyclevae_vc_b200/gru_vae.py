@@ -295,7 +295,7 @@ class GRU_RNN(nn.Module):
                                                  or (h0 is not None and h0.requires_grad))
         max_rows = MAX_ROWS_PER_LAUNCH
         if B > 64:
-            max_rows = int(lib.cvb_recurrence_max_rows(C.byref(self._net_struct(params)), 1 if want_grad else 0))
+            max_rows = int(lib.cvb_recurrence_max_rows(C.byref(self._net_struct(params)), 1 if want_grad else (2 if mg is not None else 0)))
         if B <= max_rows:
             trj, y_last, h_last = _GruRnnFn.apply(self, head, int(lat_dim), want_grad, xb, y0, h0, mc, mg, *params)
         else:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 6
+#define CVB_ABI_VERSION 7
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -93,8 +93,9 @@ size_t cvb_scratch_floats(const cvb_net* net, int B, int T, int training);
 /* Largest batch-row count (<= 128) one launch of the persistent recurrence kernels should be given at this network
  * shape (the tensor-core kernels keep all rows of a step in one MMA tile and their shared-memory ring scales with the
  * rows).  Rows never interact inside GRU_RNN.forward (gru_vae.py:364-399), so the host runs wider batches as
- * independent slices. */
-int cvb_recurrence_max_rows(const cvb_net* net, int training);
+ * independent slices.  mode 0: inference without recurrent dropout (the folded one-exchange kernel), 1: forward + BPTT,
+ * 2: forward only, with dropout masks. */
+int cvb_recurrence_max_rows(const cvb_net* net, int mode);
 
 /* ---- GRU_RNN.forward (gru_vae.py:322-455; kwargs do / clamp_vae / lat_dim / h_in) ------------
  * x_bm [B,T,in]; y_in [B,out] (the reference's [B,1,out]); h_in [B,H] or NULL (= zeros);
