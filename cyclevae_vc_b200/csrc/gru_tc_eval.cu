@@ -70,11 +70,12 @@ struct GruTcEvalArgs {
     const float* Wfb;    // [3H,H] = W_y W_o
     const float* bhh;    // [3H]
     float* hs;           // [T+1,B,H], slot 0 = h_in
-    uint16_t* hx;        // [2 slots][2 parts][H/KCA chunks][MB][KCA/8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
-    unsigned* ctr;       // zero-initialised
+    uint16_t* hx;        // [3 slots][2 parts][H/KCA chunks][MB][KCA/8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
+    unsigned* ctr;       // [H/32] arrival counters, one per cluster; zero-initialised
     int B, T, H;
     int smem_max;
     int keepalive;
+    int rotate;          // CVB_TC_ROTATE (default 1): per-cluster start stage of the K walk
     long long* trace;    // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE_EVAL), else null
 };
 
@@ -120,6 +121,9 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbox_full + 1);
     const size_t hx_part = (size_t)H * L.MB * 8;
     const uint32_t kca_sh = L.KCA == 64 ? 6u : 5u;   // log2(KCA)
+    // the 32 CTAs that own the same K-slice read the same stages of h: each cluster starts its walk over the slice at a
+    // different stage so that they do not all pull the same L2 lines at the same moment (fixed per cluster: deterministic)
+    const int rot = a.rotate ? (c / TE_S) % L.nsub : 0;
 
     // ---- one-time setup: folded weights -> fp16 hi/lo in UMMA K-major core-matrix order ------------------
     {
@@ -161,30 +165,45 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
 
     if (warp == 0) {
         // ================= producer: K-slice of h_{t-1} ====================================================
-        int s = 0;
+        // One arrival counter per CLUSTER (= 32 units of h): a stage of the K walk is pulled as soon as the cluster(s) that
+        // produce its units have published, so the late producers of a step hide behind the MMAs of the early stages.
+        // The stages are still issued (and accumulated) in the fixed rotated order: the sums stay deterministic.
+        int s = 0, slot = 0;
         uint32_t ph = 1;
+        const int ncs = (H / TE_S) / TE_UB;           // clusters that produce this CTA's K-slice
+        const unsigned* flag = a.ctr + j * ncs;
+        const unsigned per_stage = (unsigned)(L.KCA / TE_UB);   // producing clusters per stage: 1 or 2
+        const size_t sub_elems = (size_t)L.MB * L.KCA * 8;
         for (int t = 0; t < T; ++t) {
-            const size_t sub_elems = (size_t)L.MB * L.KCA * 8;
-            const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nsub) * sub_elems;
-            if (lane == 0) {
-                spin_until(a.ctr, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy
-                TE_TRACE(14);
-            }
-            __syncwarp();
-            for (int ch = 0; ch < L.nsub; ++ch) {
-                if (lane == 0) {
-                    mbar_wait(&empty[s], ph);
-                    uint8_t* dst = ring + (size_t)s * L.stage_bytes;
-                    mbar_expect_tx(&full[s], 2 * L.half);
-                    bulk_g2s(dst, src + (size_t)ch * sub_elems, L.half, &full[s]);
-                    bulk_g2s(dst + L.half, src + hx_part + (size_t)ch * sub_elems, L.half, &full[s]);
+            const uint16_t* src = a.hx + (size_t)slot * 2 * hx_part + (size_t)(j * L.nsub) * sub_elems;
+            const unsigned target = (unsigned)TE_S * (unsigned)(t + 1);
+            int issued = 0;
+            while (issued < L.nsub) {
+                // the writers fenced generic -> async proxy before their release
+                const unsigned v = lane < ncs ? ld_acquire_gpu(flag + lane) : 0u;
+                const unsigned ready = __ballot_sync(0xffffffffu, lane < ncs && v >= target);
+                while (issued < L.nsub) {
+                    int che = issued + rot;
+                    if (che >= L.nsub) che -= L.nsub;
+                    const unsigned need = ((1u << per_stage) - 1u) << ((unsigned)che * per_stage);
+                    if ((ready & need) != need) break;
+                    if (lane == 0) {
+                        if (issued == 0) TE_TRACE(14);
+                        mbar_wait(&empty[s], ph);
+                        uint8_t* dst = ring + (size_t)s * L.stage_bytes;
+                        mbar_expect_tx(&full[s], 2 * L.half);
+                        bulk_g2s(dst, src + (size_t)che * sub_elems, L.half, &full[s]);
+                        bulk_g2s(dst + L.half, src + hx_part + (size_t)che * sub_elems, L.half, &full[s]);
+                    }
+                    __syncwarp();
+                    ++issued;
+                    if (++s == L.NS) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
-                __syncwarp();
-                if (++s == L.NS) {
-                    s = 0;
-                    ph ^= 1;
-                }
             }
+            if (++slot == 3) slot = 0;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =========================================================================
@@ -207,7 +226,9 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                 tc_fence_after();
                 const uint64_t da = dA0 + (uint64_t)((uint32_t)s * a_step);
                 // weights stay in 64-wide K chunks; stage ch covers k = [ch*KCA, +KCA) of the slice
-                const uint32_t kq = (uint32_t)ch << kca_sh;
+                int che = ch + rot;
+                if (che >= L.nsub) che -= L.nsub;
+                const uint32_t kq = (uint32_t)che << kca_sh;
                 const uint64_t db = dW0 + (uint64_t)((kq >> 6) * w_step + ((kq & 63u) >> 4) * 16u);
                 for (int k16 = 0; k16 < kca16; ++k16) {
                     mma_bf16_ss_elect(tmem, da + 16u * k16, db + 16u * k16, idesc_s, (ch | k16) != 0);
@@ -243,8 +264,9 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             }
             fence_proxy_async_global();
             named_bar_sync(1, 128);
-            if (etid == 0) red_release_gpu_add(a.ctr, 1u);
+            if (etid == 0) red_release_gpu_add(a.ctr + c / TE_S, 1u);
         }
+        int wslot = 1;   // h_t goes to slot (t + 1) % 3: a reader may lag its writers by one step, never by two
         for (int t = 0; t < T; ++t) {
             const size_t row = (size_t)t * B + (act ? b : 0);
             float4 gxv[6];
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             uint4 hh, hl;
             split8_f16(hreg, hh, hl);
             if (act) {
-                uint16_t* hdst = a.hx + (size_t)((t + 1) & 1) * 2 * hx_part;
+                uint16_t* hdst = a.hx + (size_t)wslot * 2 * hx_part;
                 const size_t off = (((size_t)(u0 >> kca_sh) * L.MB + (b >> 3)) << (kca_sh + 3)) + (size_t)((u0 & (L.KCA - 1)) >> 3) * 64 + (size_t)(b & 7) * 8;
                 *reinterpret_cast<uint4*>(hdst + off) = hh;
                 *reinterpret_cast<uint4*>(hdst + hx_part + off) = hl;
@@ -348,7 +370,8 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             fence_proxy_async_global();
             if (etid == 0) TE_TRACE(8);
             named_bar_sync(1, 128);
-            if (etid == 0) red_release_gpu_add(a.ctr, 1u);
+            if (etid == 0) red_release_gpu_add(a.ctr + c / TE_S, 1u);
+            if (++wslot == 3) wslot = 0;
             if (etid == 0) TE_TRACE(9);
             if (act) {   // off the critical path: the state trajectory (the y product after the launch reads it)
                 float* hd = a.hs + (size_t)(t + 1) * B * H + (size_t)b * H + u0;
@@ -366,7 +389,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
 // ---- host side ----------------------------------------------------------------------------------------
 static bool eval_runnable(int B, int H, const DeviceInfo& di, TeLayout* Lout) {
     const int G = H / 8;
-    if (!(H % (TE_KC * TE_S) == 0 && H >= TE_KC * TE_S && B >= 1 && B <= 128) || G > di.n_sm) return false;
+    if (!(H % (TE_KC * TE_S) == 0 && H >= TE_KC * TE_S && B >= 1 && B <= 128 && H <= 4096) || G > di.n_sm) return false;
     struct Entry { int B, H, ok; };
     static Entry cache[16];
     static int n_cache = 0;
@@ -407,8 +430,8 @@ bool gru_tc_eval_supported(int B, int H, int out, const DeviceInfo& di) { return
 // scratch (floats): W_fb [3H,H] | hx | counter
 size_t gru_tc_eval_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
-    size_t hx = (size_t)2 * 2 * H * MB * 8 / 2;
-    return round_up_sz((size_t)3 * H * H, 64) + round_up_sz(hx, 64) + 64;
+    size_t hx = (size_t)3 * 2 * H * MB * 8 / 2;
+    return round_up_sz((size_t)3 * H * H, 64) + round_up_sz(hx, 64) + 128;
 }
 
 __global__ void k_add_rowvec(float* __restrict__ dst, int rows, int cols, float alpha, const float* __restrict__ v) {
@@ -442,7 +465,7 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStre
     const int B = f.B, T = f.T, H = f.H, out = f.out;
     float* Wfb = scratch;
     const size_t wfb_f = round_up_sz((size_t)3 * H * H, 64);
-    const size_t hx_f = round_up_sz((size_t)2 * 2 * H * L.MB * 8 / 2, 64);
+    const size_t hx_f = round_up_sz((size_t)3 * 2 * H * L.MB * 8 / 2, 64);
     // the first step's feedback is the CALLER's y_in, not W_o h_in + b_o:  gx[0] += W_y y_in - c_fb - W_fb h_in  takes
     // the folded terms (the bias above, the product the kernel will add) back out
     float* gx0 = const_cast<float*>(f.gx);
@@ -464,6 +487,8 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStre
     a.smem_max = di.max_smem_optin;
     a.keepalive = 1;
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
+    a.rotate = 1;
+    if (const char* e = getenv("CVB_TC_ROTATE")) a.rotate = atoi(e) != 0;
     a.trace = nullptr;
     const char* trace_file = getenv("CVB_TRACE_FILE_EVAL");
     const size_t trace_bytes = (size_t)(T + 1) * 64 * sizeof(long long);
@@ -471,7 +496,7 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStre
         CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
         CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));
     }
-    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, 64 * sizeof(float), s));
+    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, 128 * sizeof(float), s));
     CVB_CHECK(cudaFuncSetAttribute(k_gru_fwd_tc_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(H / 8);
