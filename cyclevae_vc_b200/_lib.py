@@ -51,6 +51,7 @@ PROTOTYPES = {
     "cvb_recurrent_ws_floats": (_sz, [_netp, _i, _i, _i, _i]),
     "cvb_scratch_floats": (_sz, [_netp, _i, _i, _i]),
     "cvb_recurrence_max_rows": (_i, [_netp, _i]),
+    "cvb_last_recurrence_path": (_i, [_i]),
     "cvb_gru_rnn_forward": (_i, [_netp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvb_gru_rnn_backward": (_i, [_netp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _gradp, _vp]),

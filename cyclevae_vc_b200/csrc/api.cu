@@ -185,6 +185,10 @@ size_t cvb_scratch_floats(const cvb_net* net, int B, int T, int training) {
     return f;
 }
 
+// which recurrence kernel the last forward / backward call of this process launched (tests: no silent fallback)
+static int g_last_path[2] = {-1, -1};
+int cvb_last_recurrence_path(int backward) { return g_last_path[backward ? 1 : 0]; }
+
 int cvb_recurrence_max_rows(const cvb_net* net, int mode) {
     // largest batch-row count (multiple of 8, <= 128) one launch of the tensor-core recurrence kernels holds at this
     // network shape; 128 when only the fp32-FMA kernels apply (they tile the batch themselves).
@@ -281,10 +285,13 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     a.T = T;
     if (fold) {
         if (int rc = gru_ar_fwd_tc_eval(a, esc, cfb, s)) return rc;
+        g_last_path[0] = CVB_PATH_TC_FOLDED;
     } else if (want_tc() && gru_tc_supported(B, H, out, di)) {
         if (int rc = gru_ar_fwd_tc(a, scratch + FS.tc, s)) return rc;
+        g_last_path[0] = CVB_PATH_TC;
     } else {
         if (int rc = gru_ar_fwd_exact(a, s)) return rc;
+        g_last_path[0] = CVB_PATH_FP32;
     }
     size_t smem = head_mode == CVB_HEAD_SCALE_OUT ? (size_t)(out * out + out) * sizeof(float) : 0;
     CVB_REQUIRE(smem <= 48 * 1024, "scale_out matrix too large (out_dim=%d)", out);
@@ -364,8 +371,10 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
                 db_in_kernel = true;
             }
             if (int rc = gru_ar_bwd_tc(a, scratch + BS.tc, s)) return rc;
+            g_last_path[1] = CVB_PATH_TC;
         } else {
             if (int rc = gru_ar_bwd_exact(a, s)) return rc;
+            g_last_path[1] = CVB_PATH_FP32;
         }
     }
     if (dy_in) CVB_CHECK(cudaMemcpyAsync(dy_in, dy_tot, (size_t)B * out * sizeof(float), cudaMemcpyDeviceToDevice, s));

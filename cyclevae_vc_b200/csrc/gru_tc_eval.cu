@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
         int s = 0, slot = 0;
         uint32_t ph = 1;
         const int ncs = (H / TE_S) / TE_UB;           // clusters that produce this CTA's K-slice
-        const unsigned* flag = a.ctr + j * ncs;
+        const unsigned* flag = lane == 31 ? a.ctr + c / TE_S - 31 : a.ctr + j * ncs;   // lane 31 watches the OWN cluster
         const unsigned per_stage = (unsigned)(L.KCA / TE_UB);   // producing clusters per stage: 1 or 2
         const size_t sub_elems = (size_t)L.MB * L.KCA * 8;
         for (int t = 0; t < T; ++t) {
@@ -180,8 +180,13 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             int issued = 0;
             while (issued < L.nsub) {
                 // the writers fenced generic -> async proxy before their release
-                const unsigned v = lane < ncs ? ld_acquire_gpu(flag + lane) : 0u;
-                const unsigned ready = __ballot_sync(0xffffffffu, lane < ncs && v >= target);
+                // The own cluster must have arrived too before the ring is written again: its CTAs arrive after their
+                // inboxes completed, i.e. after this CTA's outgoing partial sums (staged in the ring) were delivered, and
+                // after they finished reading the inbox the next exchange will overwrite.
+                const bool polls = lane < ncs || lane == 31;
+                const unsigned v = polls ? ld_acquire_gpu(flag + lane) : 0u;
+                const unsigned ready = __ballot_sync(0xffffffffu, polls && v >= target);
+                if (!(ready >> 31)) continue;
                 while (issued < L.nsub) {
                     int che = issued + rot;
                     if (che >= L.nsub) che -= L.nsub;
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
 // ---- host side ----------------------------------------------------------------------------------------
 static bool eval_runnable(int B, int H, const DeviceInfo& di, TeLayout* Lout) {
     const int G = H / 8;
-    if (!(H % (TE_KC * TE_S) == 0 && H >= TE_KC * TE_S && B >= 1 && B <= 128 && H <= 4096) || G > di.n_sm) return false;
+    if (!(H % (TE_KC * TE_S) == 0 && H >= TE_KC * TE_S && B >= 1 && B <= 128 && H <= 3968) || G > di.n_sm) return false;
     struct Entry { int B, H, ok; };
     static Entry cache[16];
     static int n_cache = 0;

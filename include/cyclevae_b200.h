@@ -97,6 +97,14 @@ size_t cvb_scratch_floats(const cvb_net* net, int B, int T, int training);
  * 2: forward only, with dropout masks. */
 int cvb_recurrence_max_rows(const cvb_net* net, int mode);
 
+/* Which recurrence kernel the last cvb_gru_rnn_forward (backward = 0) / cvb_gru_rnn_backward (backward = 1) call of this
+ * process launched; -1 before the first call.  For tests and monitoring: a shape that silently leaves the tensor-core
+ * path shows up here. */
+#define CVB_PATH_FP32 0      /* fp32-FMA persistent kernels (gru_ar.cu) */
+#define CVB_PATH_TC 1        /* tcgen05 kernels, two exchanges per step (gru_tc.cu / gru_tc_bwd.cu) */
+#define CVB_PATH_TC_FOLDED 2 /* tcgen05 inference kernel, feedback folded, one exchange per step (gru_tc_eval.cu) */
+int cvb_last_recurrence_path(int backward);
+
 /* ---- GRU_RNN.forward (gru_vae.py:322-455; kwargs do / clamp_vae / lat_dim / h_in) ------------
  * x_bm [B,T,in]; y_in [B,out] (the reference's [B,1,out]); h_in [B,H] or NULL (= zeros);
  * mask_conv_tm [T,B,in*k^n] / mask_gru_tm [T,B,H]: dropout masks already scaled by 1/(1-p), or

@@ -473,6 +473,10 @@ def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B):
             ((o * w_o).sum() + (yl * w_y).sum() + (hl * w_h).sum()).backward()
             torch.cuda.synchronize()
             grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            # no silent fallback: the tensor-core kernels (path 1) must be the ones that ran by default
+            from cyclevae_vc_b200._lib import lib
+            want = 0 if mode else 1
+            assert lib.cvb_last_recurrence_path(0) == want and lib.cvb_last_recurrence_path(1) == want
             return (o.detach(), yl.detach(), hl.detach()), (xs.grad, ys.grad, hs.grad), grads
         finally:
             os.environ.pop("CVB_RECURRENCE", None)
@@ -538,9 +542,110 @@ def test_tensor_core_forward_any_row_count(cvb):
                 o_e, y_e, h_e = enc(x, y0, h_in=h0, clamp_vae=True, lat_dim=32)
             finally:
                 os.environ.pop("CVB_RECURRENCE", None)
+            from cyclevae_vc_b200._lib import lib
+            assert lib.cvb_last_recurrence_path(0) == 0   # fp32-FMA kernels
             for _ in range(2):
                 o_t, y_t, h_t = enc(x, y0, h_in=h0, clamp_vae=True, lat_dim=32)
+                assert lib.cvb_last_recurrence_path(0) == 2   # the folded inference kernel, not a fallback
                 assert _maxabs(o_t, o_e) < 2e-5 and _maxabs(h_t, h_e) < 2e-5 and _maxabs(y_t, y_e) < 2e-5, (B, T)
+
+
+def test_forward_only_kernel_choice(cvb):
+    """Forward-only calls (torch.no_grad) and the kernel each one takes (cvb_last_recurrence_path): no dropout -> the folded
+    one-exchange kernel; dropout masks -> the two-exchange kernel (the fold needs o_t = h_t); CVB_EVAL_FOLD=0 -> the
+    two-exchange kernel without masks.  All against the all-fp32 path on the same masks, wide batch included (sliced at
+    the row count of the kernel actually used)."""
+    from cyclevae_vc_b200._lib import lib
+    lat = 32
+    mean, std = orc.synth_stats(50)
+    spec = orc.decoder_spec(lat, 2, 50, 1024)
+    P = orc.init_params(spec, 202, gain=1.5, bias_std=0.02, mean=mean[4:], scale=std[4:])
+    m = _module(cvb, spec, P)
+    g = torch.Generator().manual_seed(3)
+    for B, T in ((24, 16), (150, 7)):
+        x = torch.randn(B, T, spec.in_dim, generator=g).cuda()
+        y0 = (0.3 * torch.randn(B, 1, spec.out_dim, generator=g)).cuda()
+        h0 = (0.5 * torch.randn(1, B, 1024, generator=g)).cuda()
+        mc = ((torch.rand(B, T, spec.conv_dim, generator=g) >= 0.5).float() * 2).cuda()
+        mg = ((torch.rand(B, T, 1024, generator=g) >= 0.5).float() * 2).cuda()
+
+        def run(do, env):
+            os.environ.update(env)
+            try:
+                with torch.no_grad():
+                    if do:
+                        m.train()
+                        m.inject_dropout_masks(mc, mg)
+                    else:
+                        m.eval()
+                    out = m(x, y0, h_in=h0, do=do)
+                torch.cuda.synchronize()
+                return out, lib.cvb_last_recurrence_path(0)
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+
+        for do in (False, True):
+            ref, path = run(do, {"CVB_RECURRENCE": "exact", "CVB_GEMM": "cublas"})
+            assert path == 0
+            cases = [({}, 1 if do else 2)] + ([] if do else [({"CVB_EVAL_FOLD": "0"}, 1)])
+            for env, want in cases:
+                got, path = run(do, env)
+                assert path == want, (B, do, env, path)
+                for a, b in zip(got, ref):
+                    assert _maxabs(a, b) < 5e-5 * max(1.0, float(b.abs().max())), (B, do, env)
+
+
+def test_persistent_kernels_are_deterministic(cvb):
+    """Every cross-CTA sum of the persistent kernels is taken in a fixed order (no float atomics, fixed K walk per
+    cluster), so repeated calls must agree BIT FOR BIT — which also makes this the race detector for their exchange
+    buffers (a slot overwritten while a peer still reads it shows up as a changed bit): folded inference kernel at the
+    widest launch over 300 steps, training forward + BPTT at the bench shape."""
+    torch.manual_seed(1)
+    enc = cvb.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, do_prob=0.5, scale_out_flag=False).cuda()
+    enc.apply(cvb.initialize)
+    with torch.no_grad():
+        for p in enc.parameters():
+            if p.dim() > 1 and p.requires_grad:
+                p.mul_(2.0)   # livelier dynamics than the reference init: rounding differences would not die out
+    B, T = 128, 300
+    x = torch.randn(B, T, 54, device="cuda")
+    y0 = 0.1 * torch.randn(B, 1, 64, device="cuda")
+    h0 = 0.3 * torch.randn(1, B, 1024, device="cuda")
+    enc.eval()
+    with torch.no_grad():
+        first = None
+        for _ in range(5):
+            out = enc(x, y0, h_in=h0, clamp_vae=True, lat_dim=32)
+            if first is None:
+                first = [t.clone() for t in out]
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(out, first))
+    from cyclevae_vc_b200._lib import lib
+    assert lib.cvb_last_recurrence_path(0) == 2
+    B, T = 80, 80
+    x = torch.randn(B, T, 54, device="cuda")
+    y0 = 0.1 * torch.randn(B, 1, 64, device="cuda")
+    h0 = 0.3 * torch.randn(1, B, 1024, device="cuda")
+    mc = (torch.rand(B, T, enc.in_dim * enc.receptive_field, device="cuda") >= 0.5).float() * 2
+    mg = (torch.rand(B, T, 1024, device="cuda") >= 0.5).float() * 2
+    w = torch.randn(B, T, 64, device="cuda")
+    enc.train()
+    first = None
+    for _ in range(3):
+        xs, hs = x.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+        for p in enc.parameters():
+            p.grad = None
+        enc.inject_dropout_masks(mc, mg)
+        o, yl, hl = enc(xs, y0, h_in=hs, do=True, clamp_vae=True, lat_dim=32)
+        ((o * w).sum() + hl.sum()).backward()
+        got = [o.detach().clone(), hl.detach().clone(), xs.grad.clone(), hs.grad.clone()] + \
+              [p.grad.clone() for p in enc.parameters() if p.grad is not None]
+        if first is None:
+            first = got
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(got, first))
+    assert lib.cvb_last_recurrence_path(0) == 1 and lib.cvb_last_recurrence_path(1) == 1
 
 
 @pytest.mark.parametrize("cluster8", ["0", "1"])
