@@ -9,6 +9,8 @@ cannot run here: h5py / dtw_c / pysptk are absent).
     FlatAdam         Adam over conv+gru+out_1 of both nets          train_*.py:373-377, 1418-1420
     allreduce_grads  the one data-parallel collective (SUM)         new
     convert          stage-6 conversion composition                 decode_*.py:303-305,318
+    convert_utterances  the same for a list of ragged utterances, packed    new
+    gv_postfilter    global-variance post-filter on the device      decode_*.py:419-420
 """
 from __future__ import annotations
 
@@ -224,3 +226,72 @@ def convert(enc: gv.GRU_RNN, dec: gv.GRU_RNN, feat, code, *, lat_dim: int, y0_en
     z = gv.reparam_concat(lat, code, eps_mean, lat_dim)
     cvm, _, _ = dec(z, y0_dec)
     return cvm
+
+
+# ------------------------------------------------------------------------------------------------
+def scale_in_mean(enc: gv.GRU_RNN) -> torch.Tensor:
+    """The feature mean the encoder's frozen scale_in layer subtracts (train_*.py:344-345: weight = diag(1/std),
+    bias = -mean/std): x = mean is what the zero padding of the conv front-end looks like in the input domain
+    (gru_vae.py:336,357: pads are zeros of the NORMALISED features)."""
+    if not enc.scale_in_flag:
+        return torch.zeros(enc.in_dim, device=enc.out_1.weight.device)
+    w = enc.scale_in.weight.detach()[:, :, 0]
+    return -enc.scale_in.bias.detach() / torch.diagonal(w)
+
+
+def pack_utterances(feats: Sequence[torch.Tensor], pad_value: torch.Tensor):
+    """[T_i, C] utterances -> ([N, T_max, C] padded with pad_value [C], lengths).  Padding frames hold the value the
+    front-end's own zero padding stands for, so the two-sided convolution sees at an utterance's end exactly what it sees
+    when the utterance is run alone; the recurrence is causal, so frames t < T_i never depend on the padding after them."""
+    lens = [int(f.shape[0]) for f in feats]
+    x = pad_value.to(feats[0].device, torch.float32).repeat(len(feats), max(lens), 1)
+    for i, f in enumerate(feats):
+        x[i, :lens[i]] = f
+    return x, lens
+
+
+def convert_utterances(enc: gv.GRU_RNN, dec: gv.GRU_RNN, feats: Sequence[torch.Tensor], trg_code: torch.Tensor, *,
+                       lat_dim: int, y0_enc, y0_dec, eps_means: Optional[Sequence[torch.Tensor]] = None,
+                       n_smpl: int = 300, rows_per_group: Optional[int] = None) -> List[torch.Tensor]:
+    """Stage-6 conversion (decode_*.py:303-305,318) of MANY utterances of different lengths at once — the reference
+    converts one utterance per call.  Utterances are sorted by length and packed into groups of the row count one
+    persistent launch holds (so a group runs only to ITS longest utterance), padded as `pack_utterances` describes; the
+    decoder input of padding frames is zeroed (its front-end has no scale_in: zero IS its padding).  Returns the
+    converted mcep [T_i, out] per utterance in the caller's order; equal to converting each utterance alone.
+    trg_code: [n_spk] one-hot; y0_enc [1,1,2*lat], y0_dec [1,1,out]; eps_means[i]: [T_i, lat] averaged noise (else drawn)."""
+    n = len(feats)
+    if n == 0:
+        return []
+    dev = feats[0].device
+    if rows_per_group is None:
+        rows_per_group = min(enc.max_rows_per_launch(0), dec.max_rows_per_launch(0))
+    order = sorted(range(n), key=lambda i: -int(feats[i].shape[0]))
+    mean = scale_in_mean(enc)
+    out: List[Optional[torch.Tensor]] = [None] * n
+    code = trg_code.to(dev, torch.float32).reshape(1, 1, -1)
+    for g0 in range(0, n, rows_per_group):
+        idx = order[g0:g0 + rows_per_group]
+        x, lens = pack_utterances([feats[i] for i in idx], mean)
+        B, T = x.shape[0], x.shape[1]
+        valid = (torch.arange(T, device=dev).unsqueeze(0) < torch.tensor(lens, device=dev).unsqueeze(1)).unsqueeze(2)
+        lat, _, _ = enc(x, y0_enc.expand(B, -1, -1).contiguous(), clamp_vae=True, lat_dim=lat_dim)
+        if eps_means is None:
+            eps = torch.randn(B, T, lat_dim, device=dev) / float(n_smpl) ** 0.5
+        else:
+            eps = torch.zeros(B, T, lat_dim, device=dev)
+            for r, i in enumerate(idx):
+                eps[r, :lens[r]] = eps_means[i]
+        z = gv.reparam_concat(lat, code.expand(B, T, -1).contiguous(), eps, lat_dim) * valid
+        cvm, _, _ = dec(z, y0_dec.expand(B, -1, -1).contiguous())
+        for r, i in enumerate(idx):
+            out[i] = cvm[r, :lens[r]]
+    return out  # type: ignore[return-value]
+
+
+def gv_postfilter(cvmcep: torch.Tensor, gv_mean_trg: torch.Tensor, cvgv_mean: torch.Tensor) -> torch.Tensor:
+    """decode_*.py:419-420 on the device: coefficients 1.. are rescaled around their utterance mean by
+    sqrt(gv_mean_trg / cvgv_mean) (target-speaker global variance over the variance of converted training data);
+    c0 passes through.  cvmcep [T, D]; the statistics [D-1]."""
+    rest = cvmcep[:, 1:]
+    m = rest.mean(0, keepdim=True)
+    return torch.cat((cvmcep[:, :1], torch.sqrt(gv_mean_trg / cvgv_mean).to(rest) * (rest - m) + m), 1)

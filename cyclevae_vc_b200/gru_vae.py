@@ -238,6 +238,11 @@ class GRU_RNN(nn.Module):
                 getattr(net, field)[idx] = ptr(p)
         return net
 
+    def max_rows_per_launch(self, mode: int) -> int:
+        """cvb_recurrence_max_rows: batch rows one persistent launch holds at this shape (mode 0 inference without
+        dropout, 1 forward + BPTT, 2 forward with dropout masks)."""
+        return int(lib.cvb_recurrence_max_rows(C.byref(self._net_struct(self._param_list())), int(mode)))
+
     def _scratch(self, n_floats: int, dev) -> torch.Tensor:
         """Scratch shared by successive calls on the same stream (stream order makes reuse safe)."""
         b = self._scratch_buf

@@ -550,6 +550,53 @@ def test_tensor_core_forward_any_row_count(cvb):
                 assert _maxabs(o_t, o_e) < 2e-5 and _maxabs(h_t, h_e) < 2e-5 and _maxabs(y_t, y_e) < 2e-5, (B, T)
 
 
+def test_ragged_batch_conversion_equals_per_utterance(cvb):
+    """stage-6 conversion of utterances of different lengths packed into padded row groups
+    (cycle.convert_utterances) == the reference's one-utterance-per-call composition (decode_*.py:303-305,318), checked
+    against (i) the fp64 oracle run utterance by utterance and (ii) this library's own unbatched conversion.  The pads must
+    be invisible: the encoder's pads are the scale_in mean (zeros of the normalised domain, gru_vae.py:336,357), the
+    decoder's are zeros, and the recurrence is causal.  Plus the GV post-filter (decode_*.py:419-420)."""
+    from cyclevae_vc_b200 import cycle
+    lat, stdim = 32, 4
+    mean, std = orc.synth_stats(50)
+    enc, dec = orc.encoder_spec(54, lat, 1024), orc.decoder_spec(lat, 2, 50, 1024)
+    Pe = orc.init_params(enc, 201, gain=1.0, bias_std=0.0, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 202, gain=1.0, bias_std=0.0, mean=mean[stdim:], scale=std[stdim:])
+    me, md = _module(cvb, enc, Pe).eval(), _module(cvb, dec, Pd).eval()
+    assert _maxabs(cycle.scale_in_mean(me), mean.astype(np.float32)) < 1e-5
+    y0e = torch.zeros(1, 1, 2 * lat)
+    y0d = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1)
+    lens = [37, 120, 64, 5, 200, 81, 9]
+    feats, codes, epss = [], [], []
+    for i, T in enumerate(lens):
+        x, _, sc, tc = orc.synth_batch(1, T, 40 + i)
+        feats.append(x[0])
+        codes.append(tc[0])
+        epss.append(orc.synth_noise(1, T, lat, 1, 50 + i)[0][0][0] / np.sqrt(300.0))   # [T, lat]
+    trg_code = codes[0][0]
+    assert all(torch.equal(c, trg_code.expand_as(c)) for c in codes)
+    with torch.no_grad():
+        got = cycle.convert_utterances(me, md, [f.cuda() for f in feats], trg_code.cuda(), lat_dim=lat, y0_enc=y0e.cuda(),
+                                       y0_dec=y0d.cuda(), eps_means=[e.cuda() for e in epss], rows_per_group=3)
+        alone = [cycle.convert(me, md, f.cuda(), c.cuda(), lat_dim=lat, y0_enc=y0e.cuda(), y0_dec=y0d.cuda(), eps_mean=e.cuda())
+                 for f, c, e in zip(feats, codes, epss)]
+    P64e, P64d = ({k: v.double() for k, v in P.items()} for P in (Pe, Pd))
+    for i, T in enumerate(lens):
+        assert got[i].shape == (T, 50)
+        assert _maxabs(got[i], alone[i]) < 2e-5, i
+        exact = orc.convert(P64e, P64d, enc, dec, feats[i].double(), codes[i].double(), lat_dim=lat, y0_enc=y0e.double(),
+                            y0_dec=y0d.double(), eps_mean=epss[i].double())
+        assert _maxabs(got[i], exact.float()) < TOL, i
+    # GV post-filter, decode_*.py:419-420 restated in numpy
+    cv = got[4].double().cpu().numpy()
+    rng = np.random.default_rng(0)
+    gv_trg, cvgv = rng.uniform(0.5, 2.0, 49), rng.uniform(0.5, 2.0, 49)
+    datamean = np.mean(cv[:, 1:], axis=0)
+    ref = np.c_[cv[:, 0], np.sqrt(gv_trg / cvgv) * (cv[:, 1:] - datamean) + datamean]
+    mine = cycle.gv_postfilter(got[4], torch.tensor(gv_trg, dtype=torch.float32).cuda(), torch.tensor(cvgv, dtype=torch.float32).cuda())
+    assert _maxabs(mine, ref.astype(np.float32)) < 1e-5
+
+
 def test_forward_only_kernel_choice(cvb):
     """Forward-only calls (torch.no_grad) and the kernel each one takes (cvb_last_recurrence_path): no dropout -> the folded
     one-exchange kernel; dropout masks -> the two-exchange kernel (the fold needs o_t = h_t); CVB_EVAL_FOLD=0 -> the

@@ -123,6 +123,27 @@ def test_chunk_schedule_bit_exact(pkg, golden_dir):
         assert chunk_schedule(flens, bs) == orc.chunk_schedule(flens, bs)
 
 
+def test_pack_utterances_and_gv_postfilter(pkg):
+    """Host logic of the batched stage-6 front door: padding with the front-end's own pad value, and
+    the GV post-filter against decode_*.py:419-420 restated in numpy."""
+    from cyclevae_vc_b200 import cycle
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(T, 6, generator=g) for T in (5, 1, 9)]
+    pad = torch.arange(6, dtype=torch.float32)
+    x, lens = cycle.pack_utterances(feats, pad)
+    assert lens == [5, 1, 9] and x.shape == (3, 9, 6)
+    for i, f in enumerate(feats):
+        assert torch.equal(x[i, :lens[i]], f)
+        assert torch.equal(x[i, lens[i]:], pad.expand(9 - lens[i], 6))
+    cv = torch.randn(40, 50, generator=g, dtype=torch.float64).numpy()
+    rng = np.random.default_rng(1)
+    gv_trg, cvgv = rng.uniform(0.5, 2.0, 49), rng.uniform(0.5, 2.0, 49)
+    datamean = np.mean(cv[:, 1:], axis=0)
+    ref = np.c_[cv[:, 0], np.sqrt(gv_trg / cvgv) * (cv[:, 1:] - datamean) + datamean]
+    mine = cycle.gv_postfilter(torch.tensor(cv), torch.tensor(gv_trg), torch.tensor(cvgv)).numpy()
+    assert np.abs(mine - ref).max() < 1e-12
+
+
 def test_shard_utterances(pkg):
     from cyclevae_vc_b200.cycle import shard_utterances
     for n, w in ((80, 8), (7, 2), (5, 4), (3, 8)):
