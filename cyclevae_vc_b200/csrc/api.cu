@@ -161,6 +161,7 @@ static int check_net(const cvb_net* net) {
     CVB_REQUIRE(net->kernel_size % 2 == 1 && net->kernel_size >= 1, "kernel_size must be odd");
     CVB_REQUIRE(net->n_conv >= 1 && net->n_conv <= 4, "dilation_size (conv layers) must be in 1..4");
     CVB_REQUIRE(net->w_ih && net->w_hh && net->b_ih && net->b_hh && net->out_w && net->out_b, "GRU/out_1 parameter is NULL");
+    CVB_REQUIRE((reinterpret_cast<uintptr_t>(net->w_hh) & 15u) == 0, "w_hh must be 16-byte aligned (the kernels read it as float4)");
     for (int i = 0; i < net->n_conv; ++i) CVB_REQUIRE(net->conv_w[i] && net->conv_b[i], "conv parameter %d is NULL", i);
     if (net->has_scale_in) CVB_REQUIRE(net->scale_in_w && net->scale_in_b, "scale_in parameter is NULL");
     if (net->has_scale_out) CVB_REQUIRE(net->scale_out_w && net->scale_out_b, "scale_out parameter is NULL");

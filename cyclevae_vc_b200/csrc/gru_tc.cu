@@ -171,17 +171,23 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     if (a.trace && c == 0 && threadIdx.x == 0) a.trace[60] = clock64();
     // ---- one-time setup: weights -> fp16 hi/lo in UMMA K-major core-matrix order -----------------
     {
-        const int Kr = L.nch * TF_KC;
-        for (int i = threadIdx.x; i < TF_NW * Kr; i += TF_NT) {
-            const int n = i / Kr, kl = i - n * Kr;   // n = g*32 + unit of the block
+        // one item = 8 consecutive k of one operand row = one 16-byte core-matrix row (hi) + one (lo); consecutive
+        // threads take consecutive rows, so a quarter warp's stores cover 128 contiguous bytes (no bank conflicts) and
+        // every global read is a full 32-byte sector
+        const int n_items = TF_NW * L.nch * (TF_KC / 8);
+        for (int i = threadIdx.x; i < n_items; i += TF_NT) {
+            const int kg = i / TF_NW, n = i - kg * TF_NW;   // n = g*32 + unit of the block
             const int g = n / TF_UB, ul = n - g * TF_UB;
-            const float w = f.Whh[(size_t)(g * H + ublk0 + ul) * H + k0 + kl];
-            uint16_t hi, lo;
-            split_f16(w, hi, lo);
+            const int kl = kg * 8;
+            const float4* src = reinterpret_cast<const float4*>(f.Whh + (size_t)(g * H + ublk0 + ul) * H + k0 + kl);
+            const float4 w0 = __ldg(src), w1 = __ldg(src + 1);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            uint4 hi, lo;
+            split8_f16(w, hi, lo);
             const uint32_t off = (uint32_t)(kl / TF_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TF_KC) >> 3) * 128u +
-                                 (uint32_t)(n & 7) * 16u + (uint32_t)(kl & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sW + off) = hi;
-            *reinterpret_cast<uint16_t*>(sW + (TF_NW / 8) * 1024u + off) = lo;
+                                 (uint32_t)(n & 7) * 16u;
+            *reinterpret_cast<uint4*>(sW + off) = hi;
+            *reinterpret_cast<uint4*>(sW + (TF_NW / 8) * 1024u + off) = lo;
         }
         for (int i = threadIdx.x; i < 32 * 64; i += TF_NT) {   // B2[n = g*8+uu][k] = W_y[g*H + u0 + uu][k]; rows 24..31 zero
             const int n = i >> 6, k = i & 63;

@@ -156,16 +156,29 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
 
     // ---- one-time setup --------------------------------------------------------------------------
     {
-        const int Kr = L.nch * TB_KC;
-        for (int i = threadIdx.x; i < L.Ublk * Kr; i += TB_NT) {
-            const int n = i % L.Ublk, kl = i / L.Ublk;
-            const float w = f.Whh[(size_t)(k0 + kl) * H + ublk0 + n];
-            uint16_t hi, lo;
-            split_bf16(w, hi, lo);
-            const uint32_t off = (uint32_t)(kl / TB_KC) * ((uint32_t)S * 2048u) + (uint32_t)(n >> 3) * 1024u +
-                                 (uint32_t)((kl % TB_KC) >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(kl & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sW + off) = hi;                       // chunk layout: [hi: S blocks][lo: S blocks]
-            *reinterpret_cast<uint16_t*>(sW + (uint32_t)S * 1024u + off) = lo;
+        // one item = an 8 (k) x 4 (n) block of W_hh^T: 8 float4 reads along the contiguous unit axis, transposed in
+        // registers into four 16-byte core-matrix rows (hi) + four (lo)
+        const int nq = L.Ublk >> 2;
+        const int n_items = nq * L.nch * (TB_KC / 8);
+        for (int i = threadIdx.x; i < n_items; i += TB_NT) {
+            const int kg = i / nq, n4 = (i - kg * nq) * 4;
+            const int kl = kg * 8;
+            float4 r[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = __ldg(reinterpret_cast<const float4*>(f.Whh + (size_t)(k0 + kl + q) * H + ublk0 + n4));
+            const uint32_t off = (uint32_t)(kl / TB_KC) * ((uint32_t)S * 2048u) + (uint32_t)((kl % TB_KC) >> 3) * 128u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = e == 0 ? r[q].x : e == 1 ? r[q].y : e == 2 ? r[q].z : r[q].w;
+                uint4 hi, lo;
+                split8(w, hi, lo);
+                const int n = n4 + e;
+                const uint32_t o2 = off + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 16u;
+                *reinterpret_cast<uint4*>(sW + o2) = hi;                       // chunk layout: [hi: S blocks][lo: S blocks]
+                *reinterpret_cast<uint4*>(sW + (uint32_t)S * 1024u + o2) = lo;
+            }
         }
         for (int i = threadIdx.x; i < 16 * 64; i += TB_NT) {   // B2[n][k] = W_o[k][u0 + n]
             const int n = i >> 6, k = i & 63;

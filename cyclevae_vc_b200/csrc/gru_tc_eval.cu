@@ -127,22 +127,31 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
 
     // ---- one-time setup: folded weights -> fp16 hi/lo in UMMA K-major core-matrix order ------------------
     {
-        const int Kr = L.nch * TE_KC;
-        for (int i = threadIdx.x; i < TE_NW * Kr; i += TE_NT) {
-            const int n = i / Kr, kl = i - n * Kr;   // n = g*32 + unit of the block; g: 0 r', 1 z', 2 hn, 3 in'
+        // one item = 8 consecutive k of one operand row = one 16-byte core-matrix row (hi) + one (lo); consecutive
+        // threads take consecutive rows: conflict-free 16-byte stores, full-sector global reads
+        const int n_items = TE_NW * L.nch * (TE_KC / 8);
+        for (int i = threadIdx.x; i < n_items; i += TE_NT) {
+            const int kg = i / TE_NW, n = i - kg * TE_NW;   // n = g*32 + unit of the block; g: 0 r', 1 z', 2 hn, 3 in'
             const int g = n / TE_UB, ul = n - g * TE_UB;
-            const size_t col = (size_t)k0 + kl;
-            const int u = ublk0 + ul;
-            float w;
-            if (g < 2) w = a.Whh[(size_t)(g * H + u) * H + col] + a.Wfb[(size_t)(g * H + u) * H + col];
-            else if (g == 2) w = a.Whh[(size_t)(2 * H + u) * H + col];
-            else w = a.Wfb[(size_t)(2 * H + u) * H + col];
-            uint16_t hi, lo;
-            split_f16(w, hi, lo);
+            const int kl = kg * 8;
+            const size_t at = (size_t)((g < 2 ? g : 2) * H + ublk0 + ul) * H + k0 + kl;
+            float w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q] = 0.f;
+            if (g < 3) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.Whh + at)), w1 = __ldg(reinterpret_cast<const float4*>(a.Whh + at) + 1);
+                w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+            }
+            if (g != 2) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.Wfb + at)), w1 = __ldg(reinterpret_cast<const float4*>(a.Wfb + at) + 1);
+                w[0] += w0.x; w[1] += w0.y; w[2] += w0.z; w[3] += w0.w; w[4] += w1.x; w[5] += w1.y; w[6] += w1.z; w[7] += w1.w;
+            }
+            uint4 hi, lo;
+            split8_f16(w, hi, lo);
             const uint32_t off = (uint32_t)(kl / TE_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TE_KC) >> 3) * 128u +
-                                 (uint32_t)(n & 7) * 16u + (uint32_t)(kl & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sW + off) = hi;
-            *reinterpret_cast<uint16_t*>(sW + (TE_NW / 8) * 1024u + off) = lo;
+                                 (uint32_t)(n & 7) * 16u;
+            *reinterpret_cast<uint4*>(sW + off) = hi;
+            *reinterpret_cast<uint4*>(sW + (TE_NW / 8) * 1024u + off) = lo;
         }
         if (threadIdx.x < 24) sBh[threadIdx.x] = a.bhh[(threadIdx.x >> 3) * H + u0 + (threadIdx.x & 7)];
         if (threadIdx.x == 0) {

@@ -44,7 +44,7 @@ typedef struct cvb_net {
     const float* conv_w[4];   /* layer i: [in*k^(i+1), in*k^i, k]  (gru_vae.py:47-51) */
     const float* conv_b[4];   /* layer i: [in*k^(i+1)] */
     const float* w_ih;        /* gru.weight_ih_l0 [3H, in*k^n + out], gate rows r,z,n */
-    const float* w_hh;        /* gru.weight_hh_l0 [3H, H] */
+    const float* w_hh;        /* gru.weight_hh_l0 [3H, H]; 16-byte aligned */
     const float* b_ih;        /* [3H] */
     const float* b_hh;        /* [3H] */
     const float* out_w;       /* out_1.weight [out,H,1] */
