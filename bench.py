@@ -283,6 +283,18 @@ def run_native(args):
         # launches alternate encoder (out 64) / decoder (out 50) passes: 4 enc + 6 dec per step
         fl = B * T * (4 * recurrence_flops_per_frame(2 * LAT, bwd) + 6 * recurrence_flops_per_frame(NMCEP, bwd)) / 10.0
         achieved = fl / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (B=80 T=80 ENC pass);
+        # only quoted for the workload it was captured on
+        traffic, traffic_src = None, None
+        if B == 80 and T == 80:
+            try:
+                for line in open(os.path.join(ROOT, "profiles", "r01_ncu_tc_summary.csv")):
+                    c = line.strip().split(",")
+                    if c[0] == dom + "_tc":
+                        traffic = (float(c[8]) + float(c[9])) * 1e6
+                        traffic_src = "profiles/r01_ncu_tc_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+            except Exception:
+                pass
         res = {
             "metric": METRIC, "value": B * T * world / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -296,7 +308,7 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": n_l,
+                         "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": avg_ms, "launches_timed": n_l,
                          "algorithmic_flops_per_launch": fl, "peak_source": peak_src,
                          "share_of_step": {k: v[0] / args.steps / ms for k, v in prof.items()},
                          "us_per_recurrent_step": avg_ms * 1e3 / T,
