@@ -4,9 +4,11 @@
 //     W_y y_{t-1} = (W_y W_o) h_{t-1} + W_y b_o =: W_fb h_{t-1} + c_fb      (t >= 1)
 // and one step needs only h_{t-1}:
 //     a_r = gx_r + b_hr + (W_hr + W_fb,r) h      a_z likewise      gh_n = W_hn h + b_hn      gi_n = gx_n + W_fb,n h
-// (c_fb is added to gx[t >= 1] by the host before the launch; the first step's feedback is the caller's y_in, so
-// gx[0] += W_y y_in - W_fb h_in cancels the folded term there; all y_t come from ONE product Y = H W_o^T + b_o after
-// the launch).  Per step there is a single grid-wide exchange (h_t) instead of two.
+// (c_fb rides in the bias of the caller's gx product; the first step's feedback is the caller's y_in, so
+// gx[0] += W_y y_in - c_fb - W_fb h_in takes the folded terms back out there; all y_t come from ONE product
+// Y = H W_o^T + b_o after the launch).  Per step there is a single exchange of h_t instead of two grid-wide ones,
+// and it is not grid-wide either: arrival is counted per cluster (= per 32 units of h), a K stage of the next step is
+// pulled as soon as the cluster(s) producing its units have arrived (see the producer warp).
 //
 // Same 2-D split over clusters of 4 CTAs as gru_tc.cu: cluster = 32 hidden units, CTA j = K-slice j of the
 // contraction for the block's 4 x 32 rows [r' | z' | hn | in'], finaliser of 8 units; operands fp16 hi+lo with B
