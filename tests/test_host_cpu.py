@@ -144,6 +144,55 @@ def test_pack_utterances_and_gv_postfilter(pkg):
     assert np.abs(mine - ref).max() < 1e-12
 
 
+def test_feature_pack_roundtrip_and_trainer_batch(pkg, tmp_path):
+    """the flat feature cache returns the arrays bit for bit, PairDataset items equal the reference's
+    FeatureDatasetSingleVAE.__getitem__ semantics (dataset.py:67-101: zero padding to pad_len with `padding()`,
+    dataset.py:18-26; 2-way speaker codes keyed on the directory's speaker), and collate_trimmed equals the DataLoader's
+    default collate followed by the trainer's trimming (train_*.py:47-63)."""
+    from cyclevae_vc_b200 import features
+    rng = np.random.default_rng(5)
+    utts = []
+    for spk in ("SF1", "TF1"):
+        for k, T in enumerate((31, 17, 44)):
+            n_spc = T - 6
+            utts.append({"name": f"{spk}/utt{k}", "spk": spk, "feat_org_lf0": rng.normal(size=(T + (spk == "TF1") * 3, 54)),
+                         "cvuvlogf0fil_ap": rng.normal(size=(T + (spk == "TF1") * 3, 4)),
+                         "spcidx_range": np.sort(rng.choice(T, n_spc, replace=False))[None, :]})
+    path = str(tmp_path / "feats.cvbfeat")
+    features.write_pack(path, utts)
+    pack = features.FeaturePack(path)
+    assert len(pack) == 6 and pack.names == [u["name"] for u in utts]
+    for i, u in enumerate(utts):
+        assert np.array_equal(pack.array(i, "feat_org_lf0"), u["feat_org_lf0"].astype(np.float32))
+        assert np.array_equal(pack.array(i, "cvuvlogf0fil_ap"), u["cvuvlogf0fil_ap"].astype(np.float32))
+        assert np.array_equal(pack.array(i, "spcidx_range"), u["spcidx_range"][0])
+    src = [f"SF1/utt{k}" for k in range(3)] + [f"TF1/utt{k}" for k in range(3)]
+    src_trg = [f"TF1/utt{k}" for k in range(3)] + [f"SF1/utt{k}" for k in range(3)]
+    ds = features.PairDataset(pack, src, src_trg, spk_src="SF1", pad_len=50)
+    it = ds[4]   # a TF1 utterance: codes swap (dataset.py:77-80)
+    u, v = utts[4], utts[1]
+    T = u["feat_org_lf0"].shape[0]
+    assert it["flen_src"] == T and it["flen_src_trg"] == v["feat_org_lf0"].shape[0] and it["flen_spc_src"] == u["spcidx_range"].shape[1]
+    assert it["h_src"].shape == (50, 54) and it["h_src"].dtype == torch.float32 and it["spcidx_src"].dtype == torch.int64
+    assert torch.equal(it["h_src"][:T], torch.tensor(u["feat_org_lf0"].astype(np.float32))) and float(it["h_src"][T:].abs().sum()) == 0
+    assert torch.equal(it["src_code"][:T], torch.tensor([[0.0, 1.0]]).expand(T, 2)) and float(it["src_code"][T:].abs().sum()) == 0
+    assert torch.equal(it["trg_code"][:T], torch.tensor([[1.0, 0.0]]).expand(T, 2))
+    assert torch.equal(it["spcidx_src"][:it["flen_spc_src"]], torch.tensor(u["spcidx_range"][0]))
+    assert torch.equal(it["h_src_trg"][:it["flen_src_trg"]], torch.tensor(v["feat_org_lf0"].astype(np.float32)))
+    # trainer batch: default collate of the padded items, then the trimming of train_*.py:47-63
+    idxs = [0, 4, 2]
+    ref = torch.utils.data.default_collate([ds[i] for i in idxs])
+    got = features.collate_trimmed(ds, idxs)
+    for k, lk in (("h_src", "flen_src"), ("src_code", "flen_src"), ("trg_code", "flen_src"), ("cv_src", "flen_src"),
+                  ("spcidx_src", "flen_spc_src"), ("h_src_trg", "flen_src_trg"), ("spcidx_src_trg", "flen_spc_src_trg")):
+        mx = int(ref[lk].max())
+        assert torch.equal(got[lk], ref[lk])
+        assert got[k].dtype == ref[k].dtype and torch.equal(got[k], ref[k][:, :mx]), k
+    assert got["featfile_src"] == ref["featfile_src"]
+    staged = features.DeviceStager(torch.device("cpu")).put(got)   # CPU: pass-through copies through the slot buffers
+    assert all(torch.equal(staged[k], got[k]) for k in got if torch.is_tensor(got[k]))
+
+
 def test_shard_utterances(pkg):
     from cyclevae_vc_b200.cycle import shard_utterances
     for n, w in ((80, 8), (7, 2), (5, 4), (3, 8)):
