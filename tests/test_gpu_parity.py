@@ -532,7 +532,7 @@ def test_tensor_core_forward_any_row_count(cvb):
     torch.manual_seed(0)
     enc = cvb.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, do_prob=0.5, scale_out_flag=False).cuda().eval()
     enc.apply(cvb.initialize)
-    for B, T in ((17, 2), (17, 9), (43, 12), (86, 12), (128, 6), (300, 5)):
+    for B, T in ((1, 1), (3, 1), (17, 2), (17, 9), (43, 12), (86, 12), (128, 6), (300, 5)):
         x = torch.randn(B, T, 54, device="cuda")
         y0 = 0.1 * torch.randn(B, 1, 64, device="cuda")
         h0 = 0.3 * torch.randn(1, B, 1024, device="cuda")
@@ -595,6 +595,49 @@ def test_ragged_batch_conversion_equals_per_utterance(cvb):
     ref = np.c_[cv[:, 0], np.sqrt(gv_trg / cvgv) * (cv[:, 1:] - datamean) + datamean]
     mine = cycle.gv_postfilter(got[4], torch.tensor(gv_trg, dtype=torch.float32).cuda(), torch.tensor(cvgv, dtype=torch.float32).cuda())
     assert _maxabs(mine, ref.astype(np.float32)) < 1e-5
+
+
+def test_tensor_core_recurrence_shortest_sequences(cvb):
+    """Edge shapes of the training kernels: a single frame (T = 1: the prologue and one step, nothing carried inside the
+    launch) and a single utterance (B = 1), tensor-core path vs the all-fp32 path, outputs and every gradient."""
+    from cyclevae_vc_b200._lib import lib
+    lat = 32
+    mean, std = orc.synth_stats(50)
+    spec = orc.encoder_spec(54, lat, 1024)
+    P = orc.init_params(spec, 201, gain=1.5, bias_std=0.02, mean=mean, scale=std)
+    m = _module(cvb, spec, P).train()
+    g = torch.Generator().manual_seed(17)
+    for B, T in ((1, 1), (1, 7), (9, 1), (2, 3)):
+        x = torch.randn(B, T, spec.in_dim, generator=g).cuda()
+        y0 = (0.3 * torch.randn(B, 1, spec.out_dim, generator=g)).cuda()
+        h0 = (0.5 * torch.randn(1, B, 1024, generator=g)).cuda()
+        mc = ((torch.rand(B, T, spec.conv_dim, generator=g) >= 0.5).float() * 2).cuda()
+        mg = ((torch.rand(B, T, 1024, generator=g) >= 0.5).float() * 2).cuda()
+        w_o = torch.randn(B, T, spec.out_dim, generator=g).cuda()
+
+        def run(exact):
+            if exact:
+                os.environ["CVB_RECURRENCE"] = "exact"
+                os.environ["CVB_GEMM"] = "cublas"
+            try:
+                xs, ys, hs = (t.clone().requires_grad_(True) for t in (x, y0, h0))
+                for p in m.parameters():
+                    p.grad = None
+                m.inject_dropout_masks(mc, mg)
+                o, yl, hl = m(xs, ys, h_in=hs, do=True, clamp_vae=True, lat_dim=lat)
+                ((o * w_o).sum() + yl.sum() + hl.sum()).backward()
+                torch.cuda.synchronize()
+                assert lib.cvb_last_recurrence_path(0) == (0 if exact else 1) and lib.cvb_last_recurrence_path(1) == (0 if exact else 1)
+                return [o.detach(), yl.detach(), hl.detach(), xs.grad, ys.grad, hs.grad] + \
+                       [p.grad.clone() for p in m.parameters() if p.grad is not None]
+            finally:
+                os.environ.pop("CVB_RECURRENCE", None)
+                os.environ.pop("CVB_GEMM", None)
+
+        ref, got = run(True), run(False)
+        assert len(ref) == len(got)
+        for a, b in zip(got, ref):
+            assert _maxabs(a, b) < 1e-4 * max(1e-3, float(b.abs().max())), (B, T, tuple(b.shape))
 
 
 def test_forward_only_kernel_choice(cvb):
