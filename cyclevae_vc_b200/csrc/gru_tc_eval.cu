@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
         int s = 0, slot = 0;
         uint32_t ph = 1;
         const int ncs = (H / TE_S) / TE_UB;           // clusters that produce this CTA's K-slice
-        const unsigned* flag = lane == 31 ? a.ctr + c / TE_S - 31 : a.ctr + j * ncs;   // lane 31 watches the OWN cluster
+        // lanes [0, ncs) watch the clusters that produce this CTA's K-slice, lane 31 the OWN cluster
+        const unsigned* flag = lane == 31 ? a.ctr + c / TE_S : a.ctr + j * ncs + (lane < ncs ? lane : 0);
         const unsigned per_stage = (unsigned)(L.KCA / TE_UB);   // producing clusters per stage: 1 or 2
         const size_t sub_elems = (size_t)L.MB * L.KCA * 8;
         for (int t = 0; t < T; ++t) {
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                 // inboxes completed, i.e. after this CTA's outgoing partial sums (staged in the ring) were delivered, and
                 // after they finished reading the inbox the next exchange will overwrite.
                 const bool polls = lane < ncs || lane == 31;
-                const unsigned v = polls ? ld_acquire_gpu(flag + lane) : 0u;
+                const unsigned v = polls ? ld_acquire_gpu(flag) : 0u;
                 const unsigned ready = __ballot_sync(0xffffffffu, polls && v >= target);
                 if (!(ready >> 31)) continue;
                 while (issued < L.nsub) {
