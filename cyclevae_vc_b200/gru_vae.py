@@ -281,7 +281,7 @@ class GRU_RNN(nn.Module):
             if h0.shape[0] != B:
                 raise ValueError(f"h_in batch {h0.shape[0]} != x batch {B}")
         mc = mg = None
-        if do and self.do_prob > 0:
+        if do and self.do_prob > 0 and self.training:   # nn.Dropout is the identity in eval mode (gru_vae.py:303-304,312-313)
             if self._injected_masks is not None:
                 mcb, mgb = self._injected_masks
                 self._injected_masks = None
