@@ -11,6 +11,7 @@ cannot run here: h5py / dtw_c / pysptk are absent).
     convert          stage-6 conversion composition                 decode_*.py:303-305,318
     convert_utterances  the same for a list of ragged utterances, packed    new
     gv_postfilter    global-variance post-filter on the device      decode_*.py:419-420
+    cvgv_stats       GV statistics of converted utterances          calc_cvgv_*.py:203,320-321
 """
 from __future__ import annotations
 
@@ -295,3 +296,11 @@ def gv_postfilter(cvmcep: torch.Tensor, gv_mean_trg: torch.Tensor, cvgv_mean: to
     rest = cvmcep[:, 1:]
     m = rest.mean(0, keepdim=True)
     return torch.cat((cvmcep[:, :1], torch.sqrt(gv_mean_trg / cvgv_mean).to(rest) * (rest - m) + m), 1)
+
+
+def cvgv_stats(converted: Sequence[torch.Tensor]):
+    """calc_cvgv_*.py:203,320-321: per utterance the (population) variance over frames of coefficients 1.., then mean and
+    variance of those vectors over the utterances -> (cvgv_mean, cvgv_var), each [D-1]; `cvgv_mean` is what
+    `gv_postfilter` divides the target speaker's GV by.  Stays on the device of the inputs (float64 accumulation)."""
+    per_utt = torch.stack([c[:, 1:].double().var(dim=0, unbiased=False) for c in converted])
+    return per_utt.mean(0), per_utt.var(dim=0, unbiased=False)

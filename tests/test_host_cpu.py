@@ -142,6 +142,12 @@ def test_pack_utterances_and_gv_postfilter(pkg):
     ref = np.c_[cv[:, 0], np.sqrt(gv_trg / cvgv) * (cv[:, 1:] - datamean) + datamean]
     mine = cycle.gv_postfilter(torch.tensor(cv), torch.tensor(gv_trg), torch.tensor(cvgv)).numpy()
     assert np.abs(mine - ref).max() < 1e-12
+    # GV statistics over a set of converted utterances, calc_cvgv_*.py:203,320-321 restated in numpy
+    convs = [torch.randn(T, 50, generator=g, dtype=torch.float64) for T in (30, 12, 51)]
+    cvlist = [np.var(c.numpy()[:, 1:], axis=0) for c in convs]
+    m, v = cycle.cvgv_stats(convs)
+    assert np.abs(m.numpy() - np.mean(np.array(cvlist), axis=0)).max() < 1e-12
+    assert np.abs(v.numpy() - np.var(np.array(cvlist), axis=0)).max() < 1e-12
 
 
 def test_feature_pack_roundtrip_and_trainer_batch(pkg, tmp_path):
