@@ -326,10 +326,12 @@ int gemm_tc(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
     const int smem = GT_NS * GT_STAGE_BYTES + 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // function attributes are per device
+    int dev = 0;
+    CVB_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         CVB_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     GemmTcArgs g;
     g.At = At;
