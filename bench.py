@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""mcep frames/sec of one CycleVAE optimisation step (cyc2: 4 encoder + 6 decoder GRU_RNN passes forward,
-losses, BPTT, gradient all-reduce at N>1, Adam) -- BASELINE.json's metric on configs[1].
+"""Throughput of the GRU-VAE hot path in mcep frames/sec -- BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch-utt B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|decode|spk4] [--batch-utt B] [--impl reference]
 
 N>1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
-Workload (config.workload): hu1024 ld32 ks3 ds2 cyc2, 80-frame chunks (the reference's --batch_size 80 frames,
-train_*.py:70-134) x B utterances per GPU (default 80: the literal "bs80" of configs[1]; the recipe's own
-batch_size_utt values 1 / 8 are reachable with --batch-utt).  Weak scaling: B per GPU is fixed.
 
-`--impl reference` times the CPU restatement of the reference's path (oracle/gru_vae_oracle.py -- the reference
-is pure Python and cannot travel to the GPU box) on the host cores with the same step
-composition, on a bounded sample of the workload.
+Workloads (config.workload names the one that ran):
+  train   configs[1]: SF1<->TF1 CycleVAE hu1024 ld32 ks3 ds2 cyc2 -- one optimisation step = 4 encoder + 6 decoder
+          GRU_RNN passes forward (dropout + noise drawn on device), losses, BPTT, gradient all-reduce at N>1, Adam
+          (train_*.py:1298-1420) on 80-frame chunks (--batch_size 80, train_*.py:70-134) x B utterances per GPU.
+          Default B = 80 (the literal "bs80"); the recipe's own batch_size_utt values are --batch-utt 1 / 8.
+  spk4    configs[3]: the same step with 4-speaker one-hot codes (decoder in_dim 36), default B = 8 per GPU.
+  decode  configs[2]: stage-6 conversion (decode_*.py:303-305,318: ENC -> latent mean -> DEC) of 512 utterances x 800
+          frames per GPU, eval mode; config.full_stage6 adds the 2 ENC + 3 DEC of decode_*.py:303-323.
+Weak scaling: the per-GPU batch is fixed.
+
+`--impl reference` times the reference's own CPU implementation of the same workload at the SAME batch size: the
+unmodified src/nets/gru_vae.py (vendored by __graft_entry__.build() into the git-ignored oracle/_ref/, kind
+"reference"; the CPU restatement oracle/gru_vae_oracle.py, kind "port", when that copy is absent) driven by the
+trainer's / decoder's step composition restated from train_*.py:1298-1420 / decode_*.py:303-318 (the scripts themselves
+need h5py / dtw_c / pysptk, absent here).  It never imports cyclevae_vc_b200.
 """
 import argparse
 import json
@@ -26,8 +34,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-HIDDEN, LAT, NSPK, NMCEP, STDIM, NCYC, TCHUNK = 1024, 32, 2, 50, 4, 2, 80
+HIDDEN, LAT, NMCEP, STDIM, NCYC, TCHUNK = 1024, 32, 50, 4, 2, 80
+DEC_UTT, DEC_T, N_SMPL = 512, 800, 300
 METRIC = "mcep frames/sec (cyc2 enc+dec fwd+bwd)"
+METRIC_DECODE = "mcep frames/sec (stage-6 conversion, enc+dec fwd)"
 
 
 def parse():
@@ -35,24 +45,46 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch-utt", type=int, default=80, help="utterances per GPU (80-frame chunk each)")
+    ap.add_argument("--workload", default="train", choices=["train", "decode", "spk4"])
+    ap.add_argument("--batch-utt", type=int, default=None, help="utterances per GPU (default: 80 train, 8 spk4, 512 decode)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--ref-batch-utt", type=int, default=8, help="utterances in the CPU sample of --impl reference / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch_utt is None:
+        a.batch_utt = {"train": 80, "spk4": 8, "decode": DEC_UTT}[a.workload]
+    a.n_spk = 4 if a.workload == "spk4" else 2
+    return a
 
 
-def workload_name(B):
-    return f"SF1<->TF1 CycleVAE hu{HIDDEN} ld{LAT} ks3 ds2 cyc{NCYC}, {TCHUNK}-frame chunk x {B} utterances per GPU (bs80)"
+def config_of(args, world):
+    """The `config` object -- identical in the native and the reference arm."""
+    B = args.batch_utt
+    if args.workload == "decode":
+        return {"workload": f"stage-6 decode: batch conversion {B} utts x {DEC_T} frames x {NMCEP} mcep per GPU, hu{HIDDEN} ld{LAT}, "
+                            f"1 ENC + 1 DEC forward, latent = mean of {N_SMPL} samples (configs[2])",
+                "frames_per_step_per_gpu": B * DEC_T, "parallelism": f"dp{world} (utterance shards, no collective)"}
+    name = "SF1<->TF1 CycleVAE" if args.workload == "train" else "4-speaker many-to-many CycleVAE (one-hot spk code, dec in 36)"
+    return {"workload": f"{name} hu{HIDDEN} ld{LAT} ks3 ds2 cyc{NCYC}, {TCHUNK}-frame chunk x {B} utterances per GPU"
+                        + (" (bs80, configs[1])" if args.workload == "train" and B == 80 else ""),
+            "frames_per_step_per_gpu": B * TCHUNK, "passes_per_step": "4 ENC + 6 DEC fwd+bwd",
+            "parallelism": f"dp{world}", "optimizer": "Adam (in timed region)"}
 
 
 # ------------------------------------------------------------------------------------------------
-# algorithmic work of the recurrence kernels: per frame and per network pass
+# algorithmic work (SURVEY.md §8d)
 def recurrence_flops_per_frame(out_dim, backward):
     fwd = 2 * 3 * HIDDEN * (HIDDEN + out_dim) + 2 * out_dim * HIDDEN          # W_hh h + W_y y ; W_o o
     if not backward:
         return fwd
     return 2 * 3 * HIDDEN * HIDDEN + 2 * 3 * HIDDEN * out_dim + 2 * out_dim * HIDDEN   # dgh W_hh ; dgi W_y ; dy W_o
+
+
+def folded_flops_per_frame():
+    return 2 * 4 * HIDDEN * HIDDEN        # [r' | z' | hn | in'] rows of the folded inference recurrence (gru_tc_eval.cu)
+
+
+def frontend_bytes_per_frame(in_dim):
+    return 4 * in_dim + 4 * 9 * in_dim    # read x, write xc (SURVEY.md §8d: 2160 B ENC, 1360 B DEC)
 
 
 class ClockSampler:
@@ -100,14 +132,82 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_factory(state_enc, state_dec, B):
-    """One cyc2 fwd+bwd+Adam step of the CPU restatement (the checker, used here only as the timed baseline)."""
+# CPU arm: the reference module (oracle/_ref) or the port (oracle/gru_vae_oracle.py).  Nothing here imports
+# cyclevae_vc_b200; the oracle is the thing TIMED here, never a product path.
+def _load_reference_module():
+    """The unmodified reference src/nets/gru_vae.py, vendored into oracle/_ref/ by build(); None when absent."""
+    path = os.path.join(ROOT, "oracle", "_ref", "gru_vae.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("cyclevae_reference_gru_vae", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _cpu_models(ref, n_spk):
+    """Encoder / decoder as the trainer builds them (train_*.py:310-347) from the reference's own classes."""
     import torch
     from oracle import gru_vae_oracle as orc
-    from cyclevae_vc_b200 import synth
-    enc, dec = orc.encoder_spec(STDIM + NMCEP, LAT, HIDDEN), orc.decoder_spec(LAT, NSPK, NMCEP, HIDDEN)
-    Pe = {k: v.detach().cpu().clone() for k, v in state_enc.items()}
-    Pd = {k: v.detach().cpu().clone() for k, v in state_dec.items()}
+    mean, std = orc.synth_stats(NMCEP)
+    torch.manual_seed(1)
+    enc = ref.GRU_RNN(in_dim=STDIM + NMCEP, out_dim=2 * LAT, hidden_units=HIDDEN, do_prob=0.5, scale_out_flag=False)
+    dec = ref.GRU_RNN(in_dim=LAT + n_spk, out_dim=NMCEP, hidden_units=HIDDEN, do_prob=0.5, scale_in_flag=False)
+    enc.apply(ref.initialize)
+    dec.apply(ref.initialize)
+    enc.scale_in.weight = torch.nn.Parameter(torch.diag(torch.tensor(1.0 / std, dtype=torch.float32)).unsqueeze(2))
+    enc.scale_in.bias = torch.nn.Parameter(torch.tensor(-(mean / std), dtype=torch.float32))
+    dec.scale_out.weight = torch.nn.Parameter(torch.diag(torch.tensor(std[STDIM:], dtype=torch.float32)).unsqueeze(2))
+    dec.scale_out.bias = torch.nn.Parameter(torch.tensor(mean[STDIM:], dtype=torch.float32))
+    for p in list(enc.scale_in.parameters()) + list(dec.scale_out.parameters()):
+        p.requires_grad = False
+    return enc, dec, mean, std
+
+
+def cpu_train_step_factory(B, n_spk):
+    """One cyc2 fwd+bwd+Adam step on the CPU at B utterances x 80 frames -> (step(), kind)."""
+    import torch
+    from oracle import gru_vae_oracle as orc
+    ref = _load_reference_module()
+    x, cv, sc, tc = orc.synth_batch(B, TCHUNK, 100, n_spk=n_spk)
+    mean, std = orc.synth_stats(NMCEP)
+    y0e = torch.zeros(B, 1, 2 * LAT)
+    y0d = torch.tensor((0 - mean[STDIM:]) / std[STDIM:], dtype=torch.float32).reshape(1, 1, -1).repeat(B, 1, 1)
+    if ref is not None:
+        # the reference's own modules, dropout drawn by their nn.Dropout, losses by its loss_vae / TWFSEloss in the
+        # trainer's per-utterance loops (train_*.py:1326-1338, 1363-1410), torch.optim.Adam (:377)
+        enc, dec, _, _ = _cpu_models(ref, n_spk)
+        enc.train(); dec.train()
+        crit = ref.TWFSEloss()
+        train = [p for m in (enc, dec) for sub in (m.conv, m.gru, m.out_1) for p in sub.parameters()]
+        opt = torch.optim.Adam(train, lr=1e-4)
+
+        def samp(p):   # sampling_vae_batch (gru_vae.py:85-98) without its hard-coded .cuda()
+            return p[:, :, :LAT] + torch.exp(p[:, :, LAT:] / 2) * torch.randn(B, TCHUNK, LAT)
+
+        def step():
+            rec = None
+            total = 0.0
+            for i in range(NCYC):
+                ein = x if i == 0 else torch.cat((x[:, :, :STDIM], rec), 2)
+                lat_src, _, _ = enc(ein, y0e, clamp_vae=True, lat_dim=LAT, do=True)
+                trj_ss, _, _ = dec(torch.cat((sc, samp(lat_src)), 2), y0d, do=True)
+                trj_st, _, _ = dec(torch.cat((tc, samp(lat_src)), 2), y0d, do=True)
+                lat_st, _, _ = enc(torch.cat((cv, trj_st), 2), y0e, clamp_vae=True, lat_dim=LAT, do=True)
+                rec, _, _ = dec(torch.cat((sc, samp(lat_st)), 2), y0d, do=True)
+                for j in range(B):
+                    total = total + crit(trj_ss[j], x[j, :, STDIM:], L2=False, GV=False)[1] + crit(rec[j], x[j, :, STDIM:], L2=False, GV=False)[1] \
+                        + ref.loss_vae(lat_src[j], lat_dim=LAT) + ref.loss_vae(lat_st[j], lat_dim=LAT)
+            opt.zero_grad()
+            total.backward()
+            opt.step()
+            return float(total.detach())
+
+        return step, "reference"
+    enc_s, dec_s = orc.encoder_spec(STDIM + NMCEP, LAT, HIDDEN), orc.decoder_spec(LAT, n_spk, NMCEP, HIDDEN)
+    Pe = orc.init_params(enc_s, 1, mean=mean, scale=std)
+    Pd = orc.init_params(dec_s, 2, mean=mean[STDIM:], scale=std[STDIM:])
     train = []
     for P in (Pe, Pd):
         for k, v in P.items():
@@ -115,24 +215,58 @@ def cpu_reference_step_factory(state_enc, state_dec, B):
                 v.requires_grad_(True)
                 train.append(v)
     opt = torch.optim.Adam(train, lr=1e-4)
-    x, cv, sc, tc = synth.make_batch(B, TCHUNK, 0, NSPK, NMCEP)
-    mean, std = synth.feature_stats(NMCEP)
-    y0e = torch.zeros(B, 1, 2 * LAT)
-    y0d = torch.tensor((0 - mean[STDIM:]) / std[STDIM:], dtype=torch.float32).reshape(1, 1, -1).repeat(B, 1, 1)
 
     def step():
-        eps = [[torch.randn(B, TCHUNK, LAT) for _ in range(3)] for _ in range(NCYC)]          # gru_vae.py:91
+        eps = [[torch.randn(B, TCHUNK, LAT) for _ in range(3)] for _ in range(NCYC)]
         masks = [[((torch.rand(B, TCHUNK, s.conv_dim) >= 0.5).float() * 2, (torch.rand(B, TCHUNK, HIDDEN) >= 0.5).float() * 2)
-                  for s in (enc, dec, dec, enc, dec)] for _ in range(NCYC)]                      # nn.Dropout draws
+                  for s in (enc_s, dec_s, dec_s, enc_s, dec_s)] for _ in range(NCYC)]
         opt.zero_grad()
-        out, _ = orc.cyc_forward(Pe, Pd, enc, dec, x=x, cv=cv, src_code=sc, trg_code=tc, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM,
+        out, _ = orc.cyc_forward(Pe, Pd, enc_s, dec_s, x=x, cv=cv, src_code=sc, trg_code=tc, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM,
                                  y0_enc=y0e, y0_dec=y0d, eps=eps, masks=masks)
         loss, _ = orc.cyc_loss(out, x, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, flen_acc=[TCHUNK] * B, select_utt_idx=list(range(B)))
         loss.backward()
         opt.step()
         return float(loss.detach())
 
-    return step
+    return step, "port"
+
+
+def cpu_decode_step_factory(n_utt):
+    """Stage-6 conversion of n_utt utterances x 800 frames the way the reference does it: ONE utterance per call, unbatched
+    [T,54] layout, 300 latent samples averaged (decode_*.py:303-305,318) -> (step(), kind)."""
+    import torch
+    from oracle import gru_vae_oracle as orc
+    ref = _load_reference_module()
+    x, _, _, tc = orc.synth_batch(n_utt, DEC_T, 200)
+    mean, std = orc.synth_stats(NMCEP)
+    y0e = torch.zeros(1, 1, 2 * LAT)
+    y0d = torch.tensor((0 - mean[STDIM:]) / std[STDIM:], dtype=torch.float32).reshape(1, 1, -1)
+    if ref is not None:
+        enc, dec, _, _ = _cpu_models(ref, 2)
+        enc.eval(); dec.eval()
+
+        def step():
+            with torch.no_grad():
+                for u in range(n_utt):
+                    lat_src, _, _ = enc(x[u], y0e, clamp_vae=True, lat_dim=LAT)
+                    rep = lat_src.unsqueeze(0).repeat(N_SMPL, 1, 1)                       # decode_*.py:304
+                    smp = rep[:, :, :LAT] + torch.exp(rep[:, :, LAT:] / 2) * torch.randn(N_SMPL, DEC_T, LAT)
+                    lat_feat = torch.mean(smp, 0)                                         # :305
+                    dec(torch.cat((tc[u], lat_feat), 1), y0d)                             # :318
+            return 0.0
+
+        return step, "reference"
+    enc_s, dec_s = orc.encoder_spec(STDIM + NMCEP, LAT, HIDDEN), orc.decoder_spec(LAT, 2, NMCEP, HIDDEN)
+    Pe = orc.init_params(enc_s, 1, mean=mean, scale=std)
+    Pd = orc.init_params(dec_s, 2, mean=mean[STDIM:], scale=std[STDIM:])
+
+    def step():
+        for u in range(n_utt):
+            eps_mean = torch.randn(DEC_T, LAT) / N_SMPL ** 0.5
+            orc.convert(Pe, Pd, enc_s, dec_s, x[u], tc[u], lat_dim=LAT, y0_enc=y0e, y0_dec=y0d, eps_mean=eps_mean)
+        return 0.0
+
+    return step, "port"
 
 
 def time_cpu(step, steps, warmup):
@@ -152,32 +286,43 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    from cyclevae_vc_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
-    B = args.ref_batch_utt
-    enc, dec, _ = synth.build_models(HIDDEN, LAT, NSPK, NMCEP, STDIM, device=None)
-    step = cpu_reference_step_factory(enc.state_dict(), dec.state_dict(), B)
-    sec, cores = time_cpu(step, args.steps, max(1, args.warmup))
-    fps = B * TCHUNK / sec
-    sample = f"{B} utterances x {TCHUNK} frames per step (bounded sample of the workload), median of {args.steps} steps"
+    W = max(1, args.warmup)
+    if args.workload == "decode":
+        # a step = a bounded sample of the workload: 4 of the utterances, converted one at a time as the reference does
+        n = 4
+        step, kind = cpu_decode_step_factory(n)
+        frames = n * DEC_T
+        sample = f"{n} of the {args.batch_utt} utterances x {DEC_T} frames per step, one utterance per call (the reference's batch = 1)"
+        metric = METRIC_DECODE
+    else:
+        step, kind = cpu_train_step_factory(args.batch_utt, args.n_spk)
+        frames = args.batch_utt * TCHUNK
+        sample = f"the full per-GPU step: {args.batch_utt} utterances x {TCHUNK} frames, cyc2 fwd+bwd+Adam"
+        metric = METRIC
+    sec, cores = time_cpu(step, args.steps, W)
+    fps = frames / sec
+    src = "unmodified reference src/nets/gru_vae.py (oracle/_ref)" if kind == "reference" else "oracle/gru_vae_oracle.py (CPU restatement)"
+    sample += f"; median of {args.steps} steps; {src}"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args.batch_utt), "cpu_sample": sample},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(args, args.gpus),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
-    import cyclevae_vc_b200 as cvb
+    import cyclevae_vc_b200 as cvb  # noqa: F401  (raises when libcyclevae_b200.so is missing: no fallback)
     from cyclevae_vc_b200 import cycle, synth
     from cyclevae_vc_b200._lib import lib
-    import ctypes as C
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,28 +333,50 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, T = args.batch_utt, TCHUNK
-    enc, dec, y0d1 = synth.build_models(HIDDEN, LAT, NSPK, NMCEP, STDIM, seed=1, device=dev)
-    enc.train(); dec.train()
-    opt = cycle.FlatAdam(cycle.trainable_parameters(enc, dec), lr=1e-4)
-    torch.manual_seed(1000 + rank)                                  # per-rank noise / dropout streams
-    host = synth.make_batch(B, T, 100 + rank, NSPK, NMCEP, pin=True)   # this rank's utterance shard
-    devb = [t.to(dev) for t in host]
-    stage = [torch.empty_like(t, device=dev) for t in host]
+    decode = args.workload == "decode"
+    B, T = args.batch_utt, (DEC_T if decode else TCHUNK)
+    enc, dec, y0d1 = synth.build_models(HIDDEN, LAT, args.n_spk, NMCEP, STDIM, seed=1, device=dev)
+    torch.manual_seed(1000 + rank)                                       # per-rank noise / dropout streams
+    host = synth.make_batch(B, T, 100 + rank, args.n_spk, NMCEP, pin=True)   # this rank's utterance shard
     y0e = torch.zeros(B, 1, 2 * LAT, device=dev)
     y0d = y0d1.to(dev).repeat(B, 1, 1).contiguous()
-    flens = torch.full((B,), T, dtype=torch.int32, device=dev)
-    sel = list(range(B))
 
-    def step(x, cv, sc, tc):
-        opt.zero_grad()
-        out, _ = cycle.cyc_forward(enc, dec, x=x, cv=cv, src_code=sc, trg_code=tc, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM,
-                                   y0_enc=y0e, y0_dec=y0d, do=True)
-        loss, _ = cycle.cyc_loss(out, x, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, flen_acc=None, select_utt_idx=sel, flens_dev=flens)
-        loss.backward()
-        cycle.allreduce_grads(opt.grad)
-        opt.step()
-        return loss
+    if decode:
+        enc.eval(); dec.eval()
+        host = (host[0], host[3])                                        # features, target-speaker code
+        out_host = torch.empty(B, T, NMCEP).pin_memory()
+
+        def step(x, tc):
+            return cycle.convert(enc, dec, x, tc, lat_dim=LAT, y0_enc=y0e, y0_dec=y0d, n_smpl=N_SMPL)
+
+        def read_back(res):
+            out_host.copy_(res, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(out_host[0, 0, 0])
+
+        d2h = B * T * NMCEP * 4
+    else:
+        enc.train(); dec.train()
+        opt = cycle.FlatAdam(cycle.trainable_parameters(enc, dec), lr=1e-4)
+        flens = torch.full((B,), T, dtype=torch.int32, device=dev)
+        sel = list(range(B))
+
+        def step(x, cv, sc, tc):
+            opt.zero_grad()
+            out, _ = cycle.cyc_forward(enc, dec, x=x, cv=cv, src_code=sc, trg_code=tc, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM,
+                                       y0_enc=y0e, y0_dec=y0d, do=True)
+            loss, _ = cycle.cyc_loss(out, x, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, flen_acc=None, select_utt_idx=sel, flens_dev=flens)
+            loss.backward()
+            cycle.allreduce_grads(opt.grad)
+            opt.step()
+            return loss
+
+        def read_back(res):
+            return float(res.item())
+
+        d2h = 4
+    devb = [t.to(dev) for t in host]
+    stage = [torch.empty_like(t, device=dev) for t in host]
 
     def barrier():
         if world > 1:
@@ -245,12 +412,12 @@ def run_native(args):
     launches = (lib.cvb_launch_count() - n0) // args.steps
     lib.cvb_profile_enable(0)
     prof = {}
-    for kind, name in ((0, "k_gru_fwd"), (1, "k_gru_bwd")):
+    for kind, name in ((0, "k_gru_fwd"), (1, "k_gru_bwd"), (3, "frontend_fwd")):
         tot, n = C.c_float(0), C.c_int(0)
         lib.cvb_profile_summary(kind, C.byref(tot), C.byref(n))
         prof[name] = (tot.value, n.value)
     lib.cvb_profile_reset()
-    # ---- end-to-end timing: host (pinned) inputs -> H2D -> step -> loss read back ----------------
+    # ---- end-to-end timing: host (pinned) inputs -> H2D -> step -> result read back ---------------
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -258,12 +425,32 @@ def run_native(args):
     for _ in range(args.steps):
         for d, h in zip(stage, host):
             d.copy_(h, non_blocking=True)
-        last = float(step(*stage).item())
+        last = read_back(step(*stage))
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3) / args.steps)
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(t.numel() * t.element_size() for t in host)
+    full_ms = None
+    if decode:
+        # the complete model work of stage 6 (decode_*.py:303-323): 2 ENC (source, target features) + 3 DEC
+        x, tc = devb
+        sc = torch.roll(tc, 1, 2)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(max(1, args.steps // 2)):
+            with torch.no_grad():
+                lat_s, _, _ = enc(x, y0e, clamp_vae=True, lat_dim=LAT)
+                lat_t, _, _ = enc(x, y0e, clamp_vae=True, lat_dim=LAT)
+                eps = torch.randn(B, T, LAT, device=dev) / N_SMPL ** 0.5
+                from cyclevae_vc_b200 import gru_vae as gv
+                dec(gv.reparam_concat(lat_s, tc, eps, LAT), y0d)
+                dec(gv.reparam_concat(lat_s, sc, eps, LAT), y0d)
+                dec(gv.reparam_concat(lat_t, tc, eps, LAT), y0d)
+        f1.record()
+        barrier()
+        full_ms = max_over_ranks(f0.elapsed_time(f1) / max(1, args.steps // 2))
 
     if rank == 0:
         peaks = {}
@@ -275,56 +462,82 @@ def run_native(args):
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
         if not peak_tf:
             peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+        peak_hbm = peaks.get("hbm_gbs") or 6400.0
         # dominant kernel = the recurrence kernel with the larger share of the step
-        dom = max(prof, key=lambda k: prof[k][0])
-        tot_ms, n_l = prof[dom]
+        rec = {k: v for k, v in prof.items() if k.startswith("k_gru")}
+        dom = max(rec, key=lambda k: rec[k][0])
+        tot_ms, n_l = rec[dom]
         avg_ms = tot_ms / max(1, n_l)
-        bwd = dom == "k_gru_bwd"
-        # launches alternate encoder (out 64) / decoder (out 50) passes: 4 enc + 6 dec per step
-        fl = B * T * (4 * recurrence_flops_per_frame(2 * LAT, bwd) + 6 * recurrence_flops_per_frame(NMCEP, bwd)) / 10.0
+        rows = min(B, 128)                                               # batch rows of one launch (wider batches are sliced)
+        if decode:
+            fl = rows * T * folded_flops_per_frame()
+            note = ("folded inference recurrence (gru_tc_eval.cu): one exchange of h per step, [4H x H] fp16 hi+lo operand resident in "
+                    "shared memory; `achieved` counts algorithmic fp32-equivalent FLOPs (issued 16-bit MMA FLOPs are 3x)")
+        else:
+            bwd = dom == "k_gru_bwd"
+            # launches alternate encoder (out 64) / decoder (out 50) passes: 4 enc + 6 dec per step
+            fl = rows * T * (4 * recurrence_flops_per_frame(2 * LAT, bwd) + 6 * recurrence_flops_per_frame(NMCEP, bwd)) / 10.0
+            note = ("split-precision tcgen05 recurrence (fp16/bf16 hi+lo operands, fp32 TMEM accumulation); `achieved` counts ALGORITHMIC "
+                    "fp32-equivalent FLOPs (issued 16-bit MMA FLOPs are 3x) against the dense bf16 peak; the kernel is bound by the "
+                    "grid-wide exchanges of every recurrent step (us_per_recurrent_step), not by the tensor pipe")
         achieved = fl / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (B=80 T=80 ENC pass);
-        # only quoted for the workload it was captured on
         traffic, traffic_src = None, None
-        if B == 80 and T == 80:
-            try:
-                for line in open(os.path.join(ROOT, "profiles", "r01_ncu_tc_summary.csv")):
-                    c = line.strip().split(",")
-                    if c[0] == dom + "_tc":
-                        traffic = (float(c[8]) + float(c[9])) * 1e6
-                        traffic_src = "profiles/r01_ncu_tc_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
-            except Exception:
-                pass
+        try:
+            for line in open(os.path.join(ROOT, "profiles", "r02_ncu_summary.csv")):
+                c = line.strip().split(",")
+                if c[0] == dom + ("_tc_eval" if decode else "_tc") and int(c[1]) == B:
+                    traffic = (float(c[2]) + float(c[3])) * 1e6
+                    traffic_src = "profiles/r02_ncu_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        except Exception:
+            pass
+        cfg = config_of(args, world)
+        cfg["l2"] = "per-step working set (saved gate activations / gx, > 1 GB at the default batch) exceeds the 126 MB L2; no flush needed"
+        cfg["last_result"] = last
+        if full_ms is not None:
+            cfg["full_stage6"] = {"composition": "2 ENC + 3 DEC (decode_*.py:303-323)", "ms_per_step": full_ms,
+                                  "frames_per_s": B * T * world / (full_ms * 1e-3)}
+        fe_ms, fe_n = prof.get("frontend_fwd", (0.0, 0))
+        roof_fe = None
+        if fe_n:
+            n_enc = fe_n * (1 if decode else 4) // (2 if decode else 10)
+            by = rows * T * (n_enc * frontend_bytes_per_frame(STDIM + NMCEP) + (fe_n - n_enc) * frontend_bytes_per_frame(LAT + args.n_spk)) / fe_n
+            gbs = by / (fe_ms / fe_n * 1e-3) / 1e9
+            roof_fe = {"bound": "hbm", "kernel": "front-end chain (scale_in + two-sided dilated conv + dropout -> xc)", "achieved": gbs,
+                       "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "avg_ms": fe_ms / fe_n, "launches_timed": fe_n,
+                       "algorithmic_bytes_per_call": by,
+                       "note": "bytes = x in + xc out once (SURVEY.md §8d); at fp32-parity precision the conv is compute-bound "
+                               "(243 FLOP/B ENC), so the tensor pipe, not HBM, binds this chain"}
         res = {
-            "metric": METRIC, "value": B * T * world / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": workload_name(B), "frames_per_step_per_gpu": B * T, "passes_per_step": "4 ENC + 6 DEC fwd+bwd",
-                       "parallelism": f"dp{world}", "optimizer": "Adam (fused, in timed region)",
-                       "l2": "per-step working set (saved gate activations ~1.3 GB at B=80) exceeds the 126 MB L2; no flush needed",
-                       "last_loss": last},
-            "e2e": {"value": B * T * world / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "metric": METRIC_DECODE if decode else METRIC, "value": B * T * world / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": B * T * world / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": avg_ms, "launches_timed": n_l,
-                         "algorithmic_flops_per_launch": fl, "peak_source": peak_src,
+            "roofline": {"bound": "tensor", "kernel": dom + ("_tc_eval" if decode else "_tc"), "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                         "avg_launch_ms": avg_ms, "launches_timed": n_l, "algorithmic_flops_per_launch": fl, "peak_source": peak_src,
                          "share_of_step": {k: v[0] / args.steps / ms for k, v in prof.items()},
-                         "us_per_recurrent_step": avg_ms * 1e3 / T,
-                         "note": "split-precision tcgen05 recurrence (fp16/bf16 hi+lo operands, 2 MMAs per K step, fp32 TMEM "
-                                 "accumulation); `achieved` counts ALGORITHMIC fp32-equivalent FLOPs (the issued 16-bit MMA FLOPs are "
-                                 "3x) against the dense bf16 peak; the kernel is bound by the two grid-wide exchanges of every "
-                                 "recurrent step (us_per_recurrent_step), not by the tensor pipe"},
+                         "us_per_recurrent_step": avg_ms * 1e3 / T, "rows_per_launch": rows, "note": note},
         }
+        if roof_fe:
+            res["roofline_frontend"] = roof_fe
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            Bc = args.ref_batch_utt
-            cstep = cpu_reference_step_factory(enc.state_dict(), dec.state_dict(), Bc)
-            sec, cores = time_cpu(cstep, 3, 1)
-            res["cpu_baseline"] = {"value": Bc * T / sec, "unit": "frames/s", "cores": cores, "kind": "port",
-                                   "sample": f"{Bc} utterances x {T} frames per step, median of 3 steps after 1 warm-up "
-                                             f"({sec:.2f} s/step); oracle/gru_vae_oracle.py on the host CPU"}
+            if decode:
+                n = 4
+                cstep, kind = cpu_decode_step_factory(n)
+                sec, cores = time_cpu(cstep, 2, 1)
+                val, what = n * DEC_T / sec, f"{n} of the {B} utterances x {DEC_T} frames, one utterance per call as the reference decodes"
+            else:
+                cstep, kind = cpu_train_step_factory(B, args.n_spk)
+                sec, cores = time_cpu(cstep, 2, 1)
+                val, what = B * T / sec, f"the same step: {B} utterances x {T} frames"
+            res["cpu_baseline"] = {"value": val, "unit": "frames/s", "cores": cores, "kind": kind,
+                                   "sample": f"{what}; median of 2 steps after 1 warm-up ({sec:.2f} s/step); "
+                                             + ("unmodified reference gru_vae.py (oracle/_ref)" if kind == "reference" else "oracle/gru_vae_oracle.py")
+                                             + " on the host CPU"}
         print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()

@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcyclevae_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -65,6 +65,8 @@ PROTOTYPES = {
     "cvb_mcd_l1_bwd": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cvb_dropout_mask": (_i, [_sz, _f, _u64, _u64, _vp, _vp]),
     "cvb_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp]),
+    "cvb_weights_changed": (_i, []),
+    "cvb_reserve_workspace": (_i, [_sz]),
     "cvb_profile_enable": (_i, [_i]),
     "cvb_profile_reset": (_i, []),
     "cvb_profile_summary": (_i, [_i, C.POINTER(C.c_float), C.POINTER(_i)]),

@@ -40,7 +40,7 @@ static RecLayout rec_layout(const cvb_net* net, int B, int T, bool training, boo
 }
 
 struct FwdScratch {
-    size_t gx, part, bar, tc, total;
+    size_t gx, part, bar, tc, tc_floats, total;
 };
 static FwdScratch fwd_scratch(const cvb_net* net, int B, int T) {
     FwdScratch S;
@@ -50,11 +50,12 @@ static FwdScratch fwd_scratch(const cvb_net* net, int B, int T) {
     S.part = off; off += r4((size_t)gru_exact_grid(net->hidden) * B * out);
     S.bar = off; off += 16;
     S.tc = off;
-    if (gru_tc_shape_ok(B, net->hidden, net->out_dim)) {
-        size_t a = gru_tc_scratch_floats(B, net->hidden);
-        size_t e = gru_tc_eval_scratch_floats(B, net->hidden) + r4((size_t)6 * H);   // folded inference path: W_fb | hx | ctr | c_fb | b_ih + c_fb
-        off += r4(a > e ? a : e);
-    }
+    // sized by the same shape predicates that pick the kernel: the two-exchange kernel needs out <= 64, the folded
+    // inference kernel holds any out_dim (e.g. the encoder at lat_dim 50 / 64, egs/one-to-one/run.sh)
+    size_t a = gru_tc_shape_ok(B, net->hidden, net->out_dim) ? gru_tc_scratch_floats(B, net->hidden) : 0;
+    size_t e = gru_tc_eval_shape_ok(B, net->hidden) ? gru_tc_eval_scratch_floats(B, net->hidden) + r4((size_t)6 * H) : 0;   // W_fb | hx | ctr | c_fb | b_ih + c_fb
+    S.tc_floats = r4(a > e ? a : e);
+    off += S.tc_floats;
     S.total = off;
     return S;
 }
@@ -197,7 +198,7 @@ int cvb_recurrence_max_rows(const cvb_net* net, int mode) {
     if (!net || !want_tc()) return 128;
     DeviceInfo di;
     if (get_device_info(&di)) return 128;
-    static int cache_key[12], cache_val[12], n_cache = 0;
+    static int cache_key[64], cache_val[64], n_cache = 0;
     const bool fold = mode == 0 && want_fold();
     const int key = (net->hidden * 131 + net->out_dim) * 4 + (fold ? 3 : mode == 1 ? 1 : 0);
     for (int i = 0; i < n_cache; ++i)
@@ -213,7 +214,7 @@ int cvb_recurrence_max_rows(const cvb_net* net, int mode) {
         }
         if (B == 8) best = 128;
     }
-    if (n_cache < 12) {
+    if (n_cache < 64) {
         cache_key[n_cache] = key;
         cache_val[n_cache++] = best;
     }
@@ -235,7 +236,9 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     RecLayout RL = rec_layout(net, B, T, training != 0, mask_gru_tm != nullptr);
     FwdScratch FS = fwd_scratch(net, B, T);
     float* xc = fe_ws + frontend_xc_offset(net, B, T);
+    prof_begin(s, CVB_PROF_FRONTEND);
     if (int rc = frontend_fwd(net, B, T, x_bm, mask_conv_tm, fe_ws, xc, s)) return rc;
+    prof_end(s, CVB_PROF_FRONTEND);
     float* gx = scratch + FS.gx;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
@@ -252,12 +255,17 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
     float* cfb = esc + gru_tc_eval_scratch_floats(B, H);   // c_fb | b_ih + c_fb
     const float* gx_bias = net->b_ih;
     if (fold) {
+        CVB_REQUIRE(gru_tc_eval_scratch_floats(B, H) + r4((size_t)6 * H) <= FS.tc_floats,
+                    "internal: scratch of the folded inference path not reserved (B=%d H=%d out=%d)", B, H, out);
         if (int rc = gru_tc_eval_prepare(a, net->b_ih, esc, cfb, s)) return rc;
         gx_bias = cfb + 3 * H;
     }
     if (want_tc_gemm() && gemm_tc_eligible((int)TB, 3 * H, C)) {
         // gx = xc W_x^T + b_ih: bias in the GEMM epilogue (no fill pass, no read-modify-write of the 3H-wide rows)
-        if (int rc = gemm_tc(s, false, true, (int)TB, 3 * H, C, xc, C, net->w_ih, TI, false, gx_bias, gx, 3 * H, true)) return rc;
+        GemmDesc g;
+        g.transB = true; g.M = (int)TB; g.N = 3 * H; g.K = C;
+        g.A = xc; g.lda = C; g.B = net->w_ih; g.ldb = TI; g.b_const = true; g.bias = gx_bias; g.C = gx; g.ldc = 3 * H;
+        if (int rc = gemm_tc_group(s, &g, 1)) return rc;
     } else {
         if (int rc = fill_rows(s, gx, TB, 3 * H, 3 * H, gx_bias)) return rc;
         if (int rc = gemm_rm(s, false, true, (int)TB, 3 * H, C, 1.f, xc, C, net->w_ih, TI, 1.f, gx, 3 * H)) return rc;
@@ -288,6 +296,7 @@ int cvb_gru_rnn_forward(const cvb_net* net, int B, int T, const float* x_bm, con
         if (int rc = gru_ar_fwd_tc_eval(a, esc, cfb, s)) return rc;
         g_last_path[0] = CVB_PATH_TC_FOLDED;
     } else if (want_tc() && gru_tc_supported(B, H, out, di)) {
+        CVB_REQUIRE(gru_tc_scratch_floats(B, H) <= FS.tc_floats, "internal: scratch of the tensor-core recurrence not reserved");
         if (int rc = gru_ar_fwd_tc(a, scratch + FS.tc, s)) return rc;
         g_last_path[0] = CVB_PATH_TC;
     } else {
@@ -384,31 +393,66 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
     const float beta = (gr && gr->accumulate) ? 1.f : 0.f;
     const bool acc = gr && gr->accumulate;
     const float* xc = fe_ws + frontend_xc_offset(net, B, T);
+    bool fe_needed = dx_bm != nullptr;
     if (gr) {
-        if (gr->w_hh) {
+        for (int i = 0; i < net->n_conv; ++i) fe_needed = fe_needed || gr->conv_w[i] || gr->conv_b[i];
+        fe_needed = fe_needed || gr->scale_in_w || gr->scale_in_b;
+    }
+    float* dxc = scratch + BS.dxc;
+    const float* o_tm = mask_gru_tm ? rec_ws + RL.o : hs + (size_t)B * H;
+    const float* dy1 = dy_tot + (size_t)B * out;
+    if (want_tc_gemm() && gemm_tc_eligible(3 * H, H, iTB)) {
+        // every product that only needs the recurrence's outputs, in ONE persistent launch (long-K tiles first):
+        //   dW_hh = [dgi_r; dgi_z; dan*r]^T hs      dW_ih = dgi^T [xc | y_prev]      dW_o = dy^T o      dxc = dgi W_x
+        GemmDesc d[5];
+        int n = 0;
+        if (gr && gr->w_hh) {   // rows r, z from dgi (the operand image is shared with dW_ih below), rows n from dan*r
+            GemmDesc& g = d[n++];
+            g.transA = true; g.M = 2 * H; g.N = H; g.K = iTB;
+            g.A = dgi; g.lda = 3 * H; g.B = hs; g.ldb = H; g.C = gr->w_hh; g.ldc = H; g.beta1 = acc; g.f16 = false;
+            GemmDesc& g2 = d[n++];
+            g2.transA = true; g2.M = H; g2.N = H; g2.K = iTB;
+            g2.A = dghn; g2.lda = H; g2.B = hs; g2.ldb = H; g2.C = gr->w_hh + (size_t)2 * H * H; g2.ldc = H; g2.beta1 = acc; g2.f16 = false;
+        }
+        if (gr && gr->w_ih) {
+            GemmDesc& g = d[n++];
+            g.transA = true; g.M = 3 * H; g.N = TI; g.K = iTB;
+            g.A = dgi; g.lda = 3 * H; g.B = xc; g.ldb = C; g.B2 = ys; g.ldb2 = out; g.N1 = C;
+            g.C = gr->w_ih; g.ldc = TI; g.beta1 = acc; g.f16 = false;
+        }
+        if (gr && gr->out_w) {
+            GemmDesc& g = d[n++];
+            g.transA = true; g.M = out; g.N = H; g.K = iTB;
+            g.A = dy1; g.lda = out; g.B = o_tm; g.ldb = H; g.C = gr->out_w; g.ldc = H; g.beta1 = acc; g.f16 = false;
+        }
+        if (fe_needed) {
+            GemmDesc& g = d[n++];
+            g.M = iTB; g.N = C; g.K = 3 * H;
+            g.A = dgi; g.lda = 3 * H; g.B = net->w_ih; g.ldb = TI; g.b_const = true; g.C = dxc; g.ldc = C; g.f16 = false;
+        }
+        if (n)
+            if (int rc = gemm_tc_group(s, d, n)) return rc;
+    } else {
+        if (gr && gr->w_hh) {
             if (int rc = gemm_rm(s, true, false, 2 * H, H, iTB, 1.f, dgi, 3 * H, hs, H, beta, gr->w_hh, H, true)) return rc;
             if (int rc = gemm_rm(s, true, false, H, H, iTB, 1.f, dghn, H, hs, H, beta, gr->w_hh + (size_t)2 * H * H, H, true)) return rc;
         }
+        if (gr && gr->w_ih) {
+            if (int rc = gemm_rm(s, true, false, 3 * H, C, iTB, 1.f, dgi, 3 * H, xc, C, beta, gr->w_ih, TI, true)) return rc;
+            if (int rc = gemm_rm(s, true, false, 3 * H, out, iTB, 1.f, dgi, 3 * H, ys, out, beta, gr->w_ih + C, TI, true)) return rc;
+        }
+        if (gr && gr->out_w)
+            if (int rc = gemm_rm(s, true, false, out, H, iTB, 1.f, dy1, out, o_tm, H, beta, gr->out_w, H, true)) return rc;
+        if (fe_needed)
+            if (int rc = gemm_rm(s, false, false, iTB, C, 3 * H, 1.f, dgi, 3 * H, net->w_ih, TI, 0.f, dxc, C, true)) return rc;
+    }
+    if (gr) {
         if (gr->b_hh && !db_in_kernel) {
             if (int rc = colsum(s, dgi, iTB, 2 * H, 3 * H, gr->b_hh, acc)) return rc;
             if (int rc = colsum(s, dghn, iTB, H, H, gr->b_hh + 2 * H, acc)) return rc;
         }
-        if (gr->w_ih) {
-            if (want_tc_gemm() && gemm_tc_eligible(3 * H, TI, iTB)) {
-                // dW_ih = dgi^T [xc | y_prev]: one product, the two sources meet in the operand pass
-                if (int rc = gemm_tc(s, true, false, 3 * H, TI, iTB, dgi, 3 * H, xc, C, beta == 1.f, nullptr, gr->w_ih, TI, false, ys, out, C))
-                    return rc;
-            } else {
-                if (int rc = gemm_rm(s, true, false, 3 * H, C, iTB, 1.f, dgi, 3 * H, xc, C, beta, gr->w_ih, TI, true)) return rc;
-                if (int rc = gemm_rm(s, true, false, 3 * H, out, iTB, 1.f, dgi, 3 * H, ys, out, beta, gr->w_ih + C, TI, true)) return rc;
-            }
-        }
         if (gr->b_ih && !db_in_kernel)
             if (int rc = colsum(s, dgi, iTB, 3 * H, 3 * H, gr->b_ih, acc)) return rc;
-        const float* o_tm = mask_gru_tm ? rec_ws + RL.o : hs + (size_t)B * H;
-        const float* dy1 = dy_tot + (size_t)B * out;
-        if (gr->out_w)
-            if (int rc = gemm_rm(s, true, false, out, H, iTB, 1.f, dy1, out, o_tm, H, beta, gr->out_w, H, true)) return rc;
         if (gr->out_b)
             if (int rc = colsum(s, dy1, iTB, out, out, gr->out_b, acc)) return rc;
         if (want_so) {
@@ -420,16 +464,8 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm, co
                 if (int rc = colsum(s, dtrj_tm, iTB, out, out, gr->scale_out_b, acc)) return rc;
         }
     }
-    bool fe_needed = dx_bm != nullptr;
-    if (gr) {
-        for (int i = 0; i < net->n_conv; ++i) fe_needed = fe_needed || gr->conv_w[i] || gr->conv_b[i];
-        fe_needed = fe_needed || gr->scale_in_w || gr->scale_in_b;
-    }
-    if (fe_needed) {
-        float* dxc = scratch + BS.dxc;
-        if (int rc = gemm_rm(s, false, false, iTB, C, 3 * H, 1.f, dgi, 3 * H, net->w_ih, TI, 0.f, dxc, C, true)) return rc;
+    if (fe_needed)
         if (int rc = frontend_bwd(net, B, T, x_bm, mask_conv_tm, fe_ws, dxc, scratch + BS.fe, dx_bm, gr, s)) return rc;
-    }
     return 0;
 }
 }

@@ -76,6 +76,32 @@ struct ConvGather {
 int gemm_tc(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
             bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2 = nullptr, int ldb2 = 0, int N1 = 0,
             const ConvGather* gA = nullptr, const ConvGather* gB = nullptr);
+// one product of a grouped launch: C[M,N] = alpha op(A) op(B) (+ C if beta1) (+ bias[N]); same operand conventions as gemm_tc
+struct GemmDesc {
+    bool transA = false, transB = false;
+    int M = 0, N = 0, K = 0;
+    const float* A = nullptr;
+    int lda = 0;
+    const float* B = nullptr;
+    int ldb = 0;
+    const float* A2 = nullptr;   // A stored [K,M] (transA): columns >= M1 come from A2 (lda2)
+    int lda2 = 0, M1 = 0;
+    const float* B2 = nullptr;   // B stored [K,N]: columns >= N1 come from B2 (ldb2)
+    int ldb2 = 0, N1 = 0;
+    const ConvGather* gA = nullptr;
+    const ConvGather* gB = nullptr;
+    float* C = nullptr;
+    int ldc = 0;
+    const float* bias = nullptr;
+    float alpha = 1.f;
+    bool beta1 = false;
+    bool a_const = false, b_const = false;   // the operand is a PARAMETER: its 16-bit image is kept until weights_changed()
+    bool f16 = true;             // fp16 hi/lo operands (forward products) or bf16 hi/lo (gradient products)
+};
+// up to 6 independent products in ONE persistent launch (their tiles are walked back to back; list long-K products first)
+int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n);
+void weights_changed();                 // invalidates the cached images of parameter operands
+int reserve_workspace(size_t bytes);    // pre-sizes the operand-image arena of the current device
 
 // elementwise / small kernels, elementwise.cu
 int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out, bool accumulate);

@@ -369,6 +369,13 @@ int cvb_adam_step(size_t n, float* param, const float* grad, float* exp_avg, flo
     k_adam<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, bc1,
                                                                sqrtf(bc2), grad_scale);
     CVB_LAUNCH_CHECK();
+    cvb::weights_changed();   // cached 16-bit images of parameter operands (gemm_tc.cu) are stale from here on
     return 0;
 }
+
+int cvb_weights_changed(void) {
+    cvb::weights_changed();
+    return 0;
+}
+int cvb_reserve_workspace(size_t bytes) { return cvb::reserve_workspace(bytes); }
 }

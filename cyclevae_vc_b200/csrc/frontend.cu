@@ -173,7 +173,7 @@ __global__ void k_col2im_add(size_t R, size_t rows, size_t m, int ci, int k, int
 
 // the k taps of a layer as ONE tensor-core product over the virtual im2col (K = k*ci) when that is the faster path
 static bool conv_fused(size_t rows, int co, int ci, int k) {
-    return want_tc_gemm() && rows >= 128 && co >= 128 && (double)rows * co * ci * k >= 5.0e8;
+    return want_tc_gemm() && gemm_tc_eligible((int)rows, co, ci * k);
 }
 
 // xc_tm[t,b,c] = xcp[b,pad+t,c] * mask_tm[t,b,c]

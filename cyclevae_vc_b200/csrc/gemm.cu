@@ -31,7 +31,7 @@ struct ProfRec {
 };
 static int g_prof_level = 0;
 static std::vector<ProfRec> g_prof;
-static std::vector<cudaEvent_t> g_prof_open[3];
+static std::vector<cudaEvent_t> g_prof_open[4];
 void prof_begin(cudaStream_t s, int kind) {
     if (g_prof_level <= 0 || (kind == CVB_PROF_GEMM && g_prof_level < 2)) return;
     cudaEvent_t e;
@@ -74,11 +74,23 @@ bool want_tc_gemm() {
 int gemm_rm(cudaStream_t s, bool transA, bool transB, int M, int N, int K, float alpha,
             const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc, bool grad) {
     if (M <= 0 || N <= 0) return 0;
-    if (alpha == 1.f && (beta == 0.f || beta == 1.f) && gemm_tc_eligible(M, N, K) && want_tc_gemm()) {
-        prof_begin(s, CVB_PROF_GEMM);
-        int rc = gemm_tc(s, transA, transB, M, N, K, A, lda, B, ldb, beta == 1.f, nullptr, C, ldc, !grad);
-        prof_end(s, CVB_PROF_GEMM);
-        return rc;
+    if ((beta == 0.f || beta == 1.f) && gemm_tc_eligible(M, N, K) && want_tc_gemm()) {
+        GemmDesc d;
+        d.transA = transA;
+        d.transB = transB;
+        d.M = M;
+        d.N = N;
+        d.K = K;
+        d.A = A;
+        d.lda = lda;
+        d.B = B;
+        d.ldb = ldb;
+        d.C = C;
+        d.ldc = ldc;
+        d.alpha = alpha;
+        d.beta1 = beta == 1.f;
+        d.f16 = !grad;
+        return gemm_tc_group(s, &d, 1);
     }
     cublasHandle_t h;
     if (int rc = get_handle(&h)) return rc;

@@ -1,19 +1,33 @@
-// Split-precision tensor-core GEMM for the throughput-bound dense products of the path (gx = xc W_x^T,
-// conv taps, deferred weight gradients of BPTT, dxc = dgi W_x):  C[M,N] (+)= op(A) op(B) (+ bias), fp32 in/out.
+// Split-precision tensor-core GEMM for the throughput-bound dense products of the path (gx = xc W_x^T, conv taps,
+// deferred weight gradients of BPTT, dxc = dgi W_x, y = H W_o^T ...):  C[M,N] (+)= alpha op(A) op(B) (+ bias), fp32 in/out.
 //
-// fp32 parity on tensor cores: every operand element is split x = hi + lo into two
-// 16-bit floats (fp16 for the forward products: 2 x 11 mantissa bits; bf16 for gradients: fp32's exponent
-// range), and C = A_hi B_hi + A_lo B_hi + A_hi B_lo with fp32 accumulation in TMEM.
+// fp32 parity on tensor cores: every operand element is split x = hi + lo into two 16-bit
+// floats (fp16 for the forward products: 2 x 11 mantissa bits, lo stored scaled by 2^11; bf16 for gradients: fp32's
+// exponent range) and C = A_hi B_hi + (A_hi B_lo + A_lo B_hi) with fp32 accumulation in TMEM.
 //
-//   1. k_split_tiles (one pass per operand, HBM-bound): fp32 row-major (optionally transposed) -> 16-bit hi/lo
-//      in "tile order": blocks of 128 rows x 64 k, each block already in the UMMA K-major core-matrix layout
-//      [16 row groups][8 k blocks][8 rows][8 k] with the hi block followed by the lo block.  A (block, part)
-//      is contiguous, so the GEMM needs no tensor maps: one cp.async.bulk per operand per stage.
-//   2. k_gemm_tc (persistent, warp-specialised): w0 bulk-copy producer (3-stage ring, 64 KB per stage),
-//      w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.  B's [hi | lo] blocks are adjacent in shared memory,
-//      so ONE tcgen05.mma with N = 256 forms A_hi B_hi (columns 0..127) and A_hi B_lo (columns 128..255) and a
-//      second with N = 128 adds A_lo B_hi: 2 MMAs per K step instead of 3.  Two 256-column accumulators
-//      alternate so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   1. k_split_group (HBM-bound, ONE launch for every operand of a group of products): fp32 operand (row-major,
+//      transposed, two sources side by side, or the virtual im2col of a dilated conv) -> 16-bit hi/lo "image" in tile
+//      order: blocks of 128 rows x 64 k, each already in the UMMA K-major core-matrix layout
+//      [16 row groups][8 k groups][8 rows][8 k], hi plane then lo plane.  No shared memory: a thread reads 8 consecutive k
+//      of one row (vector loads; for transposed sources the lanes run along the rows, so every load is one full line)
+//      and writes one 16-byte core-matrix row per plane.  Operands that appear more than once in a group are split once
+//      (dgi^T feeds both dW_hh and dW_ih); parameter operands keep their image until the parameters change
+//      (cvb_weights_changed / cvb_adam_step), so W_x is split once per optimiser step, not once per pass.
+//   2. k_gemm_tc (persistent, warp-specialised, up to 6 products per launch): w0 bulk-copy producer (3-stage ring, 64 KB
+//      per stage: one cp.async.bulk per operand block), w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.  B's [hi | lo]
+//      planes are adjacent in shared memory, so ONE tcgen05.mma with N = 256 forms A_hi B_hi (columns 0..127) and
+//      A_hi B_lo (columns 128..255) and a second with N = 128 adds A_lo B_hi onto the correction columns.  Two 256-column
+//      accumulators alternate; an accumulator only ever sums K = 128 (a tcgen05 accumulation chain truncates toward zero:
+//      the error of a 6400-deep chain was measured at 9e-5 relative) -- the epilogue warps add the slices in fp32
+//      registers with round-to-nearest while the other accumulator fills.
+// Measured and rejected (round 2): splitting inside the GEMM's loader warps (fp32 -> registers -> hi/lo planes in the
+// ring).  Correct, but registers cannot hold enough bytes in flight: 256 loader threads x 128 B against ~1500 cycles of
+// loaded L2/HBM latency feed 22 B/clk per SM where the tile needs 42; 5800 cycles per stage against 1560 for bulk copies
+// of pre-split images (gx 358 us vs 150 us).  The operand pass stays, but as one fused, deduplicated, cached launch.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -23,90 +37,215 @@ namespace cvb {
 using namespace umma;
 
 constexpr int GT_BM = 128, GT_BN = 128, GT_BK = 64;
-constexpr int GT_BLOCK_ELEMS = GT_BM * GT_BK;          // one part of one block
-constexpr int GT_STAGE_BYTES = 4 * GT_BLOCK_ELEMS * 2;  // A hi, A lo, B hi, B lo
+constexpr int GT_PLANE_BYTES = GT_BM * GT_BK * 2;        // one 16-bit plane of one operand block
+constexpr int GT_BLOCK_BYTES = 2 * GT_PLANE_BYTES;        // hi + lo
+constexpr int GT_STAGE_BYTES = 2 * GT_BLOCK_BYTES;        // A block, B block
 constexpr int GT_NS = 3;
 constexpr int GT_KD = 2;   // chunks (of 64) accumulated inside the tensor core before the slice is added in fp32 registers
 constexpr int GT_THREADS = 256;
+constexpr int GT_MAXP = 6;                                // products per launch
+constexpr int GT_MAXO = 2 * GT_MAXP;                      // operands per split launch
 
-// ---- operand preparation ---------------------------------------------------------------------------------
-// X: row-major [R, K] with leading dimension ld (transposed = false) or [K, R] (transposed = true).
-// out: [ceil(R/128)][ceil(K/64)][2 parts][16][8][8][8] 16-bit.
-template <bool F16>
-__global__ void __launch_bounds__(256) k_split_tiles(const float* __restrict__ X, int ld, int R, int K, int transposed, int KC,
-                                                     uint16_t* __restrict__ out, const float* __restrict__ X2, int ld2, int R1,
-                                                     int conv_ci, int conv_dshift) {
-    // transposed sources may be two matrices side by side: rows [0, R1) from X, rows [R1, R) from X2 (e.g. [xc | y] for dW_ih).
-    // conv_ci > 0: the operand is the virtual im2col of a dilated conv on the flattened padded grid (frontend.cu): logical
-    // element (row r, column kk = tap*ci + c) lives at X[(r + tap*conv_dshift)*ci + c]; `transposed` then only says which of
-    // (r, kk) is the tile's row index.
-    __shared__ float T[GT_BM * (GT_BK + 1)];
-    const int rt = blockIdx.y, kc = blockIdx.x;
-    const int r0 = rt * GT_BM, k0 = kc * GT_BK;
-    if (!transposed) {
-        for (int i = threadIdx.x; i < GT_BM * GT_BK; i += 256) {
-            const int r = i >> 6, k = i & 63;
-            const bool ok = (r0 + r < R) && (k0 + k < K);
-            float v = 0.f;
-            if (ok) {
-                if (conv_ci > 0) {
-                    const int kk = k0 + k, tap = kk / conv_ci, cch = kk - tap * conv_ci;
-                    v = X[((size_t)(r0 + r) + (size_t)tap * conv_dshift) * conv_ci + cch];
-                } else {
-                    v = X[(size_t)(r0 + r) * ld + k0 + k];
-                }
-            }
-            T[r * (GT_BK + 1) + k] = v;
-        }
-    } else {
-        for (int i = threadIdx.x; i < GT_BM * GT_BK; i += 256) {
-            const int k = i >> 7, r = i & 127;
-            const bool ok = (r0 + r < R) && (k0 + k < K);
-            float v = 0.f;
-            if (ok) {
-                if (conv_ci > 0) {   // tile row = kk (tap, channel), tile k = grid row
-                    const int kk = r0 + r, tap = kk / conv_ci, cch = kk - tap * conv_ci;
-                    v = X[((size_t)(k0 + k) + (size_t)tap * conv_dshift) * conv_ci + cch];
-                } else {
-                    v = (r0 + r < R1) ? X[(size_t)(k0 + k) * ld + r0 + r] : X2[(size_t)(k0 + k) * ld2 + (r0 + r - R1)];
-                }
-            }
-            T[r * (GT_BK + 1) + k] = v;
-        }
-    }
-    __syncthreads();
-    uint16_t* blk = out + ((size_t)rt * KC + kc) * (2 * GT_BLOCK_ELEMS);
-    for (int p = threadIdx.x; p < GT_BLOCK_ELEMS / 8; p += 256) {
-        // 16-byte piece p of the block: row group p/64, k block (p/8)%8, row p%8
-        const int r = (p >> 6) * 8 + (p & 7), kb = (p >> 3) & 7;
-        const float* src = T + r * (GT_BK + 1) + kb * 8;
-        uint16_t h[8], l[8];
+// one fp32 operand seen as [rows, K], and where its 16-bit image goes
+struct GtOperand {
+    const float* p;
+    const float* p2;   // rows >= R1 come from p2 (row index - R1), only for kmajor == 0
+    uint16_t* img;     // [ceil(rows/128)][KC][hi plane | lo plane]
+    int ld, ld2, R1;
+    int rows, K, KC;
+    int kmajor;        // 1: element (r, k) at p[r*ld + k];  0: at p[k*ld + r]
+    int conv_ci;       // > 0: virtual im2col of a dilated conv on the flattened padded grid (frontend.cu):
+    int conv_ds;       //      kmajor: (r, kk = tap*ci + c) at p[(r + tap*ds)*ci + c];  !kmajor: (r = kk, k) at p[(k + tap*ds)*ci + c]
+    int vec;           // widest aligned vector load of 8 consecutive k (kmajor, no conv): 4, 2 or 1 floats
+    int f16;
+    int block_end;     // running block count of the split launch up to and including this operand
+};
+struct SplitArgs {
+    GtOperand o[GT_MAXO];
+    int n;
+};
+
+// ---- operand pass ----------------------------------------------------------------------------------------------
+// 256 threads per 128 x 64 block, 4 "items" (8 consecutive k of one row) per thread:
+//   K contiguous in memory (kmajor): 8 lanes = the 8 rows of one core matrix (conflict-free / coalesced 16-byte stores,
+//     32-byte global segments): row = (lt >> 6) * 8 + (lt & 7) + 16 * it, k group = (lt >> 3) & 7
+//   rows contiguous (!kmajor): lanes = consecutive rows (every load of a warp is one 128-byte line): row = lt, k group = it
+// with lt = thread & 127 and it = 4 * (thread >> 7) + i.
+static __device__ __forceinline__ void gt_zero8(float* v) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+}
+
+// generic element fetch of the conv-gather operands (virtual im2col; small products only)
+static __device__ __forceinline__ void gt_load8_conv(const GtOperand& o, int r, int k0, float* v) {
+    gt_zero8(v);
+    if (r >= o.rows || k0 >= o.K) return;
+    if (o.kmajor) {
+        int tap = k0 / o.conv_ci, c = k0 - tap * o.conv_ci;
+        const float* base = o.p + ((size_t)r + (size_t)tap * o.conv_ds) * o.conv_ci;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            if (F16) split_f16(src[q], h[q], l[q]);
-            else split_bf16(src[q], h[q], l[q]);
+            if (k0 + q < o.K) v[q] = __ldg(base + c);
+            if (++c == o.conv_ci) {
+                c = 0;
+                base += (size_t)o.conv_ds * o.conv_ci;
+            }
         }
-        const uint4 hv = make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
-                                    (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
-        const uint4 lv = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
-                                    (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
-        reinterpret_cast<uint4*>(blk)[p] = hv;
-        reinterpret_cast<uint4*>(blk + GT_BLOCK_ELEMS)[p] = lv;
+    } else {
+        const int tap = r / o.conv_ci, c = r - tap * o.conv_ci;
+        const float* base = o.p + ((size_t)k0 + (size_t)tap * o.conv_ds) * o.conv_ci + c;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (k0 + q < o.K) v[q] = __ldg(base + (size_t)q * o.conv_ci);
+    }
+}
+
+// v[0..8) -> one 16-byte core-matrix row of the hi plane and one of the lo plane
+template <bool F16>
+static __device__ __forceinline__ void gt_split_store(const float* v, uint8_t* hi_dst) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (F16) {
+            const float a = fminf(fmaxf(v[2 * q], -60000.f), 60000.f), b = fminf(fmaxf(v[2 * q + 1], -60000.f), 60000.f);
+            const __half2 hh = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn((a - hf.x) * F16_LO_SCALE, (b - hf.y) * F16_LO_SCALE);
+            h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+        } else {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+            const float r0 = v[2 * q] - __uint_as_float(hb << 16), r1 = v[2 * q + 1] - __uint_as_float(hb & 0xffff0000u);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+            h[q] = hb;
+            l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+    }
+    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(hi_dst + GT_PLANE_BYTES) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(256) k_split_group(const __grid_constant__ SplitArgs a) {
+    int oi = 0;
+    while ((int)blockIdx.x >= a.o[oi].block_end) ++oi;
+    const GtOperand& o = a.o[oi];
+    const int local = (int)blockIdx.x - (oi ? a.o[oi - 1].block_end : 0);
+    const int rt = local / o.KC, kc = local - rt * o.KC;
+    const int lt = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int r0 = rt * GT_BM, k0 = kc * GT_BK;
+    float v[32];
+    bool kmajor = o.kmajor != 0;
+    if (o.conv_ci > 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int it = half * 4 + i;
+            const int r = kmajor ? (lt >> 6) * 8 + (lt & 7) + 16 * it : lt;
+            const int kg = kmajor ? (lt >> 3) & 7 : it;
+            gt_load8_conv(o, r0 + r, k0 + kg * 8, v + 8 * i);
+        }
+    } else if (kmajor) {
+        const int rb = (lt >> 6) * 8 + (lt & 7), kg = (lt >> 3) & 7;
+        const int kleft = o.K - k0 - kg * 8;
+        const float* p = o.p + (size_t)(r0 + rb) * o.ld + k0 + kg * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float* d = v + 8 * i;
+            const int it = half * 4 + i;
+            const float* src = p + (size_t)it * 16 * o.ld;
+            const bool row_ok = r0 + rb + 16 * it < o.rows;
+            if (row_ok && kleft >= 8 && o.vec == 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(src)), y = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w; d[4] = y.x; d[5] = y.y; d[6] = y.z; d[7] = y.w;
+            } else if (row_ok && kleft >= 8 && o.vec == 2) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 x = __ldg(reinterpret_cast<const float2*>(src) + q);
+                    d[2 * q] = x.x;
+                    d[2 * q + 1] = x.y;
+                }
+            } else {
+                gt_zero8(d);
+                if (row_ok) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < kleft) d[q] = __ldg(src + q);
+                }
+            }
+        }
+    } else {
+        const int r = r0 + lt;
+        const bool row_ok = r < o.rows;
+        const bool second = r >= o.R1;
+        const int ld = second ? o.ld2 : o.ld;
+        const float* p = (second ? o.p2 + (r - o.R1) : o.p + r) + (size_t)k0 * ld;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float* d = v + 8 * i;
+            const int it = half * 4 + i;
+            const int kl = o.K - k0 - it * 8;   // warp-uniform
+            const float* src = p + (size_t)it * 8 * ld;
+            if (row_ok && kl >= 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[q] = __ldg(src + (size_t)q * ld);
+            } else {
+                gt_zero8(d);
+                if (row_ok) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < kl) d[q] = __ldg(src + (size_t)q * ld);
+                }
+            }
+        }
+    }
+    // kmajor: item it -> row group 2*it + (lt >> 6), k group (lt >> 3) & 7, row lt & 7;  !kmajor: row lt, k group it
+    uint8_t* blk = reinterpret_cast<uint8_t*>(o.img) + ((size_t)rt * o.KC + kc) * GT_BLOCK_BYTES;
+    uint8_t* d = kmajor ? blk + ((half * 8 + (lt >> 6)) * 1024 + ((lt >> 3) & 7) * 128 + (lt & 7) * 16)
+                        : blk + ((lt >> 3) * 1024 + half * 4 * 128 + (lt & 7) * 16);
+    const int step = kmajor ? 2048 : 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (o.f16) gt_split_store<true>(v + 8 * i, d + i * step);
+        else gt_split_store<false>(v + 8 * i, d + i * step);
     }
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------------------------
-struct GemmTcArgs {
+struct GtProblem {
     const uint16_t* At;
     const uint16_t* Bt;
     float* C;
     const float* bias;
-    int M, N, ldc, MT, NTl, KC;
-    int beta1;
-    int f16;
+    float alpha;
+    int M, N, ldc, MT, NT, KC;
+    int beta1, f16;
+    int tile_end;      // running tile count up to and including this product
+};
+struct GemmTcArgs {
+    GtProblem p[GT_MAXP];
+    int n_prob;
 };
 
-__global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
+// walk of the tile sequence of one persistent CTA, shared by the three roles.  The CTAs take the tile list in
+// boustrophedon order (wave w of gridDim tiles forwards, wave w+1 backwards): with the long-K products listed first the
+// CTAs that got an extra long tile are the last to be handed a short one.
+struct GtWalk {
+    int wave, tile, prob, mt, nt;
+    __device__ __forceinline__ void start() { wave = -1; }
+    __device__ __forceinline__ bool next(const GemmTcArgs& g) {
+        ++wave;
+        tile = wave * (int)gridDim.x + ((wave & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
+        if (tile >= g.p[g.n_prob - 1].tile_end) return false;
+        prob = 0;
+        while (tile >= g.p[prob].tile_end) ++prob;
+        const int local = tile - (prob ? g.p[prob - 1].tile_end : 0);
+        nt = local / g.p[prob].MT;
+        mt = local - nt * g.p[prob].MT;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant__ GemmTcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_NS * GT_STAGE_BYTES);
     uint64_t* empty = full + GT_NS;
@@ -115,7 +254,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const int n_tiles = g.MT * g.NTl;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GT_NS; ++s) {
@@ -138,17 +276,18 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
         // ================= producer =====================================================================
         int s = 0;
         uint32_t ph = 1;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int nt = tile / g.MT, mt = tile - nt * g.MT;
-            const uint16_t* a_src = g.At + (size_t)mt * g.KC * (2 * GT_BLOCK_ELEMS);
-            const uint16_t* b_src = g.Bt + (size_t)nt * g.KC * (2 * GT_BLOCK_ELEMS);
-            for (int kc = 0; kc < g.KC; ++kc) {
+        GtWalk w;
+        for (w.start(); w.next(g);) {
+            const GtProblem& P = g.p[w.prob];
+            const uint8_t* a_src = reinterpret_cast<const uint8_t*>(P.At) + (size_t)w.mt * P.KC * GT_BLOCK_BYTES;
+            const uint8_t* b_src = reinterpret_cast<const uint8_t*>(P.Bt) + (size_t)w.nt * P.KC * GT_BLOCK_BYTES;
+            for (int kc = 0; kc < P.KC; ++kc) {
                 if (lane == 0) {
                     mbar_wait(&empty[s], ph);
                     uint8_t* dst = smem + (size_t)s * GT_STAGE_BYTES;
                     mbar_expect_tx(&full[s], GT_STAGE_BYTES);
-                    bulk_g2s(dst, a_src + (size_t)kc * (2 * GT_BLOCK_ELEMS), GT_STAGE_BYTES / 2, &full[s]);
-                    bulk_g2s(dst + GT_STAGE_BYTES / 2, b_src + (size_t)kc * (2 * GT_BLOCK_ELEMS), GT_STAGE_BYTES / 2, &full[s]);
+                    bulk_g2s(dst, a_src + (size_t)kc * GT_BLOCK_BYTES, GT_BLOCK_BYTES, &full[s]);
+                    bulk_g2s(dst + GT_BLOCK_BYTES, b_src + (size_t)kc * GT_BLOCK_BYTES, GT_BLOCK_BYTES, &full[s]);
                 }
                 __syncwarp();
                 if (++s == GT_NS) {
@@ -159,18 +298,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
         }
     } else if (warp == 1) {
         // ================= MMA issuer =====================================================================
-        // The accumulation chain inside the tensor core rounds toward zero (measured: error grows ~K / 2^22), so a
-        // TMEM accumulator only ever sums GT_KD chunks (K = 128); the epilogue warps add the slices in fp32 registers
-        // with round-to-nearest while the other accumulator buffer receives the next slice.
-        const uint32_t idesc_s = g.f16 ? idesc_f16_f32(128, 256) : idesc_bf16_f32(128, 256);   // B rows [hi | lo]
-        const uint32_t idesc_h = g.f16 ? idesc_f16_f32(128, 128) : idesc_bf16_f32(128, 128);   // B hi rows only
         const uint64_t d0 = smem_desc(smem_u32(smem), 128, 1024);
         int s = 0, acc = 0;
         uint32_t ph = 0, acc_ph = 1;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int kc = 0; kc < g.KC; ++kc) {
+        GtWalk w;
+        for (w.start(); w.next(g);) {
+            const GtProblem& P = g.p[w.prob];
+            const uint32_t idesc_s = P.f16 ? idesc_f16_f32(128, 256) : idesc_bf16_f32(128, 256);   // B rows [hi | lo]
+            const uint32_t idesc_h = P.f16 ? idesc_f16_f32(128, 128) : idesc_bf16_f32(128, 128);   // B hi rows only
+            for (int kc = 0; kc < P.KC; ++kc) {
                 const bool slice_start = (kc % GT_KD) == 0;
-                const bool slice_end = ((kc + 1) % GT_KD) == 0 || kc == g.KC - 1;
+                const bool slice_end = ((kc + 1) % GT_KD) == 0 || kc == P.KC - 1;
                 if (slice_start) {
                     if (lane == 0) mbar_wait(&tmem_empty[acc], acc_ph);
                     __syncwarp();
@@ -180,11 +318,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)acc * 256u;
                 const uint64_t da = d0 + (uint64_t)((uint32_t)s * (GT_STAGE_BYTES >> 4));
-                const uint64_t db = da + (uint64_t)(GT_STAGE_BYTES >> 5);
+                const uint64_t db = da + (uint64_t)(GT_BLOCK_BYTES >> 4);
 #pragma unroll
                 for (int k16 = 0; k16 < GT_BK / 16; ++k16) {
                     mma_bf16_ss_elect(d_tmem, da + 16u * k16, db + 16u * k16, idesc_s, !(slice_start && k16 == 0));
-                    mma_bf16_ss_elect(d_tmem, da + (uint32_t)(GT_BLOCK_ELEMS * 2 >> 4) + 16u * k16, db + 16u * k16, idesc_h, true);
+                    mma_bf16_ss_elect(d_tmem + 128u, da + (uint32_t)(GT_PLANE_BYTES >> 4) + 16u * k16, db + 16u * k16, idesc_h, true);
                 }
                 mma_commit_elect(&empty[s]);
                 if (++s == GT_NS) {
@@ -204,12 +342,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
         // ================= epilogue: TMEM lane == row of the tile =========================================
         int acc = 0;
         uint32_t acc_ph = 0;
-        const bool vec_ok = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-        const int n_slices = (g.KC + GT_KD - 1) / GT_KD;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int nt = tile / g.MT, mt = tile - nt * g.MT;
-            const int row = mt * GT_BM + (warp - 4) * 32 + lane;
-            const int n0 = nt * GT_BN;
+        GtWalk w;
+        for (w.start(); w.next(g);) {
+            const GtProblem& P = g.p[w.prob];
+            // both cross products sit in the second 128 columns; fp16 lo planes are stored scaled by 2^11 (umma.cuh)
+            const float lo_inv = P.f16 ? F16_LO_INV : 1.0f;
+            const bool vec_ok = (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+            const int n_slices = (P.KC + GT_KD - 1) / GT_KD;
+            const int row = w.mt * GT_BM + (warp - 4) * 32 + lane;
+            const int n0 = w.nt * GT_BN;
             float sum[GT_BN];
 #pragma unroll
             for (int q = 0; q < GT_BN; ++q) sum[q] = 0.f;
@@ -224,7 +365,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
                     tmem_ld_x16(taddr + 128 + c0, v2);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) sum[c0 + q] += v[q] + v2[q];
+                    for (int q = 0; q < 16; ++q) sum[c0 + q] += fmaf(v2[q], lo_inv, v[q]);
                 }
                 tc_fence_before();
                 mbar_arrive(&tmem_empty[acc]);
@@ -233,28 +374,28 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
                     acc_ph ^= 1;
                 }
             }
-            if (row < g.M) {
-                float* crow = g.C + (size_t)row * g.ldc + n0;
+            if (row < P.M) {
+                float* crow = P.C + (size_t)row * P.ldc + n0;
 #pragma unroll
                 for (int c0 = 0; c0 < GT_BN; c0 += 4) {
-                    if (n0 + c0 < g.N) {
-                        float o[4] = {sum[c0], sum[c0 + 1], sum[c0 + 2], sum[c0 + 3]};
-                        if (g.bias) {
+                    if (n0 + c0 < P.N) {
+                        float o[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (n0 + c0 + q < g.N) o[q] += g.bias[n0 + c0 + q];
+                        for (int q = 0; q < 4; ++q) {
+                            o[q] = P.alpha * sum[c0 + q];
+                            if (P.bias && n0 + c0 + q < P.N) o[q] += P.bias[n0 + c0 + q];
                         }
-                        if (vec_ok && n0 + c0 + 4 <= g.N) {
-                            float4 w = make_float4(o[0], o[1], o[2], o[3]);
-                            if (g.beta1) {
+                        if (vec_ok && n0 + c0 + 4 <= P.N) {
+                            float4 wv = make_float4(o[0], o[1], o[2], o[3]);
+                            if (P.beta1) {
                                 const float4 old = *reinterpret_cast<const float4*>(crow + c0);
-                                w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                                wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
                             }
-                            *reinterpret_cast<float4*>(crow + c0) = w;
+                            *reinterpret_cast<float4*>(crow + c0) = wv;
                         } else {
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                if (n0 + c0 + q < g.N) crow[c0 + q] = g.beta1 ? crow[c0 + q] + o[q] : o[q];
+                                if (n0 + c0 + q < P.N) crow[c0 + q] = P.beta1 ? crow[c0 + q] + o[q] : o[q];
                         }
                     }
                 }
@@ -267,90 +408,237 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(GemmTcArgs g) {
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------
-struct TcWorkspace {
-    uint16_t* buf[2] = {nullptr, nullptr};
-    size_t cap[2] = {0, 0};
+// Operand images live in a per-device arena owned by the library: grow-only, bump-allocated per group of products
+// (everything is stream-ordered on the caller's stream, so the next group may overwrite it).  cvb_reserve_workspace
+// sizes it up front -- growth calls cudaFree/cudaMalloc (a device synchronisation, illegal during graph capture), so a
+// caller that captures graphs reserves first (the warm-up steps before a capture do the same implicitly).
+// Images of PARAMETER operands are kept in their own buffers until the parameters change.
+struct Arena {
+    uint8_t* buf = nullptr;
+    size_t cap = 0;
+};
+struct ConstImage {
+    const float* p = nullptr;
+    int ld = 0, rows = 0, K = 0, kmajor = 0, f16 = 0;
+    unsigned long long gen = 0;
+    uint16_t* img = nullptr;
+    size_t bytes = 0;
+    unsigned long long last_use = 0;
 };
 static std::mutex g_ws_mu;
-static TcWorkspace g_ws[64];
+static Arena g_arena[64];
+static ConstImage g_const[64][16];
+static unsigned long long g_weights_gen = 1, g_use_clock = 0;
 
-static int ws_get(int which, size_t elems, uint16_t** out) {
+void weights_changed() {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    ++g_weights_gen;
+}
+
+static int arena_reserve(int dev, size_t bytes) {
+    Arena& a = g_arena[dev];
+    if (a.cap >= bytes) return 0;
+    if (a.buf) CVB_CHECK(cudaFree(a.buf));   // synchronises: earlier products are done with it
+    a.buf = nullptr;
+    a.cap = 0;
+    const size_t want = bytes + bytes / 8 + (1u << 20);
+    CVB_CHECK(cudaMalloc(&a.buf, want));
+    a.cap = want;
+    return 0;
+}
+
+int reserve_workspace(size_t bytes) {
     int dev = 0;
     CVB_CHECK(cudaGetDevice(&dev));
     CVB_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(g_ws_mu);
-    TcWorkspace& w = g_ws[dev];
-    if (w.cap[which] < elems) {
-        if (w.buf[which]) CVB_CHECK(cudaFree(w.buf[which]));   // synchronises: earlier GEMMs are done with it
-        w.buf[which] = nullptr;
-        w.cap[which] = 0;
-        const size_t want = elems + elems / 4;
-        CVB_CHECK(cudaMalloc(&w.buf[which], want * sizeof(uint16_t)));
-        w.cap[which] = want;
-    }
-    *out = w.buf[which];
-    return 0;
+    return arena_reserve(dev, bytes);
 }
 
-// measured on B200 (tools/bench_gemm.py): the two operand passes + the GEMM beat cuBLAS fp32 3-5x from ~3e9 MACs up
-// (gx, dW_hh, dW_x, dxc at the training shapes) and lose below ~1.5e9 (conv taps, dW_y, dW_o)
-bool gemm_tc_eligible(int M, int N, int K) {
-    return M >= 128 && N >= 128 && K >= 128 && (double)M * N * K >= 3.0e9;
+bool gemm_tc_eligible(int M, int N, int K) { return M >= 1 && N >= 1 && K >= 16 && (double)M * N * K >= 2.0e5; }
+
+static int widest_vec(const float* p, int ld) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 15) == 0 && (ld & 3) == 0) return 4;
+    if ((a & 7) == 0 && (ld & 1) == 0) return 2;
+    return 1;
+}
+
+static size_t image_bytes(int rows, int K) { return (size_t)ceil_div(rows, GT_BM) * ceil_div(K, GT_BK) * GT_BLOCK_BYTES; }
+
+static bool same_source(const GtOperand& a, const GtOperand& b) {
+    return a.p == b.p && a.p2 == b.p2 && a.ld == b.ld && a.ld2 == b.ld2 && a.K == b.K && a.kmajor == b.kmajor && a.conv_ci == b.conv_ci &&
+           a.conv_ds == b.conv_ds && a.f16 == b.f16;
+}
+
+int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
+    CVB_REQUIRE(n >= 1 && n <= GT_MAXP, "gemm_tc_group: %d products (1..%d)", n, GT_MAXP);
+    int dev = 0;
+    CVB_CHECK(cudaGetDevice(&dev));
+    CVB_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    GemmTcArgs g;
+    memset(&g, 0, sizeof(g));
+    g.n_prob = n;
+    GtOperand ops[GT_MAXO];       // distinct operands of this group
+    bool is_const[GT_MAXO];
+    int n_ops = 0, which[GT_MAXP][2];
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        const GemmDesc& D = d[i];
+        CVB_REQUIRE(D.M > 0 && D.N > 0 && D.K > 0 && D.A && D.B && D.C, "gemm_tc: empty product (M=%d N=%d K=%d)", D.M, D.N, D.K);
+        CVB_REQUIRE(!D.B2 || !D.transB, "gemm_tc: a second B source needs B stored [K,N]");
+        CVB_REQUIRE(!D.A2 || (D.transA && !D.gA), "gemm_tc: a second A source needs A stored [K,M]");
+        CVB_REQUIRE(!D.gA || !D.transA, "gemm_tc: a conv-gathered A is addressed as [M,K]");
+        CVB_REQUIRE(!D.gB || (!D.transB && !D.B2), "gemm_tc: a conv-gathered B is addressed as [K,N]");
+        for (int side = 0; side < 2; ++side) {
+            GtOperand o;
+            memset(&o, 0, sizeof(o));
+            if (side == 0) {
+                o.p = D.A; o.p2 = D.A2; o.ld = D.lda; o.ld2 = D.lda2; o.rows = D.M; o.R1 = D.A2 ? D.M1 : D.M;
+                o.kmajor = D.transA ? 0 : 1;      // A stored [M,K] unless transA ([K,M])
+                o.conv_ci = D.gA ? D.gA->ci : 0; o.conv_ds = D.gA ? D.gA->dshift : 0;
+            } else {
+                o.p = D.B; o.p2 = D.B2; o.ld = D.ldb; o.ld2 = D.ldb2; o.rows = D.N; o.R1 = D.B2 ? D.N1 : D.N;
+                o.kmajor = D.transB ? 1 : 0;      // B as [N rows, K]: stored [N,K] when transB, [K,N] otherwise
+                o.conv_ci = D.gB ? D.gB->ci : 0; o.conv_ds = D.gB ? D.gB->dshift : 0;
+            }
+            o.K = D.K;
+            o.KC = ceil_div(D.K, GT_BK);
+            o.vec = widest_vec(o.p, o.ld);
+            o.f16 = D.f16 ? 1 : 0;
+            const bool cst = (side == 0 ? D.a_const : D.b_const) && !o.p2 && !o.conv_ci;
+            // the same source with at least as many rows: share the image (a prefix of whole row tiles)
+            int found = -1;
+            for (int j = 0; j < n_ops && found < 0; ++j)
+                if (same_source(ops[j], o) && (ops[j].rows == o.rows || (ops[j].rows > o.rows && o.rows % GT_BM == 0 && !o.p2))) found = j;
+            if (found < 0) {
+                for (int j = 0; j < n_ops && found < 0; ++j)   // ... or grow an earlier, shorter one
+                    if (same_source(ops[j], o) && o.rows > ops[j].rows && ops[j].rows % GT_BM == 0 && !o.p2) {
+                        ops[j].rows = o.rows;
+                        ops[j].R1 = o.R1;
+                        found = j;
+                    }
+            }
+            if (found < 0) {
+                found = n_ops;
+                is_const[n_ops] = cst;
+                ops[n_ops++] = o;
+            }
+            which[i][side] = found;
+        }
+        GtProblem& P = g.p[i];
+        P.C = D.C;
+        P.bias = D.bias;
+        P.alpha = D.alpha;
+        P.M = D.M;
+        P.N = D.N;
+        P.ldc = D.ldc;
+        P.MT = ceil_div(D.M, GT_BM);
+        P.NT = ceil_div(D.N, GT_BN);
+        P.KC = ceil_div(D.K, GT_BK);
+        P.beta1 = D.beta1 ? 1 : 0;
+        P.f16 = D.f16 ? 1 : 0;
+        tiles += P.MT * P.NT;
+        P.tile_end = tiles;
+    }
+    // place the images: cached parameter images in their own buffers, the rest bump-allocated in the arena
+    SplitArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        size_t need = 0;
+        for (int j = 0; j < n_ops; ++j)
+            if (!is_const[j]) need += image_bytes(ops[j].rows, ops[j].K);
+        if (int rc = arena_reserve(dev, need)) return rc;
+        size_t off = 0;
+        int blocks = 0;
+        for (int j = 0; j < n_ops; ++j) {
+            GtOperand& o = ops[j];
+            const size_t bytes = image_bytes(o.rows, o.K);
+            bool fresh = true;
+            if (is_const[j]) {
+                ConstImage* slot = nullptr;
+                for (auto& c : g_const[dev])
+                    if (c.p == o.p && c.ld == o.ld && c.rows == o.rows && c.K == o.K && c.kmajor == o.kmajor && c.f16 == o.f16) slot = &c;
+                if (!slot) {   // least recently used slot
+                    slot = &g_const[dev][0];
+                    for (auto& c : g_const[dev])
+                        if (c.last_use < slot->last_use) slot = &c;
+                    if (slot->bytes < bytes) {
+                        if (slot->img) CVB_CHECK(cudaFree(slot->img));
+                        slot->img = nullptr;
+                        slot->bytes = 0;
+                        CVB_CHECK(cudaMalloc(&slot->img, bytes));
+                        slot->bytes = bytes;
+                    }
+                    slot->p = o.p; slot->ld = o.ld; slot->rows = o.rows; slot->K = o.K; slot->kmajor = o.kmajor; slot->f16 = o.f16;
+                    slot->gen = 0;
+                }
+                slot->last_use = ++g_use_clock;
+                o.img = slot->img;
+                fresh = slot->gen != g_weights_gen;
+                slot->gen = g_weights_gen;
+            } else {
+                o.img = reinterpret_cast<uint16_t*>(g_arena[dev].buf + off);
+                off += bytes;
+            }
+            if (fresh) {
+                GtOperand& t = sa.o[sa.n++];
+                t = o;
+                blocks += ceil_div(o.rows, GT_BM) * o.KC;
+                t.block_end = blocks;
+            }
+        }
+        if (sa.n) {
+            k_split_group<<<blocks, 256, 0, s>>>(sa);
+            CVB_LAUNCH_CHECK();
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        g.p[i].At = ops[which[i][0]].img;
+        g.p[i].Bt = ops[which[i][1]].img;
+    }
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+    const int smem = GT_NS * GT_STAGE_BYTES + 256;
+    static bool attr_set[64] = {};   // function attributes are per device
+    if (!attr_set[dev]) {
+        CVB_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[dev] = true;
+    }
+    const int grid = tiles < di.n_sm ? tiles : di.n_sm;
+    prof_begin(s, CVB_PROF_GEMM);
+    k_gemm_tc<<<grid, GT_THREADS, smem, s>>>(g);
+    prof_end(s, CVB_PROF_GEMM);
+    CVB_LAUNCH_CHECK();
+    return 0;
 }
 
 // C[M,N] = op(A) op(B) (+ C if beta1) (+ bias[N]);  A: [M,K] (lda) or [K,M] if transA;  B: [N,K] (ldb) if transB else [K,N].
 int gemm_tc(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
             bool beta1, const float* bias, float* C, int ldc, bool f16, const float* B2, int ldb2, int N1, const ConvGather* gA,
             const ConvGather* gB) {
-    CVB_REQUIRE(!B2 || !transB, "gemm_tc: a second B source needs B stored [K,N]");
-    CVB_REQUIRE(!gA || !transA, "gemm_tc: a conv-gathered A is addressed as [M,K]");
-    CVB_REQUIRE(!gB || (!transB && !B2), "gemm_tc: a conv-gathered B is addressed as [K,N]");
-    if (!B2) N1 = N;
-    const int a_ci = gA ? gA->ci : 0, a_ds = gA ? gA->dshift : 0, b_ci = gB ? gB->ci : 0, b_ds = gB ? gB->dshift : 0;
-    const int MT = ceil_div(M, GT_BM), NTl = ceil_div(N, GT_BN), KC = ceil_div(K, GT_BK);
-    uint16_t *At, *Bt;
-    if (int rc = ws_get(0, (size_t)MT * KC * 2 * GT_BLOCK_ELEMS, &At)) return rc;
-    if (int rc = ws_get(1, (size_t)NTl * KC * 2 * GT_BLOCK_ELEMS, &Bt)) return rc;
-    // A as [M rows, K]: stored [M,K] when !transA, [K,M] when transA.  B as [N rows, K]: stored [N,K] when transB.
-    if (f16) {
-        k_split_tiles<true><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M, a_ci, a_ds);
-        CVB_LAUNCH_CHECK();
-        k_split_tiles<true><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1, b_ci, b_ds);
-        CVB_LAUNCH_CHECK();
-    } else {
-        k_split_tiles<false><<<dim3(KC, MT), 256, 0, s>>>(A, lda, M, K, transA ? 1 : 0, KC, At, nullptr, 0, M, a_ci, a_ds);
-        CVB_LAUNCH_CHECK();
-        k_split_tiles<false><<<dim3(KC, NTl), 256, 0, s>>>(B, ldb, N, K, transB ? 0 : 1, KC, Bt, B2, ldb2, N1, b_ci, b_ds);
-        CVB_LAUNCH_CHECK();
-    }
-    DeviceInfo di;
-    if (int rc = get_device_info(&di)) return rc;
-    const int smem = GT_NS * GT_STAGE_BYTES + 256;
-    static bool attr_set[64] = {};   // function attributes are per device
-    int dev = 0;
-    CVB_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        CVB_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
-    GemmTcArgs g;
-    g.At = At;
-    g.Bt = Bt;
-    g.C = C;
-    g.bias = bias;
-    g.M = M;
-    g.N = N;
-    g.ldc = ldc;
-    g.MT = MT;
-    g.NTl = NTl;
-    g.KC = KC;
-    g.beta1 = beta1 ? 1 : 0;
-    g.f16 = f16 ? 1 : 0;
-    const int tiles = MT * NTl;
-    const int grid = tiles < di.n_sm ? tiles : di.n_sm;
-    k_gemm_tc<<<grid, GT_THREADS, smem, s>>>(g);
-    CVB_LAUNCH_CHECK();
-    return 0;
+    GemmDesc d;
+    d.transA = transA;
+    d.transB = transB;
+    d.M = M;
+    d.N = N;
+    d.K = K;
+    d.A = A;
+    d.lda = lda;
+    d.B = B;
+    d.ldb = ldb;
+    d.beta1 = beta1;
+    d.bias = bias;
+    d.C = C;
+    d.ldc = ldc;
+    d.f16 = f16;
+    d.B2 = B2;
+    d.ldb2 = ldb2;
+    d.N1 = N1;
+    d.gA = gA;
+    d.gB = gB;
+    return gemm_tc_group(s, &d, 1);
 }
 
 }  // namespace cvb

@@ -54,6 +54,7 @@ size_t gru_tc_scratch_floats(int B, int H);
 int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s);
 
 // inference-only forward with the y feedback folded into the recurrent matrix (one exchange per step), gru_tc_eval.cu
+bool gru_tc_eval_shape_ok(int B, int H);                    // host-only shape test (any out_dim)
 bool gru_tc_eval_supported(int B, int H, int out, const DeviceInfo& di);
 size_t gru_tc_eval_scratch_floats(int B, int H);
 // prepare (weights only; cfb = 6H floats: c_fb | b_ih + c_fb)  ->  caller's gx product with bias cfb + 3H  ->  launch

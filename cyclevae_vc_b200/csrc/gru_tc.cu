@@ -34,9 +34,15 @@ constexpr int TF_KC = 64;             // K per ring stage
 constexpr int TF_S = 4;               // cluster size
 constexpr int TF_UB = 8 * TF_S;       // units per cluster
 constexpr int TF_NW = 3 * TF_UB;      // rows of the W_hh operand (r, z, n of the block) = 96
-constexpr uint32_t TF_COL_Y = 192;    // D2: W_y y for the own units, 2 x 32 columns
-constexpr uint32_t TF_COL_P = 256;    // D3: partial of y_t, 2 x 64 columns
-constexpr uint32_t TF_COL_DUMMY = 384;
+// TMEM columns.  D1 = [main0 | corrections | main1]: the hi x hi products of the first / second half of the K-slice go to
+// two accumulators (a tcgen05 accumulation chain truncates toward zero: no fp32 accumulator sums more than K = 128,
+// tools/split_error_budget.py), the two cross products (lo planes scaled by 2^11, umma.cuh) share the middle one.
+constexpr uint32_t TF_COL_M0 = 0;
+constexpr uint32_t TF_COL_C = TF_NW;
+constexpr uint32_t TF_COL_M1 = 2 * TF_NW;
+constexpr uint32_t TF_COL_Y = 288;    // D2: W_y y for the own units, 32 main + 32 correction columns
+constexpr uint32_t TF_COL_P = 352;    // D3: partial of y_t, 64 main + 64 correction columns
+constexpr uint32_t TF_COL_DUMMY = 480;
 
 struct TfLayout {
     int MB, nch, NS;
@@ -120,7 +126,7 @@ static __device__ __forceinline__ void drain_partial_y(uint32_t taddr_p, float* 
         if (row_ok) {
 #pragma unroll
             for (int q = 0; q < 16; ++q)
-                if (o0 + q < out) pd[(size_t)(o0 + q) * B] = v[q] + v2[q];
+                if (o0 + q < out) pd[(size_t)(o0 + q) * B] = fmaf(v2[q], F16_LO_INV, v[q]);
         }
     }
 }
@@ -167,6 +173,8 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     unsigned* ctrA = a.ctr;
     unsigned* ctrB = a.ctr + 32;
     const int n_pairs = B * out;
+    const int half1 = (L.nch + 1) / 2;   // first chunk of the K-slice that accumulates into main1 (== nch: a single chain of <= 8 MMAs)
+    const bool two_main = half1 < L.nch;
 
     if (a.trace && c == 0 && threadIdx.x == 0) a.trace[60] = clock64();
     // ---- one-time setup: weights -> fp16 hi/lo in UMMA K-major core-matrix order -----------------
@@ -186,8 +194,11 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             split8_f16(w, hi, lo);
             const uint32_t off = (uint32_t)(kl / TF_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TF_KC) >> 3) * 128u +
                                  (uint32_t)(n & 7) * 16u;
-            *reinterpret_cast<uint4*>(sW + off) = hi;
-            *reinterpret_cast<uint4*>(sW + (TF_NW / 8) * 1024u + off) = lo;
+            // chunks of the second half of the K walk are stored [lo rows | hi rows]: their stacked MMA starts at the
+            // correction columns and runs on into main1
+            const bool swapped = (kl / TF_KC) >= half1;
+            *reinterpret_cast<uint4*>(sW + off + (swapped ? (TF_NW / 8) * 1024u : 0u)) = hi;
+            *reinterpret_cast<uint4*>(sW + off + (swapped ? 0u : (TF_NW / 8) * 1024u)) = lo;
         }
         for (int i = threadIdx.x; i < 32 * 64; i += TF_NT) {   // B2[n = g*8+uu][k] = W_y[g*H + u0 + uu][k]; rows 24..31 zero
             const int n = i >> 6, k = i & 63;
@@ -304,10 +315,24 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 tc_fence_after();
                 const uint64_t da = dA0 + (uint64_t)((uint32_t)s * a_step);
                 const uint64_t db = dW0 + (uint64_t)((uint32_t)ch * w_step);
+                const uint32_t w_half16 = (TF_NW / 8) * 1024u >> 4;   // hi rows -> lo rows (or lo -> hi in a swapped chunk)
+                if (ch < half1) {   // [hi | lo] rows: main0 and corrections side by side
 #pragma unroll
-                for (int k16 = 0; k16 < TF_KC / 16; ++k16) {
-                    mma_bf16_ss_elect(tmem, da + 16u * k16, db + 16u * k16, idesc1s, (ch | k16) != 0);
-                    mma_bf16_ss_elect(tmem, da + half16 + 16u * k16, db + 16u * k16, idesc1, true);
+                    for (int k16 = 0; k16 < TF_KC / 16; ++k16) {
+                        mma_bf16_ss_elect(tmem + TF_COL_M0, da + 16u * k16, db + 16u * k16, idesc1s, (ch | k16) != 0);
+                        mma_bf16_ss_elect(tmem + TF_COL_C, da + half16 + 16u * k16, db + 16u * k16, idesc1, true);
+                    }
+                } else {            // [lo | hi] rows: corrections and main1 side by side
+#pragma unroll
+                    for (int k16 = 0; k16 < TF_KC / 16; ++k16) {
+                        if (ch == half1 && k16 == 0) {   // main1 starts from zero while the corrections keep accumulating
+                            mma_bf16_ss_elect(tmem + TF_COL_C, da, db, idesc1, true);
+                            mma_bf16_ss_elect(tmem + TF_COL_M1, da, db + w_half16, idesc1, false);
+                        } else {
+                            mma_bf16_ss_elect(tmem + TF_COL_C, da + 16u * k16, db + 16u * k16, idesc1s, true);
+                        }
+                        mma_bf16_ss_elect(tmem + TF_COL_C, da + half16 + 16u * k16, db + w_half16 + 16u * k16, idesc1, true);
+                    }
                 }
                 mma_commit_elect(&empty[s]);
                 if (ch == L.nch - 1) mma_commit_elect(d1_full);   // the exchange of the partial sums does not wait for y_{t-1}
@@ -323,7 +348,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
 #pragma unroll
                 for (int k16 = 0; k16 < TF_KC / 16; ++k16) {
                     mma_bf16_ss_elect(tmem + TF_COL_Y, dY0 + 16u * k16, dB2 + 16u * k16, idesc2s, k16 != 0);
-                    mma_bf16_ss_elect(tmem + TF_COL_Y, dY0 + half16 + 16u * k16, dB2 + 16u * k16, idesc2, true);
+                    mma_bf16_ss_elect(tmem + TF_COL_Y + 32u, dY0 + half16 + 16u * k16, dB2 + 16u * k16, idesc2, true);
                 }
                 mma_commit_elect(y_empty);
                 mma_commit_elect(accum_full);
@@ -332,7 +357,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             wait_warm(a2_full, (uint32_t)t & 1);
             tc_fence_after();
             mma_bf16_ss_elect(tmem + TF_COL_P, dA2, dB3, idesc3s, false);
-            mma_bf16_ss_elect(tmem + TF_COL_P, dA2 + 256u, dB3, idesc3, true);
+            mma_bf16_ss_elect(tmem + TF_COL_P + 64u, dA2 + 256u, dB3, idesc3, true);
             mma_commit_elect(part_full);
         }
     } else if (warp >= 4 && warp < 8) {
@@ -389,17 +414,25 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     float v[16], v2[16];
-                    tmem_ld_x16(taddr + g * TF_UB + 16 * k, v);
-                    tmem_ld_x16(taddr + TF_NW + g * TF_UB + 16 * k, v2);
-                    tmem_ld_wait();
+                    tmem_ld_x16(taddr + TF_COL_M0 + g * TF_UB + 16 * k, v);
+                    tmem_ld_x16(taddr + TF_COL_C + g * TF_UB + 16 * k, v2);
+                    if (two_main) {
+                        float v3[16];
+                        tmem_ld_x16(taddr + TF_COL_M1 + g * TF_UB + 16 * k, v3);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v[q] += v3[q];
+                    } else {
+                        tmem_ld_wait();
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = fmaf(v2[q], F16_LO_INV, v[q]);
                     if (b < L.MB * 8) {
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
                             float* d = stage + (size_t)(2 * k + h2) * slot_f + b * 24 + g * 8;
-                            *reinterpret_cast<float4*>(d) = make_float4(v[8 * h2 + 0] + v2[8 * h2 + 0], v[8 * h2 + 1] + v2[8 * h2 + 1],
-                                                                        v[8 * h2 + 2] + v2[8 * h2 + 2], v[8 * h2 + 3] + v2[8 * h2 + 3]);
-                            *reinterpret_cast<float4*>(d + 4) = make_float4(v[8 * h2 + 4] + v2[8 * h2 + 4], v[8 * h2 + 5] + v2[8 * h2 + 5],
-                                                                            v[8 * h2 + 6] + v2[8 * h2 + 6], v[8 * h2 + 7] + v2[8 * h2 + 7]);
+                            *reinterpret_cast<float4*>(d) = make_float4(v[8 * h2 + 0], v[8 * h2 + 1], v[8 * h2 + 2], v[8 * h2 + 3]);
+                            *reinterpret_cast<float4*>(d + 4) = make_float4(v[8 * h2 + 4], v[8 * h2 + 5], v[8 * h2 + 6], v[8 * h2 + 7]);
                         }
                     }
                 }
@@ -421,17 +454,17 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 tmem_ld_x8(taddr + TF_COL_Y + 32, c2);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 8; ++q) yr[q] += c2[q];
+                for (int q = 0; q < 8; ++q) yr[q] = fmaf(c2[q], F16_LO_INV, yr[q]);
                 tmem_ld_x8(taddr + TF_COL_Y + 8, yz);
                 tmem_ld_x8(taddr + TF_COL_Y + 40, c2);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 8; ++q) yz[q] += c2[q];
+                for (int q = 0; q < 8; ++q) yz[q] = fmaf(c2[q], F16_LO_INV, yz[q]);
                 tmem_ld_x8(taddr + TF_COL_Y + 16, yn);
                 tmem_ld_x8(taddr + TF_COL_Y + 48, c2);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 8; ++q) yn[q] += c2[q];
+                for (int q = 0; q < 8; ++q) yn[q] = fmaf(c2[q], F16_LO_INV, yn[q]);
             }
             tc_fence_before();
             mbar_wait_cluster(inbox_full, (uint32_t)t & 1);
@@ -686,7 +719,7 @@ static bool fwd_runnable(int B, int H, int out, const DeviceInfo& di, TfLayout* 
     const int G = H / 8;
     if (!gru_tc_shape_ok(B, H, out) || G > di.n_sm) return false;
     struct Entry { int B, H, out, ok; };
-    static Entry cache[16];
+    static Entry cache[256];   // the row-count probe of cvb_recurrence_max_rows adds up to 16 entries per network shape
     static int n_cache = 0;
     int ok = -1;
     for (int i = 0; i < n_cache; ++i)
@@ -718,7 +751,7 @@ static bool fwd_runnable(int B, int H, int out, const DeviceInfo& di, TfLayout* 
             }
         }
         cudaGetLastError();
-        if (n_cache < 16) cache[n_cache++] = Entry{B, H, out, ok};
+        if (n_cache < 256) cache[n_cache++] = Entry{B, H, out, ok};
     }
     if (ok && Lout) *Lout = L;
     return ok != 0;

@@ -683,7 +683,7 @@ static int pick_cluster(int B, int H, int out, const DeviceInfo& di, TbLayout* L
     const char* e8 = getenv("CVB_TC_CLUSTER8");
     const int first = (e8 && e8[0] == '1') ? 8 : 4;
     struct Entry { int B, H, out, first, S; };
-    static Entry cache[16];
+    static Entry cache[256];   // the row-count probe of cvb_recurrence_max_rows adds up to 16 entries per network shape
     static int n_cache = 0;
     int S = -1;
     for (int i = 0; i < n_cache; ++i)
@@ -717,7 +717,7 @@ static int pick_cluster(int B, int H, int out, const DeviceInfo& di, TbLayout* L
             if (getenv("CVB_DEBUG")) fprintf(stderr, "[cvb] k_gru_bwd_tc: cluster %d: %d co-resident clusters (need %d), smem %u, ring %d\n", cand, ncl, G / cand, L.total, L.NS);
             if (ncl * cand >= G) S = cand;
         }
-        if (n_cache < 16) cache[n_cache++] = Entry{B, H, out, first, S};
+        if (n_cache < 256) cache[n_cache++] = Entry{B, H, out, first, S};
     }
     if (S && Lout) *Lout = tb_layout(B, H, S, G, out, di.max_smem_optin);
     return S;

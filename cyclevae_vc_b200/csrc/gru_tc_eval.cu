@@ -28,6 +28,10 @@ constexpr int TE_KC = 64;
 constexpr int TE_S = 4;
 constexpr int TE_UB = 8 * TE_S;     // units per cluster
 constexpr int TE_NW = 4 * TE_UB;    // rows of the folded operand: r', z', hn, in' of the block = 128
+// TMEM columns [main0 | corrections | main1]: the hi x hi products of the first / second half of the K walk go to two
+// accumulators (a tcgen05 accumulation chain truncates toward zero: none sums more than K = 128), the two cross products
+// (lo planes scaled by 2^11, umma.cuh) share the middle one (tools/split_error_budget.py)
+constexpr uint32_t TE_COL_M0 = 0, TE_COL_C = TE_NW, TE_COL_M1 = 2 * TE_NW, TE_COL_DUMMY = 3 * TE_NW;
 
 struct TeLayout {
     int MB, nch, NS;
@@ -125,7 +129,12 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
     const uint32_t kca_sh = L.KCA == 64 ? 6u : 5u;   // log2(KCA)
     // the 32 CTAs that own the same K-slice read the same stages of h: each cluster starts its walk over the slice at a
     // different stage so that they do not all pull the same L2 lines at the same moment (fixed per cluster: deterministic)
-    const int rot = a.rotate ? (c / TE_S) % L.nsub : 0;
+    // (rotation in units of the 64-wide weight chunks: a chunk's stages stay in the same half of the walk)
+    const int per64 = TE_KC / L.KCA;
+    const int rot = a.rotate ? ((c / TE_S) % L.nch) * per64 : 0;
+    const int half1c = (L.nch + 1) / 2;        // walk position (in weight chunks) from which main1 accumulates
+    const int half1 = half1c * per64;          // the same in ring stages
+    const bool two_main = half1c < L.nch;
 
     // ---- one-time setup: folded weights -> fp16 hi/lo in UMMA K-major core-matrix order ------------------
     {
@@ -152,8 +161,13 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             split8_f16(w, hi, lo);
             const uint32_t off = (uint32_t)(kl / TE_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TE_KC) >> 3) * 128u +
                                  (uint32_t)(n & 7) * 16u;
-            *reinterpret_cast<uint4*>(sW + off) = hi;
-            *reinterpret_cast<uint4*>(sW + (TE_NW / 8) * 1024u + off) = lo;
+            // chunks walked in the second half are stored [lo rows | hi rows]: their stacked MMA starts at the correction
+            // columns and runs on into main1
+            int pos = kl / TE_KC - rot / per64;
+            if (pos < 0) pos += L.nch;
+            const bool swapped = pos >= half1c;
+            *reinterpret_cast<uint4*>(sW + off + (swapped ? (TE_NW / 8) * 1024u : 0u)) = hi;
+            *reinterpret_cast<uint4*>(sW + off + (swapped ? 0u : (TE_NW / 8) * 1024u)) = lo;
         }
         if (threadIdx.x < 24) sBh[threadIdx.x] = a.bhh[(threadIdx.x >> 3) * H + u0 + (threadIdx.x & 7)];
         if (threadIdx.x == 0) {
@@ -237,7 +251,7 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                     uint32_t ok = (lane == 0) ? (mbar_test_wait(&full[s], ph) ? 1u : 0u) : 0u;
                     ok = __shfl_sync(0xffffffffu, ok, 0);
                     if (ok) break;
-                    if (a.keepalive) mma_bf16_ss_elect(tmem + 384u, dW0, dW0, idesc_dummy, false);
+                    if (a.keepalive) mma_bf16_ss_elect(tmem + TE_COL_DUMMY, dW0, dW0, idesc_dummy, false);
                 }
                 if (lane == 0 && ch < 8) TE_TRACE(40 + ch);
                 tc_fence_after();
@@ -247,9 +261,22 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                 if (che >= L.nsub) che -= L.nsub;
                 const uint32_t kq = (uint32_t)che << kca_sh;
                 const uint64_t db = dW0 + (uint64_t)((kq >> 6) * w_step + ((kq & 63u) >> 4) * 16u);
-                for (int k16 = 0; k16 < kca16; ++k16) {
-                    mma_bf16_ss_elect(tmem, da + 16u * k16, db + 16u * k16, idesc_s, (ch | k16) != 0);
-                    mma_bf16_ss_elect(tmem, da + half16 + 16u * k16, db + 16u * k16, idesc_h, true);
+                const uint32_t w_half16 = (TE_NW / 8) * 1024u >> 4;   // hi rows -> lo rows (lo -> hi in a swapped chunk)
+                if (ch < half1) {   // [hi | lo] rows: main0 and corrections side by side
+                    for (int k16 = 0; k16 < kca16; ++k16) {
+                        mma_bf16_ss_elect(tmem + TE_COL_M0, da + 16u * k16, db + 16u * k16, idesc_s, (ch | k16) != 0);
+                        mma_bf16_ss_elect(tmem + TE_COL_C, da + half16 + 16u * k16, db + 16u * k16, idesc_h, true);
+                    }
+                } else {            // [lo | hi] rows: corrections and main1 side by side
+                    for (int k16 = 0; k16 < kca16; ++k16) {
+                        if (ch == half1 && k16 == 0) {   // main1 starts from zero while the corrections keep accumulating
+                            mma_bf16_ss_elect(tmem + TE_COL_C, da, db, idesc_h, true);
+                            mma_bf16_ss_elect(tmem + TE_COL_M1, da, db + w_half16, idesc_h, false);
+                        } else {
+                            mma_bf16_ss_elect(tmem + TE_COL_C, da + 16u * k16, db + 16u * k16, idesc_s, true);
+                        }
+                        mma_bf16_ss_elect(tmem + TE_COL_C, da + half16 + 16u * k16, db + w_half16 + 16u * k16, idesc_h, true);
+                    }
                 }
                 mma_commit_elect(&empty[s]);
                 if (ch == L.nsub - 1) mma_commit_elect(d1_full);
@@ -307,24 +334,32 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     float v[16], v2[16];
-                    tmem_ld_x16(taddr + g * TE_UB + 16 * k, v);
-                    tmem_ld_x16(taddr + TE_NW + g * TE_UB + 16 * k, v2);
-                    tmem_ld_wait();
+                    tmem_ld_x16(taddr + TE_COL_M0 + g * TE_UB + 16 * k, v);
+                    tmem_ld_x16(taddr + TE_COL_C + g * TE_UB + 16 * k, v2);
+                    if (two_main) {
+                        float v3[16];
+                        tmem_ld_x16(taddr + TE_COL_M1 + g * TE_UB + 16 * k, v3);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v[q] += v3[q];
+                    } else {
+                        tmem_ld_wait();
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = fmaf(v2[q], F16_LO_INV, v[q]);
 #pragma unroll
                     for (int h2 = 0; h2 < 2; ++h2) {
                         const int p = 2 * k + h2;   // destination CTA of the cluster
                         if (p == j) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) own[g * 8 + q] = v[8 * h2 + q] + v2[8 * h2 + q];
+                            for (int q = 0; q < 8; ++q) own[g * 8 + q] = v[8 * h2 + q];
                         } else if (b < L.MB * 8) {
                             // a row is 8 x 16 B; slot q of row b sits at q ^ (b & 7) so that a quarter warp covers all 32 banks
                             float* row = stage + (size_t)(p - (p > j ? 1 : 0)) * slot_f + b * 32;
                             float* d = row + (((2 * g) ^ (b & 7)) << 2);
                             float* d1 = row + (((2 * g + 1) ^ (b & 7)) << 2);
-                            *reinterpret_cast<float4*>(d) = make_float4(v[8 * h2 + 0] + v2[8 * h2 + 0], v[8 * h2 + 1] + v2[8 * h2 + 1],
-                                                                        v[8 * h2 + 2] + v2[8 * h2 + 2], v[8 * h2 + 3] + v2[8 * h2 + 3]);
-                            *reinterpret_cast<float4*>(d1) = make_float4(v[8 * h2 + 4] + v2[8 * h2 + 4], v[8 * h2 + 5] + v2[8 * h2 + 5],
-                                                                            v[8 * h2 + 6] + v2[8 * h2 + 6], v[8 * h2 + 7] + v2[8 * h2 + 7]);
+                            *reinterpret_cast<float4*>(d) = make_float4(v[8 * h2 + 0], v[8 * h2 + 1], v[8 * h2 + 2], v[8 * h2 + 3]);
+                            *reinterpret_cast<float4*>(d1) = make_float4(v[8 * h2 + 4], v[8 * h2 + 5], v[8 * h2 + 6], v[8 * h2 + 7]);
                         }
                     }
                 }
@@ -404,11 +439,14 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
+// host-only shape test (no device query): what the scratch sizing keys on -- any out_dim (y comes from a GEMM after the launch)
+bool gru_tc_eval_shape_ok(int B, int H) { return H % (TE_KC * TE_S) == 0 && H >= TE_KC * TE_S && B >= 1 && B <= 128 && H <= 3968; }
+
 static bool eval_runnable(int B, int H, const DeviceInfo& di, TeLayout* Lout) {
     const int G = H / 8;
-    if (!(H % (TE_KC * TE_S) == 0 && H >= TE_KC * TE_S && B >= 1 && B <= 128 && H <= 3968) || G > di.n_sm) return false;
+    if (!gru_tc_eval_shape_ok(B, H) || G > di.n_sm) return false;
     struct Entry { int B, H, ok; };
-    static Entry cache[16];
+    static Entry cache[256];   // the row-count probe of cvb_recurrence_max_rows adds up to 16 entries per network shape
     static int n_cache = 0;
     int ok = -1;
     for (int i = 0; i < n_cache; ++i)
@@ -436,7 +474,7 @@ static bool eval_runnable(int B, int H, const DeviceInfo& di, TeLayout* Lout) {
             fprintf(stderr, "[cvb] k_gru_fwd_tc_eval: not runnable at B=%d H=%d: ring %d stages, smem %u of %d\n", B, H, L.NS, L.total, di.max_smem_optin);
         }
         cudaGetLastError();
-        if (n_cache < 16) cache[n_cache++] = Entry{B, H, ok};
+        if (n_cache < 256) cache[n_cache++] = Entry{B, H, ok};
     }
     if (ok && Lout) *Lout = L;
     return ok != 0;
@@ -546,6 +584,8 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStre
         CVB_CHECK(cudaFree(a.trace));
     }
     // all outputs at once: ys[1..T] = hs[1..T] W_o^T + b_o
+    if (want_tc_gemm() && gemm_tc_eligible(T * B, out, H))
+        return gemm_tc(s, false, true, T * B, out, H, f.hs + (size_t)B * H, H, f.Wo, H, false, f.bo, f.ys + (size_t)B * out, out, true);
     if (int rc = fill_rows(s, f.ys + (size_t)B * out, (size_t)T * B, out, out, f.bo)) return rc;
     if (int rc = gemm_rm(s, false, true, T * B, out, H, 1.f, f.hs + (size_t)B * H, H, f.Wo, H, 1.f, f.ys + (size_t)B * out, out)) return rc;
     return 0;

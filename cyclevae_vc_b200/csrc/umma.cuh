@@ -205,11 +205,16 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
     lo = (uint16_t)(q >> 16);
 }
 
-// ---- fp16 split: x = hi + lo (+ O(2^-22 |x|)); 11 + 11 mantissa bits, for bounded operands (|x| < 6e4) ----
+// ---- fp16 split: x = hi + 2^-11 lo (+ O(2^-22 |x|)); 11 + 11 mantissa bits, for bounded operands (|x| < 6e4) ----
+// The residual is stored SCALED by 2^11: unscaled it is an fp16 subnormal for every |x| < 0.125 (absolute resolution
+// 2^-24 instead of 2^-22 |x|).  The two cross products (hi x lo, lo x hi) therefore live in their own TMEM accumulator
+// and are folded in as  main + 2^-11 * corrections  when the accumulators are read (tools/split_error_budget.py).
+constexpr float F16_LO_SCALE = 2048.0f;
+constexpr float F16_LO_INV = 1.0f / 2048.0f;
 __device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
     const float c = fminf(fmaxf(x, -60000.f), 60000.f);
     const __half h = __float2half_rn(c);
-    const __half l = __float2half_rn(x - __half2float(h));
+    const __half l = __float2half_rn((c - __half2float(h)) * F16_LO_SCALE);
     hi = __half_as_ushort(h);
     lo = __half_as_ushort(l);
 }

@@ -167,22 +167,27 @@ class FlatAdam:
     .grad become views of two contiguous tensors, so the data-parallel exchange is a single all-reduce
     and the update is a single kernel (cvb_adam_step)."""
 
+    ALIGN = 16   # floats
+
     def __init__(self, params: Sequence[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
         params = list(params)
         dev = params[0].device
-        n = sum(p.numel() for p in params)
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        # every parameter starts on a 64-byte boundary (the kernels read weight rows as float4); the pad elements stay
+        # zero in grad / exp_avg / exp_avg_sq, so the single Adam kernel and the single all-reduce run over them harmlessly
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in params:
+        for p, off in zip(params, offs):
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
             p.requires_grad_(True)
-            off += k
         self.params, self.n = params, n
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
 
@@ -191,6 +196,10 @@ class FlatAdam:
 
     def step(self, grad_scale: float = 1.0):
         self.t += 1
+        with torch.cuda.device(self.flat.device):
+            self._launch(grad_scale)
+
+    def _launch(self, grad_scale):
         check(lib.cvb_adam_step(self.n, ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.lr,
                                 self.betas[0], self.betas[1], self.eps, self.t, grad_scale,
                                 torch.cuda.current_stream().cuda_stream), "cvb_adam_step")

@@ -198,6 +198,7 @@ class GRU_RNN(nn.Module):
             self.scale_out = nn.Conv1d(self.out_dim, self.out_dim, 1)
         self._injected_masks = None
         self._scratch_buf = None
+        self._param_stamp = None
 
     # -- plumbing ----------------------------------------------------------------------------------
     @property
@@ -295,7 +296,21 @@ class GRU_RNN(nn.Module):
             head = _lib.HEAD_CLAMP
         else:
             head = _lib.HEAD_NONE
+        with torch.cuda.device(xb.device):   # the library launches on the CURRENT device and stream
+            trj, y_last, h_last = self._dispatch(xb, y0, h0, mc, mg, head, int(lat_dim), B)
+        if not batched:
+            trj = trj.squeeze(0)
+        return trj, y_last.unsqueeze(1), h_last.unsqueeze(0)
+
+    def _dispatch(self, xb, y0, h0, mc, mg, head, lat_dim, B):
         params = self._param_list()
+        # the library keeps 16-bit images of parameter matrices across calls: tell it when the parameters moved or were
+        # modified by anything but its own Adam kernel (torch.optim, load_state_dict, the .cpu()/.cuda() round trip of
+        # save_checkpoint, train_*.py:152-167)
+        stamp = tuple((p.data_ptr(), p._version) for p in params)
+        if stamp != self._param_stamp:
+            self._param_stamp = stamp
+            lib.cvb_weights_changed()
         want_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or xb.requires_grad or y0.requires_grad
                                                  or (h0 is not None and h0.requires_grad))
         max_rows = MAX_ROWS_PER_LAUNCH
@@ -315,18 +330,17 @@ class GRU_RNN(nn.Module):
                                             None if mc is None else mc[:, lo:hi].contiguous(),
                                             None if mg is None else mg[:, lo:hi].contiguous(), *params))
             trj, y_last, h_last = (torch.cat([o[i] for o in outs], 0) for i in range(3))
-        if not batched:
-            trj = trj.squeeze(0)
-        return trj, y_last.unsqueeze(1), h_last.unsqueeze(0)
+        return trj, y_last, h_last
 
 
 def draw_dropout_masks(B, T, conv_dim, hidden, p, device):
     """Time-major dropout masks [T,B,conv_dim], [T,B,hidden] with values {0, 1/(1-p)} -- the Bernoulli
     draws of nn.Dropout at gru_vae.py:355/:369/:380, from Philox4x32-10 keyed by torch's seed."""
     n1, n2 = T * B * conv_dim, T * B * hidden
-    buf = torch.empty(n1 + n2, dtype=torch.float32, device=device)
-    seed, off = _Rng.take((n1 + n2 + 3) // 4)
-    check(lib.cvb_dropout_mask(n1 + n2, float(p), seed, off, ptr(buf), _stream()), "cvb_dropout_mask")
+    with torch.cuda.device(device):
+        buf = torch.empty(n1 + n2, dtype=torch.float32, device=device)
+        seed, off = _Rng.take((n1 + n2 + 3) // 4)
+        check(lib.cvb_dropout_mask(n1 + n2, float(p), seed, off, ptr(buf), _stream()), "cvb_dropout_mask")
     return buf[:n1].view(T, B, conv_dim), buf[n1:].view(T, B, hidden)
 
 
@@ -367,7 +381,8 @@ def reparam_concat(param, code=None, eps=None, lat_dim=None):
     p3 = _f32c(param.unsqueeze(0) if squeeze else param)
     c3 = None if code is None else _f32c(code.unsqueeze(0) if squeeze else code)
     e3 = None if eps is None else _f32c(eps.reshape(p3.shape[0], p3.shape[1], lat_dim))
-    out = _ReparamConcatFn.apply(p3, c3, e3, int(lat_dim))
+    with torch.cuda.device(p3.device):
+        out = _ReparamConcatFn.apply(p3, c3, e3, int(lat_dim))
     return out.squeeze(0) if squeeze else out
 
 
@@ -409,7 +424,8 @@ class _KlFn(torch.autograd.Function):
 def kl_per_utt(lat, flens, lat_dim):
     """loss_vae (gru_vae.py:117-123) for every utterance of a [B,T,2*lat] batch at once:
     out[j] = loss_vae(lat[j, :flens[j]], lat_dim).  flens: int32 CUDA tensor [B]."""
-    return _KlFn.apply(_f32c(lat), flens, int(lat_dim))
+    with torch.cuda.device(lat.device):
+        return _KlFn.apply(_f32c(lat), flens, int(lat_dim))
 
 
 def loss_vae(param, lat_dim=None, relu_vae=False):
@@ -467,7 +483,8 @@ def mcd_l1_per_utt(x, y, flens, x_off=0, y_off=0, D=None):
     tensors of shape [B]."""
     if D is None:
         D = x.shape[2] - x_off
-    return _McdFn.apply(_f32c(x), _f32c(y), flens, int(x_off), int(y_off), int(D))
+    with torch.cuda.device(x.device):
+        return _McdFn.apply(_f32c(x), _f32c(y), flens, int(x_off), int(y_off), int(D))
 
 
 class TWFSEloss(nn.Module):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 7
+#define CVB_ABI_VERSION 8
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -171,13 +171,24 @@ int cvb_adam_step(size_t n, float* param, const float* grad, float* exp_avg, flo
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                   void* stream);
 
+/* ---- parameter residency --------------------------------------------------------------------------
+ * The dense products keep 16-bit operand images of PARAMETER matrices (W_x ...) across calls.  They are refreshed
+ * after cvb_adam_step automatically; a caller that changes parameters any other way (torch.optim, load_state_dict,
+ * .cuda()/.cpu() round trips of save_checkpoint, train_*.py:152-167) calls cvb_weights_changed() before the next
+ * forward -- the Python module does so whenever a parameter's (data_ptr, version) stamp moved. */
+int cvb_weights_changed(void);
+/* Pre-size the library's operand-image arena on the current device (bytes).  The arena otherwise grows on demand with
+ * cudaFree/cudaMalloc, which synchronises the device and is illegal while a CUDA graph is being captured. */
+int cvb_reserve_workspace(size_t bytes);
+
 /* ---- measurement hooks (bench.py's roofline object) -------------------------------------------
  * When enabled, CUDA events are recorded on the launching stream around every launch of the
- * persistent recurrence kernels (kind 0 = forward, 1 = BPTT) and, at level 2, around every dense
- * product (kind 2).  cvb_profile_summary synchronises those events and returns total ms / launches. */
+ * persistent recurrence kernels (kind 0 = forward, 1 = BPTT), around the front-end chain of every forward call
+ * (kind 3) and, at level 2, around every dense product (kind 2).  cvb_profile_summary synchronises those events and returns total ms / launches. */
 #define CVB_PROF_GRU_FWD 0
 #define CVB_PROF_GRU_BWD 1
 #define CVB_PROF_GEMM 2
+#define CVB_PROF_FRONTEND 3 /* the front-end chain of one forward call (scale_in + conv stack + dropout -> xc) */
 int cvb_profile_enable(int level);
 int cvb_profile_reset(void);
 int cvb_profile_summary(int kind, float* total_ms, int* launches);

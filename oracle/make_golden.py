@@ -311,6 +311,69 @@ def golden_spk4():
     print("spk4.npz")
 
 
+def golden_spk4_cyc2():
+    """configs[3]: 4-speaker many-to-many CycleVAE (decoder in_dim = lat + 4, one-hot codes), training-mode cyc2 step at
+    B=2 T=80 with injected dropout masks: loss, sub-sampled outputs, gradient norms + samples from the reference's autograd."""
+    lat, stdim, n_spk = 32, 4, 4
+    mean, std = orc.synth_stats(50)
+    enc = orc.encoder_spec(54, lat, 1024)
+    dec = orc.decoder_spec(lat, n_spk, 50, 1024)
+    Pe = orc.init_params(enc, 301, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 302, mean=mean[stdim:], scale=std[stdim:])
+    me, md = build_ref(enc, Pe).train(), build_ref(dec, Pd).train()
+    B, T, n_cyc = 2, 80, 2
+    x, cv, sc, tc = orc.synth_batch(B, T, 13, n_spk=n_spk)
+    sc[1], tc[1] = 0.0, 0.0
+    sc[1, :, 2], tc[1, :, 0] = 1.0, 1.0          # utterance 1: speaker 2 -> speaker 0 (codes beyond the 2-speaker pattern)
+    eps = orc.synth_noise(B, T, lat, n_cyc, 13)
+    masks = orc.synth_masks(B, T, enc, dec, n_cyc, 13)
+    y0d1 = torch.tensor(((0 - mean[stdim:]) / std[stdim:]), dtype=torch.float32).reshape(1, 1, -1)
+    out, total = ref_cyc_step(me, md, enc, dec, x, cv, sc, tc, n_cyc, lat, stdim, torch.zeros(B, 1, 2 * lat),
+                              y0d1.repeat(B, 1, 1), eps, masks, [T, 70], [0, 1])
+    total.backward()
+    g = {"loss": total.item(), "src_code": sc.numpy(), "trg_code": tc.numpy(), "pe_sum": orc.params_checksum(Pe), "pd_sum": orc.params_checksum(Pd)}
+    for k, v in out.items():
+        for i in range(n_cyc):
+            g[f"{k}/{i}"] = sub(v[i], 8)
+    for net, m in (("enc", me), ("dec", md)):
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                gr = p.grad.detach().numpy()
+                g[f"gnorm/{net}/{k}"] = np.sqrt((gr.astype(np.float64) ** 2).sum())
+                g[f"gsamp/{net}/{k}"] = gr.reshape(-1)[:: max(1, gr.size // 64)][:64].copy()
+    np.savez_compressed(os.path.join(OUT, "spk4_cyc2.npz"), **g)
+    print("spk4_cyc2.npz loss", total.item())
+
+
+DECODE512_ROWS = [0, 37, 100, 127, 128, 200, 255, 256, 300, 383, 384, 450, 500, 511, 64, 320]
+
+
+def golden_decode512():
+    """configs[2]: stage-6 batch conversion of 512 utterances x 800 frames.  The reference converts ONE utterance per call
+    (decode_*.py:303-305,318, unbatched [T,54] layout), so the fixture is the reference run on 16 of the 512 synthetic
+    utterances (4 in each 128-row slice of the batched launch), every 5th frame of the latent and of the converted mcep."""
+    lat, stdim, B, T = 32, 4, 512, 800
+    mean, std = orc.synth_stats(50)
+    enc, dec = orc.encoder_spec(54, lat, 1024), orc.decoder_spec(lat, 2, 50, 1024)
+    Pe = orc.init_params(enc, 201, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 202, mean=mean[stdim:], scale=std[stdim:])
+    me, md = build_ref(enc, Pe).eval(), build_ref(dec, Pd).eval()
+    y0d1 = torch.tensor(((0 - mean[stdim:]) / std[stdim:]), dtype=torch.float32).reshape(1, 1, -1)
+    x, _, sc, tc = orc.synth_batch(B, T, 21)
+    eps_mean = orc.synth_noise(B, T, lat, 1, 21)[0][0] / np.sqrt(300.0)
+    lats, cvms = [], []
+    with torch.no_grad():
+        for r in DECODE512_ROWS:
+            lat_src, _, _ = me(x[r], torch.zeros(1, 1, 2 * lat), clamp_vae=True, lat_dim=lat)
+            lat_feat = lat_src[:, :lat] + torch.exp(lat_src[:, lat:] / 2) * eps_mean[r]
+            cvm, _, _ = md(torch.cat((tc[r], lat_feat), 1), y0d1)
+            lats.append(lat_src.numpy()[::5].copy())
+            cvms.append(cvm.numpy()[::5].copy())
+    np.savez_compressed(os.path.join(OUT, "decode512.npz"), rows=np.array(DECODE512_ROWS), lat=np.stack(lats), cvmcep=np.stack(cvms),
+                        x_sum=float(x.double().abs().sum()), eps_sum=float(eps_mean.double().abs().sum()))
+    print("decode512.npz", len(DECODE512_ROWS), "rows")
+
+
 def golden_chunks():
     """Bit-exact integer bookkeeping: exec the reference's own train_generator on fake loader batches."""
     src = open(os.path.join(REF, "src", "bin", "train_gru_cyclevae_gauss_batch.py")).read()
@@ -375,6 +438,6 @@ def golden_init():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["tiny", "cfg0", "flagship", "spk4", "chunks", "init"]
+    which = sys.argv[1:] or ["tiny", "cfg0", "flagship", "spk4", "spk4_cyc2", "decode512", "chunks", "init"]
     for w in which:
         globals()["golden_" + w]()

@@ -17,6 +17,13 @@ from oracle import gru_vae_oracle as orc
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
+PATH_FP32, PATH_TC, PATH_TC_FOLDED = 0, 1, 2   # include/cyclevae_b200.h CVB_PATH_*
+
+
+def _paths():
+    """(forward, backward) recurrence kernels of the last calls: a silent fall to the fp32-FMA kernels must fail a test."""
+    from cyclevae_vc_b200._lib import lib
+    return lib.cvb_last_recurrence_path(0), lib.cvb_last_recurrence_path(1)
 
 
 @pytest.fixture(scope="module")
@@ -286,6 +293,8 @@ def test_flagship_cyc2_step_vs_reference_golden(golden_dir, cvb):
     enc, dec, me, md, x, cv, sc, tc, eps, masks, y0e, y0d = _cyc_setup(cvb, 1024, lat, B, T, n_cyc, 3, 201, 202)
     out, total = _run_cyc(cvb, me, md, x, cv, sc, tc, eps, masks, y0e, y0d, n_cyc, lat, [T, 61], [0, 1])
     total.backward()
+    torch.cuda.synchronize()
+    assert _paths() == (PATH_TC, PATH_TC), "hu1024 training must run the tcgen05 recurrence kernels, not a fallback"
     assert total.item() == pytest.approx(float(g["cyc2/loss"]), rel=5e-6)
     for k in out:
         for i in range(n_cyc):
@@ -322,15 +331,16 @@ def test_flagship_decode_and_carry(golden_dir, cvb, tag, gain, bstd):
         cvm = cycle.convert(me, md, x[0].cuda(), tc[0].cuda(), lat_dim=lat, y0_enc=torch.zeros(1, 1, 2 * lat).cuda(),
                             y0_dec=y0d1, eps_mean=eps_mean[0])
     assert lat_src.shape == (T, 2 * lat) and cvm.shape == (T, 50)
+    assert _paths()[0] == PATH_TC_FOLDED, "hu1024 inference must run the folded tcgen05 kernel, not a fallback"
     assert _maxabs(lat_src[::5], g[f"{tag}/dec800_lat"]) < TOL
     if tag == "init":
         assert _maxabs(cvm[::5], g[f"{tag}/dec800_cvmcep"]) < TOL
     else:
         # Stress set (weights x3, |mcep| up to 21): the fp32 REFERENCE is itself 1.4e-4 away from exact (fp64)
         # arithmetic after 800 recurrent steps, so "within 1e-4 of the reference" is below fp32 noise here.
-        # Bar: no further from the fp64 oracle than 3x the reference's own distance (the recurrence amplifies any
-        # rounding difference on this set: split-precision tensor-core products with their own summation order
-        # land at ~2.3x, the fp32-FMA kernels at ~1x), and within 1e-4 relative to the output scale of the reference.
+        # Bar: no further from the fp64 oracle than 1.5x the reference's own distance, and within 1e-4 relative to the
+        # output scale of the reference.  (Round 1 sat at 2.3x: tools/split_error_budget.py traced it to the truncating
+        # accumulation inside long tcgen05 chains and to unscaled fp16 lo planes; both are fixed in the kernels.)
         P64e, P64d = ({k: v.double() for k, v in P.items()} for P in (Pe, Pd))
         exact = orc.convert(P64e, P64d, enc, dec, x[0].double(), tc[0].double(), lat_dim=lat,
                             y0_enc=torch.zeros(1, 1, 2 * lat, dtype=torch.float64), y0_dec=y0d1.cpu().double(),
@@ -338,7 +348,7 @@ def test_flagship_decode_and_carry(golden_dir, cvb, tag, gain, bstd):
         ref = g[f"{tag}/dec800_cvmcep"]
         ref_vs_exact = np.abs(ref - exact).max()
         mine_vs_exact = np.abs(cvm[::5].cpu().numpy() - exact).max()
-        assert mine_vs_exact <= max(TOL, 3.0 * ref_vs_exact), (mine_vs_exact, ref_vs_exact)
+        assert mine_vs_exact <= max(TOL, 1.5 * ref_vs_exact), (mine_vs_exact, ref_vs_exact)
         assert _maxabs(cvm[::5], ref) < TOL * max(1.0, np.abs(ref).max())
     B, T = 3, 80
     x, cv, sc, tc = (t.cuda() for t in orc.synth_batch(B, 2 * T, 2))
@@ -356,18 +366,23 @@ def test_flagship_decode_and_carry(golden_dir, cvb, tag, gain, bstd):
         P64e, P64d = ({k: v.double() for k, v in P.items()} for P in (Pe, Pd))
         xc, scc = x.cpu().double(), sc.cpu().double()
         e1, ey1, eh1 = orc.gru_rnn_forward(P64e, enc, xc[:, :T], torch.zeros(B, 1, 2 * lat, dtype=torch.float64), clamp_vae=True, lat_dim=lat)
-        e2, _, _ = orc.gru_rnn_forward(P64e, enc, xc[:, T:], ey1, eh1, clamp_vae=True, lat_dim=lat)
+        e2, _, eh2 = orc.gru_rnn_forward(P64e, enc, xc[:, T:], ey1, eh1, clamp_vae=True, lat_dim=lat)
         zin64 = torch.cat((scc, torch.cat((e1, e2), 1)[:, :, :lat]), 2)
         f1, fy1, fh1 = orc.gru_rnn_forward(P64d, dec, zin64[:, :T], y0d1.cpu().double().repeat(B, 1, 1))
-        f2, _, _ = orc.gru_rnn_forward(P64d, dec, zin64[:, T:], fy1, fh1)
+        f2, _, fh2 = orc.gru_rnn_forward(P64d, dec, zin64[:, T:], fy1, fh1)
         exact = torch.cat((f1, f2), 1).numpy()[:, ::4]
         ref_vs_exact = np.abs(ref - exact).max()
         mine_vs_exact = np.abs(torch.cat((d1, d2), 1)[:, ::4].cpu().numpy() - exact).max()
-        assert mine_vs_exact <= max(TOL, 3.0 * ref_vs_exact), (mine_vs_exact, ref_vs_exact)
+        assert mine_vs_exact <= max(TOL, 1.5 * ref_vs_exact), (mine_vs_exact, ref_vs_exact)
         assert _maxabs(torch.cat((d1, d2), 1)[:, ::4], ref) < TOL * max(1.0, np.abs(ref).max())
-    tol_h = TOL if tag == "init" else 3e-4   # stress set: see the bar above (the reference itself is ~2e-4 from exact)
-    assert _maxabs(h2[:, :, ::8], g[f"{tag}/carry_h_enc"]) < tol_h
-    assert _maxabs(hd2[:, :, ::8], g[f"{tag}/carry_h_dec"]) < tol_h
+    if tag == "init":
+        assert _maxabs(h2[:, :, ::8], g[f"{tag}/carry_h_enc"]) < TOL
+        assert _maxabs(hd2[:, :, ::8], g[f"{tag}/carry_h_dec"]) < TOL
+    else:   # stress set: the carried states against the fp64 oracle, same 1.5x bar
+        for mine, exact_h, key in ((h2, eh2, "carry_h_enc"), (hd2, fh2, "carry_h_dec")):
+            ex = exact_h.numpy()[:, :, ::8]
+            ref_d = np.abs(g[f"{tag}/{key}"] - ex).max()
+            assert np.abs(mine[:, :, ::8].cpu().numpy() - ex).max() <= max(TOL, 1.5 * ref_d), key
 
 
 def test_spk4_decoder(golden_dir, cvb):
@@ -386,6 +401,7 @@ def test_spk4_decoder(golden_dir, cvb):
     y0 = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1).repeat(B, 1, 1)
     with torch.no_grad():
         o, y, h = md(torch.cat((code, z), 2).cuda(), y0.cuda())
+    assert _paths()[0] == PATH_TC_FOLDED
     assert _maxabs(o, g["trj"]) < TOL
     assert _maxabs(y, g["y"]) < TOL
     assert _maxabs(h[:, :, ::8], g["h"]) < TOL
@@ -776,3 +792,152 @@ def test_tensor_core_recurrence_hu512_both_cluster_shapes(cvb, cluster8):
         assert _maxabs(a, b) < 1e-4 * max(1e-3, float(b.abs().max()))
     for k in gp_e:
         assert _maxabs(gp_t[k], gp_e[k]) < 1e-4 * max(1e-3, float(gp_e[k].abs().max())), k
+
+
+@pytest.mark.parametrize("net", ["enc", "dec"])
+def test_bench_shape_training_pass_vs_fp64_oracle(cvb, net):
+    """The bench workload's pass shape (hu1024, 80 utterances x 80 frames, dropout masks, carried y_in / h_in) on the
+    tcgen05 kernels against the FLOAT64 ORACLE (not against this library's own fp32 kernels): outputs, gradients w.r.t.
+    x / y_in / h_in and every parameter gradient (all elements + norm).  gru_vae.py:364-399, SURVEY.md A.3."""
+    lat, stdim, B, T = 32, 4, 80, 80
+    mean, std = orc.synth_stats(50)
+    if net == "enc":
+        spec = orc.encoder_spec(54, lat, 1024)
+        P = orc.init_params(spec, 201, gain=1.0, bias_std=0.02, mean=mean, scale=std)
+    else:
+        spec = orc.decoder_spec(lat, 2, 50, 1024)
+        P = orc.init_params(spec, 202, gain=1.0, bias_std=0.02, mean=mean[stdim:], scale=std[stdim:])
+    g = torch.Generator().manual_seed(23)
+    if net == "enc":
+        x = orc.synth_batch(B, T, 31)[0]
+    else:
+        x = torch.cat((orc.synth_batch(B, T, 31)[2], torch.randn(B, T, lat, generator=g)), 2)
+    y0 = 0.3 * torch.randn(B, 1, spec.out_dim, generator=g)
+    h0 = 0.5 * torch.randn(1, B, 1024, generator=g)
+    mc = (torch.rand(B, T, spec.conv_dim, generator=g) >= 0.5).float() * 2
+    mg = (torch.rand(B, T, 1024, generator=g) >= 0.5).float() * 2
+    w_o = torch.randn(B, T, spec.out_dim, generator=g)
+    w_y = torch.randn(B, 1, spec.out_dim, generator=g)
+    w_h = torch.randn(1, B, 1024, generator=g)
+    kw = dict(clamp_vae=True, lat_dim=lat) if net == "enc" else {}
+    # float64 oracle + autograd
+    P64 = {k: v.double().requires_grad_(not k.startswith("scale_")) for k, v in P.items()}
+    xr, yr, hr = (t.double().requires_grad_(True) for t in (x, y0, h0))
+    o_r, y_r, h_r = orc.gru_rnn_forward(P64, spec, xr, yr, hr, mask_conv=mc.double(), mask_gru=mg.double(), **kw)
+    ((o_r * w_o.double()).sum() + (y_r * w_y.double()).sum() + (h_r * w_h.double()).sum()).backward()
+    # device
+    m = _module(cvb, spec, P).train()
+    for k, p in m.named_parameters():
+        p.requires_grad_(not k.startswith("scale_"))
+    xs, ys, hs = (t.cuda().requires_grad_(True) for t in (x, y0, h0))
+    m.inject_dropout_masks(mc.cuda(), mg.cuda())
+    o, yl, hl = m(xs, ys, h_in=hs, do=True, **kw)
+    ((o * w_o.cuda()).sum() + (yl * w_y.cuda()).sum() + (hl * w_h.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    assert _paths() == (PATH_TC, PATH_TC)
+    for a, b, name in ((o, o_r, "trj"), (yl, y_r, "y_last"), (hl, h_r, "h_last")):
+        assert _maxabs(a.double(), b.detach()) < TOL * max(1.0, float(b.abs().max())), name
+    for a, b, name in ((xs.grad, xr.grad, "dx"), (ys.grad, yr.grad, "dy_in"), (hs.grad, hr.grad, "dh_in")):
+        assert _maxabs(a.double(), b) < 2e-4 * max(1e-3, float(b.abs().max())), (name, float(b.abs().max()))
+    n_checked = 0
+    for k, p in m.named_parameters():
+        if k.startswith("scale_"):
+            continue
+        ref = P64[k].grad
+        assert ref is not None and p.grad is not None, k
+        assert _maxabs(p.grad.double(), ref) < 2e-4 * max(1e-3, float(ref.abs().max())), (k, float(ref.abs().max()))
+        assert float(p.grad.double().norm()) == pytest.approx(float(ref.norm()), rel=2e-4), k
+        n_checked += 1
+    assert n_checked == 10
+
+
+def test_spk4_cyc2_step_vs_reference_golden(golden_dir, cvb):
+    """configs[3]: 4-speaker one-hot codes (decoder in_dim 36: conv 324, GRU input 374 -- ragged for 64-wide K chunks),
+    training-mode cyc2 step at B=2 T=80 against fixtures produced by the unmodified reference."""
+    g = _load(golden_dir, "spk4_cyc2.npz")
+    lat, B, T, n_cyc = 32, 2, 80, 2
+    enc, dec, me, md, x, cv, _, _, eps, masks, y0e, y0d = _cyc_setup(cvb, 1024, lat, B, T, n_cyc, 13, 301, 302, n_spk=4)
+    x, cv, _, _ = orc.synth_batch(B, T, 13, n_spk=4)
+    sc, tc = torch.tensor(g["src_code"]), torch.tensor(g["trg_code"])
+    out, total = _run_cyc(cvb, me, md, x, cv, sc, tc, eps, masks, y0e, y0d, n_cyc, lat, [T, 70], [0, 1])
+    total.backward()
+    torch.cuda.synchronize()
+    assert md.in_dim == 36 and _paths() == (PATH_TC, PATH_TC)
+    assert total.item() == pytest.approx(float(g["loss"]), rel=5e-6)
+    for k in out:
+        for i in range(n_cyc):
+            assert _maxabs(out[k][i][:, ::8], g[f"{k}/{i}"]) < TOL, (k, i)
+    for net, m in (("enc", me), ("dec", md)):
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                continue
+            gr = p.grad.detach().cpu().numpy()
+            assert np.sqrt((gr.astype(np.float64) ** 2).sum()) == pytest.approx(float(g[f"gnorm/{net}/{k}"]), rel=3e-4), k
+            samp = gr.reshape(-1)[:: max(1, gr.size // 64)][:64]
+            ref = g[f"gsamp/{net}/{k}"]
+            assert np.abs(samp - ref).max() < 3e-4 * max(1.0, np.abs(ref).max()), k
+
+
+def test_decode512_batch_vs_reference_golden(golden_dir, cvb):
+    """configs[2] at full size: stage-6 conversion of 512 utterances x 800 frames in one batched call (4 launches of 128
+    rows per network) against the reference run one utterance at a time on 16 of them, 4 per 128-row slice."""
+    from cyclevae_vc_b200 import cycle
+    g = _load(golden_dir, "decode512.npz")
+    lat, stdim, B, T = 32, 4, 512, 800
+    mean, std = orc.synth_stats(50)
+    enc, dec = orc.encoder_spec(54, lat, 1024), orc.decoder_spec(lat, 2, 50, 1024)
+    Pe = orc.init_params(enc, 201, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 202, mean=mean[stdim:], scale=std[stdim:])
+    me, md = _module(cvb, enc, Pe).eval(), _module(cvb, dec, Pd).eval()
+    x, _, sc, tc = orc.synth_batch(B, T, 21)
+    eps_mean = orc.synth_noise(B, T, lat, 1, 21)[0][0] / np.sqrt(300.0)
+    assert float(x.double().abs().sum()) == pytest.approx(float(g["x_sum"]), rel=1e-12)
+    y0d = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1).repeat(B, 1, 1).cuda()
+    y0e = torch.zeros(B, 1, 2 * lat).cuda()
+    with torch.no_grad():
+        lat_src, _, _ = me(x.cuda(), y0e, clamp_vae=True, lat_dim=lat)
+        assert _paths()[0] == PATH_TC_FOLDED
+        cvm = cycle.convert(me, md, x.cuda(), tc.cuda(), lat_dim=lat, y0_enc=y0e, y0_dec=y0d, eps_mean=eps_mean.cuda())
+    assert cvm.shape == (B, T, 50) and torch.isfinite(cvm).all()
+    rows = g["rows"].tolist()
+    assert len(set(r // 128 for r in rows)) == 4
+    assert _maxabs(lat_src[rows][:, ::5], g["lat"]) < TOL
+    assert _maxabs(cvm[rows][:, ::5], g["cvmcep"]) < TOL
+
+
+def test_wide_latent_encoder_eval_and_training(cvb):
+    """out_dim > 64 (encoder at lat_dim = 50, egs/one-to-one/run.sh lists 50 and 64): inference takes the folded tcgen05
+    kernel (any out_dim: y comes from a product after the launch) and its scratch must be sized for it; training falls
+    to the fp32-FMA kernels (the two-exchange tcgen05 kernels hold out <= 64).  Both against the float64 oracle."""
+    lat, B, T = 50, 8, 100
+    mean, std = orc.synth_stats(50)
+    spec = orc.encoder_spec(54, lat, 1024)
+    P = orc.init_params(spec, 211, gain=1.0, bias_std=0.02, mean=mean, scale=std)
+    P64 = {k: v.double() for k, v in P.items()}
+    x = orc.synth_batch(B, T, 41)[0]
+    y0 = torch.zeros(B, 1, 2 * lat)
+    m = _module(cvb, spec, P).eval()
+    with torch.no_grad():
+        o, y, h = m(x.cuda(), y0.cuda(), clamp_vae=True, lat_dim=lat)
+        o1, _, _ = m(x[0].cuda(), y0[:1].cuda(), clamp_vae=True, lat_dim=lat)     # B = 1: stage-6 decode of one utterance
+        o_r, y_r, h_r = orc.gru_rnn_forward(P64, spec, x.double(), y0.double(), clamp_vae=True, lat_dim=lat)
+    assert _paths()[0] == PATH_TC_FOLDED
+    assert _maxabs(o.double(), o_r) < TOL and _maxabs(h.double(), h_r) < TOL and _maxabs(y.double(), y_r) < TOL
+    assert _maxabs(o1.double(), o_r[0]) < TOL
+    m.train()
+    g = torch.Generator().manual_seed(5)
+    mc = (torch.rand(B, T, spec.conv_dim, generator=g) >= 0.5).float() * 2
+    mg = (torch.rand(B, T, 1024, generator=g) >= 0.5).float() * 2
+    Pg = {k: v.double().requires_grad_(not k.startswith("scale_")) for k, v in P.items()}
+    o_r, _, h_r = orc.gru_rnn_forward(Pg, spec, x.double(), y0.double(), mask_conv=mc.double(), mask_gru=mg.double(), clamp_vae=True, lat_dim=lat)
+    (o_r.square().sum() + h_r.sum()).backward()
+    for k, p in m.named_parameters():
+        p.requires_grad_(not k.startswith("scale_"))
+    m.inject_dropout_masks(mc.cuda(), mg.cuda())
+    o, _, h = m(x.cuda(), y0.cuda(), do=True, clamp_vae=True, lat_dim=lat)
+    (o.square().sum() + h.sum()).backward()
+    torch.cuda.synchronize()
+    assert _paths() == (PATH_FP32, PATH_FP32)
+    assert _maxabs(o.double(), o_r.detach()) < TOL
+    ref = Pg["gru.weight_hh_l0"].grad
+    assert _maxabs(m.gru.weight_hh_l0.grad.double(), ref) < 2e-4 * max(1.0, float(ref.abs().max()))

@@ -246,6 +246,61 @@ def test_spk4(golden_dir):
     assert np.abs(h.numpy()[:, :, ::8] - g["h"]).max() < 1e-4
 
 
+def test_spk4_cyc2_step(golden_dir):
+    """configs[3]: 4-speaker one-hot codes (decoder in_dim 36), training-mode cyc2 step at B=2 T=80 vs the reference."""
+    g = _load(golden_dir, "spk4_cyc2.npz")
+    lat, stdim, B, T, n_cyc, n_spk = 32, 4, 2, 80, 2, 4
+    mean, std = orc.synth_stats(50)
+    enc, dec = orc.encoder_spec(54, lat, 1024), orc.decoder_spec(lat, n_spk, 50, 1024)
+    Pe = orc.init_params(enc, 301, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 302, mean=mean[stdim:], scale=std[stdim:])
+    assert orc.params_checksum(Pd) == pytest.approx(float(g["pd_sum"]), rel=1e-12)
+    for P in (Pe, Pd):
+        for k, v in P.items():
+            if not k.startswith("scale_"):
+                v.requires_grad_(True)
+    x, cv, _, _ = orc.synth_batch(B, T, 13, n_spk=n_spk)
+    sc, tc = _t(g["src_code"]), _t(g["trg_code"])
+    eps = orc.synth_noise(B, T, lat, n_cyc, 13)
+    masks = orc.synth_masks(B, T, enc, dec, n_cyc, 13)
+    y0d = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1).repeat(B, 1, 1)
+    out, _ = orc.cyc_forward(Pe, Pd, enc, dec, x=x, cv=cv, src_code=sc, trg_code=tc, n_cyc=n_cyc, lat_dim=lat,
+                             stdim=stdim, y0_enc=torch.zeros(B, 1, 2 * lat), y0_dec=y0d, eps=eps, masks=masks)
+    total, _ = orc.cyc_loss(out, x, n_cyc=n_cyc, lat_dim=lat, stdim=stdim, flen_acc=[T, 70], select_utt_idx=[0, 1])
+    total.backward()
+    assert total.item() == pytest.approx(float(g["loss"]), rel=2e-6)
+    for k in out:
+        for i in range(n_cyc):
+            assert np.abs(out[k][i].detach().numpy()[:, ::8] - g[f"{k}/{i}"]).max() < 1e-4, (k, i)
+    for net, P in (("enc", Pe), ("dec", Pd)):
+        for k, v in P.items():
+            if v.grad is not None:
+                gr = v.grad.numpy()
+                assert np.sqrt((gr.astype(np.float64) ** 2).sum()) == pytest.approx(float(g[f"gnorm/{net}/{k}"]), rel=2e-4), k
+
+
+def test_decode512_rows(golden_dir):
+    """configs[2]: two of the 16 reference-converted utterances of the 512 x 800 synthetic batch (the GPU test checks all 16)."""
+    g = _load(golden_dir, "decode512.npz")
+    lat, stdim, B, T = 32, 4, 512, 800
+    mean, std = orc.synth_stats(50)
+    enc, dec = orc.encoder_spec(54, lat, 1024), orc.decoder_spec(lat, 2, 50, 1024)
+    Pe = orc.init_params(enc, 201, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 202, mean=mean[stdim:], scale=std[stdim:])
+    x, _, sc, tc = orc.synth_batch(B, T, 21)
+    eps_mean = orc.synth_noise(B, T, lat, 1, 21)[0][0] / np.sqrt(300.0)
+    assert float(x.double().abs().sum()) == pytest.approx(float(g["x_sum"]), rel=1e-12)
+    y0d = torch.tensor((0 - mean[stdim:]) / std[stdim:], dtype=torch.float32).reshape(1, 1, -1)
+    rows = g["rows"].tolist()
+    for i in (1, 12):
+        r = rows[i]
+        with torch.no_grad():
+            lat_src, _, _ = orc.gru_rnn_forward(Pe, enc, x[r], torch.zeros(1, 1, 2 * lat), clamp_vae=True, lat_dim=lat)
+            cvm = orc.convert(Pe, Pd, enc, dec, x[r], tc[r], lat_dim=lat, y0_enc=torch.zeros(1, 1, 2 * lat), y0_dec=y0d, eps_mean=eps_mean[r])
+        assert np.abs(lat_src.numpy()[::5] - g["lat"][i]).max() < 1e-4
+        assert np.abs(cvm.numpy()[::5] - g["cvmcep"][i]).max() < 1e-4
+
+
 def test_oracle_gradcheck_fp64():
     """BPTT of the restatement is exact in fp64 (finite differences), incl. masks, h_in, y_in."""
     spec = orc.NetSpec(in_dim=3, out_dim=4, hidden_units=5, do_prob=0.5, scale_in=True, scale_out=False)

@@ -13,6 +13,8 @@ shapes = [("gx enc", 6400, 3072, 486, 0, 1), ("gx dec", 6400, 3072, 306, 0, 1), 
           ("dW_hh n", 1024, 1024, 6400, 1, 0), ("dW_x enc", 3072, 486, 6400, 1, 0), ("dW_y", 3072, 64, 6400, 1, 0),
           ("dW_o", 64, 1024, 6400, 1, 0), ("dxc enc", 6400, 486, 3072, 0, 0), ("conv1 tap", 7040, 486, 162, 0, 1),
           ("conv0 tap", 7040, 162, 54, 0, 1), ("dconv1 w", 486, 162, 7040, 1, 0), ("dconv1 in", 7040, 162, 486, 0, 0)]
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+shapes = [s_ for s_ in shapes if only in s_[0]]
 print(f"{'product':12s} {'M':>5s} {'N':>5s} {'K':>5s}  tc_us  cublas_us  tc TFLOP/s(alg)")
 for name, M, N, K, ta, tb in shapes:
     A = torch.randn((K, M) if ta else (M, K), device="cuda")
