@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--batch-utt", type=int, default=None, help="utterances per GPU (default: 80 train, 8 spk4, 512 decode)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying the captured CUDA graph")
     a = ap.parse_args()
     if a.batch_utt is None:
         a.batch_utt = {"train": 80, "spk4": 8, "decode": DEC_UTT}[a.workload]
@@ -358,25 +359,25 @@ def run_native(args):
     else:
         enc.train(); dec.train()
         opt = cycle.FlatAdam(cycle.trainable_parameters(enc, dec), lr=1e-4)
-        flens = torch.full((B,), T, dtype=torch.int32, device=dev)
-        sel = list(range(B))
+        # the fused step driver: forward + losses + BPTT replayed as one CUDA graph, all-reduce, Adam
+        cs = cycle.CycleStep(enc, dec, opt, B=B, T=T, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, n_spk=args.n_spk, y0_enc=y0e, y0_dec=y0d,
+                             graph=not args.no_graph)
 
         def step(x, cv, sc, tc):
-            opt.zero_grad()
-            out, _ = cycle.cyc_forward(enc, dec, x=x, cv=cv, src_code=sc, trg_code=tc, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM,
-                                       y0_enc=y0e, y0_dec=y0d, do=True)
-            loss, _ = cycle.cyc_loss(out, x, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, flen_acc=None, select_utt_idx=sel, flens_dev=flens)
-            loss.backward()
-            cycle.allreduce_grads(opt.grad)
-            opt.step()
-            return loss
+            return cs.step(x, cv, sc, tc)
 
         def read_back(res):
             return float(res.item())
 
         d2h = 4
-    devb = [t.to(dev) for t in host]
-    stage = [torch.empty_like(t, device=dev) for t in host]
+    if decode:
+        devb = [t.to(dev) for t in host]
+        stage = [torch.empty_like(t, device=dev) for t in host]
+    else:   # the step driver's own static input buffers: resident inputs are used in place, host inputs are copied into them
+        stage = [cs.x, cs.cv, cs.sc, cs.tc]
+        for d, h in zip(stage, host):
+            d.copy_(h)
+        devb = stage
 
     def barrier():
         if world > 1:
@@ -399,7 +400,7 @@ def run_native(args):
     if rank == 0:
         sampler.start()
     lib.cvb_profile_reset()
-    lib.cvb_profile_enable(1)
+    lib.cvb_profile_enable(1 if decode or args.no_graph else 0)
     n0 = lib.cvb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -409,8 +410,26 @@ def run_native(args):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    launches = (lib.cvb_launch_count() - n0) // args.steps
+    launches = (lib.cvb_launch_count() - n0) // args.steps + (0 if decode else cs.kernels_per_replay)
     lib.cvb_profile_enable(0)
+    prof_steps = args.steps
+    if not (decode or args.no_graph):
+        # Per-kernel durations: a replayed graph has no host-side launches to bracket, so the SAME step (same kernels, same
+        # buffers) is run kernel by kernel for a few extra steps with CUDA events around every recurrence launch and
+        # front-end chain on the launching stream.  Outside the timed region above; only feeds the roofline objects.
+        eager = cycle.CycleStep(enc, dec, opt, B=B, T=T, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, n_spk=args.n_spk, y0_enc=y0e, y0_dec=y0d,
+                                graph=False)
+        for d, h in zip((eager.x, eager.cv, eager.sc, eager.tc), host):
+            d.copy_(h)
+        eager.step(eager.x, eager.cv, eager.sc, eager.tc)
+        barrier()
+        lib.cvb_profile_reset()
+        lib.cvb_profile_enable(1)
+        prof_steps = 3
+        for _ in range(prof_steps):
+            eager.step(eager.x, eager.cv, eager.sc, eager.tc)
+        barrier()
+        lib.cvb_profile_enable(0)
     prof = {}
     for kind, name in ((0, "k_gru_fwd"), (1, "k_gru_bwd"), (3, "frontend_fwd")):
         tot, n = C.c_float(0), C.c_int(0)
@@ -518,7 +537,7 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": dom + ("_tc_eval" if decode else "_tc"), "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "avg_launch_ms": avg_ms, "launches_timed": n_l, "algorithmic_flops_per_launch": fl, "peak_source": peak_src,
-                         "share_of_step": {k: v[0] / args.steps / ms for k, v in prof.items()},
+                         "share_of_step": {k: v[0] / prof_steps / ms for k, v in prof.items()},
                          "us_per_recurrent_step": avg_ms * 1e3 / T, "rows_per_launch": rows, "note": note},
         }
         if roof_fe:

@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcyclevae_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -56,15 +56,16 @@ PROTOTYPES = {
     "cvb_gru_rnn_backward": (_i, [_netp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _gradp, _vp]),
     "cvb_frontend_fwd": (_i, [_netp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "cvb_reparam_concat_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "cvb_reparam_concat_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "cvb_reparam_concat_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cvb_concat2_fwd": (_i, [_i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "cvb_kl_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "cvb_kl_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cvb_mcd_l1_fwd": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "cvb_mcd_l1_bwd": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "cvb_dropout_mask": (_i, [_sz, _f, _u64, _u64, _vp, _vp]),
-    "cvb_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp]),
+    "cvb_dropout_mask": (_i, [_sz, _f, _u64, _u64, _vp, _vp, _vp]),
+    "cvb_state_advance": (_i, [_vp, _u64, _u64, _vp]),
+    "cvb_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "cvb_weights_changed": (_i, []),
     "cvb_reserve_workspace": (_i, [_sz]),
     "cvb_profile_enable": (_i, [_i]),

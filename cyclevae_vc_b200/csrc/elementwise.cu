@@ -74,7 +74,14 @@ int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* o
 
 // ---------------------------------------------------------------------------------------------
 // dropout mask
-__global__ void k_dropout_mask(size_t n, float p, float keep_scale, uint64_t seed, uint64_t offset, float* __restrict__ out) {
+// `st` (optional): device-resident generator state {seed, counter, ...}: the draw uses seed = st[0] and counters
+// st[1] + offset + i, so a captured CUDA graph draws fresh numbers on every replay (cvb_state_advance moves st[1])
+__global__ void k_dropout_mask(size_t n, float p, float keep_scale, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ st,
+                               float* __restrict__ out) {
+    if (st) {
+        seed = st[0];
+        offset += st[1];
+    }
     Philox ph(seed);
     size_t n4 = (n + 3) / 4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -104,10 +111,14 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
 
 __global__ void k_reparam_concat_fwd(size_t rows, int lat, int n_code, const float* __restrict__ latp,
                                      const float* __restrict__ code, const float* __restrict__ eps,
-                                     uint64_t seed, uint64_t offset, float* __restrict__ eps_out,
-                                     float* __restrict__ out) {
+                                     uint64_t seed, uint64_t offset, const uint64_t* __restrict__ st,
+                                     float* __restrict__ eps_out, float* __restrict__ out) {
     int W = n_code + lat;
     size_t n = rows * (size_t)W;
+    if (st) {
+        seed = st[0];
+        offset += st[1];
+    }
     Philox ph(seed);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i / W;
@@ -271,9 +282,15 @@ __global__ void k_mcd_bwd(int B, int T, int D, const float* __restrict__ x, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// `st` (optional): the step count lives on the device (st[2] = steps taken so far), bias corrections computed here
 __global__ void k_adam(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                        float* __restrict__ v, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                       float gscale) {
+                       float gscale, const uint64_t* __restrict__ st) {
+    if (st) {
+        const float t = (float)(st[2] + 1);
+        bc1 = 1.0f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+    }
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float gi = g[i] * gscale;
         float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -285,29 +302,41 @@ __global__ void k_adam(size_t n, float* __restrict__ p, const float* __restrict_
     }
 }
 
+__global__ void k_state_advance(uint64_t* st, uint64_t rng_delta, uint64_t step_delta) {
+    st[1] += rng_delta;
+    st[2] += step_delta;
+}
+
 }  // namespace cvb
 
 using namespace cvb;
 
 extern "C" {
 
-int cvb_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, float* out, void* stream) {
+int cvb_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* dev_state, float* out, void* stream) {
     if (n == 0) return 0;
     CVB_REQUIRE(p >= 0.f && p < 1.f, "dropout p=%f out of [0,1)", p);
-    k_dropout_mask<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, p, 1.0f / (1.0f - p), seed, offset, out);
+    k_dropout_mask<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, p, 1.0f / (1.0f - p), seed, offset, dev_state, out);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cvb_state_advance(uint64_t* dev_state, uint64_t rng_delta, uint64_t step_delta, void* stream) {
+    CVB_REQUIRE(dev_state, "dev_state is NULL");
+    k_state_advance<<<1, 1, 0, (cudaStream_t)stream>>>(dev_state, rng_delta, step_delta);
     CVB_LAUNCH_CHECK();
     return 0;
 }
 
 int cvb_reparam_concat_fwd(int B, int T, int lat, int n_code, const float* lat_bm, const float* code_bm,
-                           const float* eps_bm, uint64_t seed, uint64_t offset, float* eps_out, float* out_bm,
+                           const float* eps_bm, uint64_t seed, uint64_t offset, const uint64_t* dev_state, float* eps_out, float* out_bm,
                            void* stream) {
     CVB_REQUIRE(B >= 0 && T >= 0 && lat > 0 && n_code >= 0, "bad dims");
     size_t rows = (size_t)B * T;
     if (rows == 0) return 0;
     CVB_REQUIRE(n_code == 0 || code_bm, "code_bm is NULL with n_code=%d", n_code);
     k_reparam_concat_fwd<<<grid_for(rows * (n_code + lat), 256), 256, 0, (cudaStream_t)stream>>>(
-        rows, lat, n_code, lat_bm, code_bm, eps_bm, seed, offset, eps_out, out_bm);
+        rows, lat, n_code, lat_bm, code_bm, eps_bm, seed, offset, dev_state, eps_out, out_bm);
     CVB_LAUNCH_CHECK();
     return 0;
 }
@@ -361,13 +390,13 @@ int cvb_mcd_l1_bwd(int B, int T, int D, const float* x_bm, int ldx, int x_off, c
 }
 
 int cvb_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                  float beta2, float eps, int step, float grad_scale, void* stream) {
+                  float beta2, float eps, int step, const uint64_t* dev_state, float grad_scale, void* stream) {
     if (n == 0) return 0;
-    CVB_REQUIRE(step >= 1, "adam step must be >= 1");
+    CVB_REQUIRE(step >= 1 || dev_state, "adam step must be >= 1");
     float bc1 = 1.0f - powf(beta1, (float)step);
     float bc2 = 1.0f - powf(beta2, (float)step);
     k_adam<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, bc1,
-                                                               sqrtf(bc2), grad_scale);
+                                                               sqrtf(bc2), grad_scale, dev_state);
     CVB_LAUNCH_CHECK();
     cvb::weights_changed();   // cached 16-bit images of parameter operands (gemm_tc.cu) are stale from here on
     return 0;

@@ -410,11 +410,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
 // ---- host ------------------------------------------------------------------------------------------------------
 // Operand images live in a per-device arena owned by the library: grow-only, bump-allocated per group of products
 // (everything is stream-ordered on the caller's stream, so the next group may overwrite it).  cvb_reserve_workspace
-// sizes it up front -- growth calls cudaFree/cudaMalloc (a device synchronisation, illegal during graph capture), so a
-// caller that captures graphs reserves first (the warm-up steps before a capture do the same implicitly).
-// Images of PARAMETER operands are kept in their own buffers until the parameters change.
+// sizes it up front; growth is a cudaMalloc (illegal while a CUDA graph is being captured: a capturing caller reserves
+// or warms up first).  An outgrown chunk is never freed: captured graphs keep replaying into the addresses they saw.
+// Images of PARAMETER operands are kept in their own buffers until the parameters change; a buffer that a captured
+// graph refers to is pinned to its operand for the life of the process.
 struct Arena {
-    uint8_t* buf = nullptr;
+    uint8_t* buf = nullptr;   // the current (largest) chunk
     size_t cap = 0;
 };
 struct ConstImage {
@@ -424,6 +425,7 @@ struct ConstImage {
     uint16_t* img = nullptr;
     size_t bytes = 0;
     unsigned long long last_use = 0;
+    bool pinned = false;
 };
 static std::mutex g_ws_mu;
 static Arena g_arena[64];
@@ -435,14 +437,15 @@ void weights_changed() {
     ++g_weights_gen;
 }
 
-static int arena_reserve(int dev, size_t bytes) {
+static int arena_reserve(int dev, size_t bytes, bool capturing) {
     Arena& a = g_arena[dev];
     if (a.cap >= bytes) return 0;
-    if (a.buf) CVB_CHECK(cudaFree(a.buf));   // synchronises: earlier products are done with it
-    a.buf = nullptr;
-    a.cap = 0;
-    const size_t want = bytes + bytes / 8 + (1u << 20);
-    CVB_CHECK(cudaMalloc(&a.buf, want));
+    CVB_REQUIRE(!capturing, "the operand-image arena must grow (%zu -> %zu bytes) while a CUDA graph is being captured: run the "
+                            "step once before the capture or call cvb_reserve_workspace", a.cap, bytes);
+    const size_t want = bytes + bytes / 4 + (1u << 20);
+    uint8_t* nb = nullptr;
+    CVB_CHECK(cudaMalloc(&nb, want));   // the outgrown chunk stays allocated (captured graphs may still address it)
+    a.buf = nb;
     a.cap = want;
     return 0;
 }
@@ -452,7 +455,7 @@ int reserve_workspace(size_t bytes) {
     CVB_CHECK(cudaGetDevice(&dev));
     CVB_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(g_ws_mu);
-    return arena_reserve(dev, bytes);
+    return arena_reserve(dev, bytes, false);
 }
 
 bool gemm_tc_eligible(int M, int N, int K) { return M >= 1 && N >= 1 && K >= 16 && (double)M * N * K >= 2.0e5; }
@@ -544,12 +547,26 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
     // place the images: cached parameter images in their own buffers, the rest bump-allocated in the arena
     SplitArgs sa;
     memset(&sa, 0, sizeof(sa));
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    CVB_CHECK(cudaStreamIsCapturing(s, &cap_st));
+    const bool capturing = cap_st != cudaStreamCaptureStatusNone;
     {
         std::lock_guard<std::mutex> lk(g_ws_mu);
+        // a parameter image needs a slot that no captured graph owns; without one the operand is split like any other
+        for (int j = 0; j < n_ops; ++j) {
+            if (!is_const[j]) continue;
+            const GtOperand& o = ops[j];
+            bool ok = false;
+            for (auto& c : g_const[dev])
+                if ((c.p == o.p && c.ld == o.ld && c.rows == o.rows && c.K == o.K && c.kmajor == o.kmajor && c.f16 == o.f16) ||
+                    (!c.pinned && !(capturing && c.bytes < image_bytes(o.rows, o.K))))
+                    ok = true;
+            if (!ok) is_const[j] = false;
+        }
         size_t need = 0;
         for (int j = 0; j < n_ops; ++j)
             if (!is_const[j]) need += image_bytes(ops[j].rows, ops[j].K);
-        if (int rc = arena_reserve(dev, need)) return rc;
+        if (int rc = arena_reserve(dev, need, capturing)) return rc;
         size_t off = 0;
         int blocks = 0;
         for (int j = 0; j < n_ops; ++j) {
@@ -560,10 +577,10 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
                 ConstImage* slot = nullptr;
                 for (auto& c : g_const[dev])
                     if (c.p == o.p && c.ld == o.ld && c.rows == o.rows && c.K == o.K && c.kmajor == o.kmajor && c.f16 == o.f16) slot = &c;
-                if (!slot) {   // least recently used slot
-                    slot = &g_const[dev][0];
+                if (!slot) {   // least recently used slot that no captured graph refers to
                     for (auto& c : g_const[dev])
-                        if (c.last_use < slot->last_use) slot = &c;
+                        if (!c.pinned && !(capturing && c.bytes < bytes) && (!slot || c.last_use < slot->last_use)) slot = &c;
+                    CVB_REQUIRE(slot, "internal: no parameter-image slot");
                     if (slot->bytes < bytes) {
                         if (slot->img) CVB_CHECK(cudaFree(slot->img));
                         slot->img = nullptr;
@@ -575,6 +592,7 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
                     slot->gen = 0;
                 }
                 slot->last_use = ++g_use_clock;
+                if (capturing) slot->pinned = true;
                 o.img = slot->img;
                 fresh = slot->gen != g_weights_gen;
                 slot->gen = g_weights_gen;

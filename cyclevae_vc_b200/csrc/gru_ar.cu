@@ -17,8 +17,8 @@ namespace cvb {
 constexpr int U = 8;        // hidden units per CTA
 constexpr int NT = 256;     // threads per CTA (one warp per unit in forward)
 constexpr int BT = 128;     // batch tile (4 rows per lane)
-constexpr int KC = 64;      // K chunk staged per cp.async group
-constexpr int KP = KC + 4;  // padded row pitch of the staging tile (conflict-free LDS.128)
+// KC = K chunk staged per cp.async group (template parameter: 64, or 16 when the wider staging tile does not fit next to
+// a wide output layer, e.g. the encoder at lat_dim 50 / 64); KP = KC + 4 = padded row pitch (conflict-free LDS.128)
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
     acc = fmaf(a.x, b.x, acc);
@@ -28,8 +28,10 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 }
 
 // stage rows [b0, b0+BT) x cols [k0, k0+KC) of src [Brows, K] into dst [BT][KP]; zero-fill outside
+template <int KC>
 __device__ __forceinline__ void stage_chunk(float* dst, const float* __restrict__ src, int b0, int Brows, int K, int k0,
                                             bool vec4, int nrows) {
+    constexpr int KP = KC + 4;
     if (vec4) {
         for (int i = threadIdx.x; i < nrows * (KC / 4); i += NT) {
             int row = i / (KC / 4), q = i - row * (KC / 4);
@@ -70,7 +72,9 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ part, 
     }
 }
 
+template <int KC>
 __global__ void __launch_bounds__(NT, 1) k_gru_fwd(GruFwdArgs a) {
+    constexpr int KP = KC + 4;
     extern __shared__ __align__(16) float smem[];
     const int B = a.B, T = a.T, H = a.H, out = a.out;
     const int Hp = (H + KC - 1) / KC * KC;
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(NT, 1) k_gru_fwd(GruFwdArgs a) {
             const int nb = min(BT, B - b0);
             const int nrows = (nb + 31) & ~31;  // rows the 4-per-lane mapping touches
             __syncthreads();  // previous tile's sO / sY / sH readers are done
-            stage_chunk(sH, hprev, b0, B, H, 0, vec4, nrows);
+            stage_chunk<KC>(sH, hprev, b0, B, H, 0, vec4, nrows);
             cp_async_commit();
             for (int i = threadIdx.x; i < nb * out; i += NT) {
                 int bl = i / out, o = i - bl * out;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) k_gru_fwd(GruFwdArgs a) {
             }
             float ar[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f}, an[4] = {0.f, 0.f, 0.f, 0.f};
             for (int kc = 0; kc < nkc; ++kc) {
-                if (kc + 1 < nkc) stage_chunk(sH + ((kc + 1) & 1) * BT * KP, hprev, b0, B, H, (kc + 1) * KC, vec4, nrows);
+                if (kc + 1 < nkc) stage_chunk<KC>(sH + ((kc + 1) & 1) * BT * KP, hprev, b0, B, H, (kc + 1) * KC, vec4, nrows);
                 cp_async_commit();
                 cp_async_wait<1>();
                 __syncthreads();
@@ -211,7 +215,9 @@ __global__ void __launch_bounds__(NT, 1) k_gru_fwd(GruFwdArgs a) {
 }
 
 // BPTT.  Warp w: unit pair (w&3), K half (w>>2); lane: 4 batch rows.
+template <int KC>
 __global__ void __launch_bounds__(NT, 1) k_gru_bwd(GruBwdArgs a) {
+    constexpr int KP = KC + 4;
     extern __shared__ __align__(16) float smem[];
     const int B = a.B, T = a.T, H = a.H, out = a.out;
     const int K3 = 3 * H;
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(NT, 1) k_gru_bwd(GruBwdArgs a) {
             __syncthreads();
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             if (have_next) {
-                stage_chunk(sG, gnext, b0, B, K3, 0, vec4, nrows);
+                stage_chunk<KC>(sG, gnext, b0, B, K3, 0, vec4, nrows);
                 cp_async_commit();
             }
             if (t >= 0) {
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(NT, 1) k_gru_bwd(GruBwdArgs a) {
             }
             if (have_next) {
                 for (int kc = 0; kc < nkc; ++kc) {
-                    if (kc + 1 < nkc) stage_chunk(sG + ((kc + 1) & 1) * BT * KP, gnext, b0, B, K3, (kc + 1) * KC, vec4, nrows);
+                    if (kc + 1 < nkc) stage_chunk<KC>(sG + ((kc + 1) & 1) * BT * KP, gnext, b0, B, K3, (kc + 1) * KC, vec4, nrows);
                     cp_async_commit();
                     cp_async_wait<1>();
                     __syncthreads();
@@ -373,13 +379,15 @@ __global__ void __launch_bounds__(NT, 1) k_gru_bwd(GruBwdArgs a) {
     }
 }
 
-static size_t fwd_smem_bytes(int H, int out) {
+static size_t fwd_smem_bytes(int H, int out, int KC) {
+    const size_t KP = KC + 4;
     size_t Hp = (size_t)ceil_div(H, KC) * KC;
     size_t outp = out | 1;
     size_t fl = 3 * U * Hp + 3 * U * out + (size_t)out * U + BT * outp + ((U * BT + 3) & ~3) + 4 + 2 * BT * KP;
     return fl * sizeof(float);
 }
-static size_t bwd_smem_bytes(int H, int out) {
+static size_t bwd_smem_bytes(int H, int out, int KC) {
+    const size_t KP = KC + 4;
     size_t K3p = (size_t)ceil_div(3 * H, KC) * KC;
     size_t outp = out | 1;
     size_t fl = U * K3p + 3 * U * out + (size_t)out * U + BT * outp + U * BT + 3 * U * BT + 4 + 2 * BT * KP;
@@ -406,13 +414,22 @@ static int launch_coop(void (*kern)(Args), Args& a, int grid, size_t smem, cudaS
     return 0;
 }
 
+// the wide staging tile when it fits next to the resident weights and the output-layer buffers, else the narrow one
+static bool fits(size_t bytes) {
+    DeviceInfo di;
+    return get_device_info(&di) == 0 && bytes <= (size_t)di.max_smem_optin;
+}
 int gru_ar_fwd_exact(GruFwdArgs& a, cudaStream_t s) {
     if (a.T <= 0 || a.B <= 0) return 0;
-    return launch_coop(k_gru_fwd, a, gru_exact_grid(a.H), fwd_smem_bytes(a.H, a.out), s, "gru_ar_fwd", CVB_PROF_GRU_FWD);
+    if (fits(fwd_smem_bytes(a.H, a.out, 64)))
+        return launch_coop(k_gru_fwd<64>, a, gru_exact_grid(a.H), fwd_smem_bytes(a.H, a.out, 64), s, "gru_ar_fwd", CVB_PROF_GRU_FWD);
+    return launch_coop(k_gru_fwd<16>, a, gru_exact_grid(a.H), fwd_smem_bytes(a.H, a.out, 16), s, "gru_ar_fwd", CVB_PROF_GRU_FWD);
 }
 int gru_ar_bwd_exact(GruBwdArgs& a, cudaStream_t s) {
     if (a.T <= 0 || a.B <= 0) return 0;
-    return launch_coop(k_gru_bwd, a, gru_exact_grid(a.H), bwd_smem_bytes(a.H, a.out), s, "gru_ar_bwd", CVB_PROF_GRU_BWD);
+    if (fits(bwd_smem_bytes(a.H, a.out, 64)))
+        return launch_coop(k_gru_bwd<64>, a, gru_exact_grid(a.H), bwd_smem_bytes(a.H, a.out, 64), s, "gru_ar_bwd", CVB_PROF_GRU_BWD);
+    return launch_coop(k_gru_bwd<16>, a, gru_exact_grid(a.H), bwd_smem_bytes(a.H, a.out, 16), s, "gru_ar_bwd", CVB_PROF_GRU_BWD);
 }
 
 }  // namespace cvb

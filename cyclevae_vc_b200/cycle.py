@@ -188,21 +188,21 @@ class FlatAdam:
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
             p.requires_grad_(True)
+            p._cvb_grad_sink = True   # GRU_RNN's backward adds its gradients straight into p.grad (gru_vae._GruRnnFn)
         self.params, self.n = params, n
         self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
 
     def zero_grad(self):
         self.grad.zero_()
 
-    def step(self, grad_scale: float = 1.0):
+    def step(self, grad_scale: float = 1.0, dev_state: Optional[torch.Tensor] = None):
+        """dev_state (gru_vae.DeviceRng.state): take the step count from the device (state[2] + 1) instead of the host --
+        the form a captured CUDA graph needs; the caller advances it (DeviceRng.end_step(step_delta=1))."""
         self.t += 1
         with torch.cuda.device(self.flat.device):
-            self._launch(grad_scale)
-
-    def _launch(self, grad_scale):
-        check(lib.cvb_adam_step(self.n, ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.lr,
-                                self.betas[0], self.betas[1], self.eps, self.t, grad_scale,
-                                torch.cuda.current_stream().cuda_stream), "cvb_adam_step")
+            check(lib.cvb_adam_step(self.n, ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.lr,
+                                    self.betas[0], self.betas[1], self.eps, self.t, None if dev_state is None else dev_state.data_ptr(),
+                                    grad_scale, torch.cuda.current_stream().cuda_stream), "cvb_adam_step")
 
 
 def allreduce_grads(flat_grad: torch.Tensor) -> None:
@@ -212,6 +212,78 @@ def allreduce_grads(flat_grad: torch.Tensor) -> None:
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+
+
+class CycleStep:
+    """one optimisation step of the trainer (train_*.py:1298-1420: zero_grad, the 5 x n_cyc GRU_RNN
+    passes, loss assembly, backward, [gradient all-reduce], Adam) as ONE call.  Forward + losses + BPTT are captured in a
+    CUDA graph and replayed; dropout masks and latent noise are drawn from a device-resident Philox state
+    (gru_vae.DeviceRng), the Adam step count lives on the device too, parameter gradients are accumulated by the kernels
+    straight into the flat gradient buffer, and the only host work per step is one graph launch, the all-reduce (N > 1)
+    and the Adam launch.  Inputs are copied into static device buffers (the copies are part of the caller's stream).
+
+    state=None runs first-chunk semantics (initial y_in, h_in = None: train_*.py:1326-1338) -- the benchmark workload.
+    flens: int32 [B] frames of each utterance that count in the losses (flen_acc; 0 = utterance not selected)."""
+
+    def __init__(self, enc: gv.GRU_RNN, dec: gv.GRU_RNN, opt: FlatAdam, *, B: int, T: int, n_cyc: int, lat_dim: int, stdim: int,
+                 n_spk: int, y0_enc: torch.Tensor, y0_dec: torch.Tensor, graph: bool = True, kl_cv_quirk: bool = True):
+        dev = opt.flat.device
+        self.enc, self.dec, self.opt = enc, dec, opt
+        self.n_cyc, self.lat_dim, self.stdim, self.kl_cv_quirk = n_cyc, lat_dim, stdim, kl_cv_quirk
+        self.x = torch.zeros(B, T, enc.in_dim, device=dev)
+        self.cv = torch.zeros(B, T, stdim, device=dev)
+        self.sc = torch.zeros(B, T, n_spk, device=dev)
+        self.tc = torch.zeros(B, T, n_spk, device=dev)
+        self.flens = torch.full((B,), T, dtype=torch.int32, device=dev)
+        self.y0_enc, self.y0_dec = y0_enc.to(dev).contiguous(), y0_dec.to(dev).contiguous()
+        self.loss = torch.zeros((), device=dev)
+        self.rng = gv.DeviceRng(dev)
+        self.sel = list(range(B))
+        self.graph = None
+        self.kernels_per_replay = 0
+        if graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):   # warm-up on a side stream: sizes every workspace before the capture
+                for _ in range(2):
+                    self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = lib.cvb_launch_count()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.kernels_per_replay = int(lib.cvb_launch_count() - n0)   # this library's kernels inside one replay
+
+    def _body(self):
+        # the parameters are new at every step: the first product that uses a parameter matrix refreshes its 16-bit image
+        # (inside the captured graph too), the other passes of the step reuse it
+        lib.cvb_weights_changed()
+        self.opt.zero_grad()
+        with gv.device_rng(self.rng):
+            out, _ = cyc_forward(self.enc, self.dec, x=self.x, cv=self.cv, src_code=self.sc, trg_code=self.tc, n_cyc=self.n_cyc,
+                                 lat_dim=self.lat_dim, stdim=self.stdim, y0_enc=self.y0_enc, y0_dec=self.y0_dec, do=True)
+            loss, _ = cyc_loss(out, self.x, n_cyc=self.n_cyc, lat_dim=self.lat_dim, stdim=self.stdim, flen_acc=None,
+                               select_utt_idx=self.sel, kl_cv_quirk=self.kl_cv_quirk, flens_dev=self.flens)
+            loss.backward()
+        self.rng.end_step()
+        self.loss.copy_(loss.detach())
+
+    def step(self, x, cv, src_code, trg_code, flens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step on this batch; returns the (device) loss scalar of the step."""
+        for dst, src in ((self.x, x), (self.cv, cv), (self.sc, src_code), (self.tc, trg_code)):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        if flens is not None:
+            self.flens.copy_(flens, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        allreduce_grads(self.opt.grad)
+        self.opt.step(dev_state=self.rng.state)
+        check(lib.cvb_state_advance(self.rng.state.data_ptr(), 0, 1, torch.cuda.current_stream().cuda_stream), "cvb_state_advance")
+        return self.loss
 
 
 def shard_utterances(n_utt: int, rank: int, world: int) -> Tuple[int, int]:

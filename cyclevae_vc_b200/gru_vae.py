@@ -31,7 +31,7 @@ from . import _lib
 from ._lib import CvbNet, CvbNetGrads, check, lib, ptr
 
 __all__ = ["initialize", "TwoSidedDilConv1d", "GRU_RNN", "TWFSEloss", "sampling_vae_batch", "sampling_vae", "loss_vae",
-           "reparam_concat", "kl_per_utt", "mcd_l1_per_utt", "draw_dropout_masks", "LOG_VAR_FLOOR"]
+           "reparam_concat", "kl_per_utt", "mcd_l1_per_utt", "draw_dropout_masks", "LOG_VAR_FLOOR", "DeviceRng", "device_rng"]
 
 LOG_VAR_FLOOR = -13.815510557964274104107948728106  # gru_vae.py:412
 MAX_ROWS_PER_LAUNCH = 128   # batch rows of one persistent recurrence launch (= the M of a tcgen05 MMA)
@@ -52,9 +52,51 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 # CPU generator (the generator the reference's sampling_vae_batch consumes, gru_vae.py:91), so
 # torch.manual_seed() makes device noise and dropout reproducible; no device sync is involved.
 class _Rng:
+    device = None   # a DeviceRng while one is active (device_rng context): draws take their key from device memory
+
     @staticmethod
     def take(n_counters: int):
-        return int(torch.randint(0, 2 ** 62, (1,)).item()), 0
+        """-> (seed, offset, dev_state pointer | None) for one draw that consumes `n_counters` Philox counters."""
+        d = _Rng.device
+        if d is not None:
+            return 0, d.take(n_counters), d.state.data_ptr()
+        return int(torch.randint(0, 2 ** 62, (1,)).item()), 0, None
+
+
+class DeviceRng:
+    """Device-resident generator / step state, uint64[4] = {Philox seed, Philox counter, optimiser steps taken, 0}
+    (include/cyclevae_b200.h, cvb_state_advance).  Inside `with device_rng(rng):` every dropout-mask / noise draw reads
+    its key from this buffer and only a fixed per-step base offset comes from the host, so a whole optimisation step can
+    be captured in a CUDA graph and still draw fresh numbers on every replay.  The seed comes from torch's CPU
+    generator once (torch.manual_seed makes runs reproducible)."""
+
+    def __init__(self, device):
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.state = torch.tensor([seed, 0, 0, 0], dtype=torch.int64, device=device)
+        self.base = 0
+
+    def take(self, n_counters: int) -> int:
+        b = self.base
+        self.base += int(n_counters)
+        return b
+
+    def end_step(self, step_delta: int = 0):
+        """Advance the device counter past this step's draws (and the optimiser step count by step_delta)."""
+        check(lib.cvb_state_advance(self.state.data_ptr(), self.base, int(step_delta), _stream()), "cvb_state_advance")
+        self.base = 0
+
+
+class device_rng:
+    def __init__(self, rng: Optional[DeviceRng]):
+        self.rng, self.prev = rng, None
+
+    def __enter__(self):
+        self.prev, _Rng.device = _Rng.device, self.rng
+        return self.rng
+
+    def __exit__(self, *exc):
+        _Rng.device = self.prev
+        return False
 
 
 def initialize(m):
@@ -142,15 +184,22 @@ class _GruRnnFn(torch.autograd.Function):
         dh_in = torch.empty(B, mod.hidden_units, device=dev) if (ctx.has_h and need[6]) else None
         grads = CvbNetGrads()
         gts = []
-        for (field, idx), p, nd in zip(mod._param_fields, params, need[9:]):
-            g = torch.empty_like(p) if nd else None
-            gts.append(g)
+        # Parameters whose .grad lives in a caller-owned flat buffer (cycle.FlatAdam marks them): the kernels ADD straight
+        # into it (accumulate = 1) and autograd gets None -- no temporary gradient tensors, no per-parameter add kernels.
+        live = mod._param_list()
+        sink = all((not nd) or (getattr(q, "_cvb_grad_sink", False) and q.grad is not None and q.grad.is_contiguous())
+                   for q, nd in zip(live, need[9:]))
+        for (field, idx), p, q, nd in zip(mod._param_fields, params, live, need[9:]):
+            g = None
+            if nd:
+                g = q.grad if sink else torch.empty_like(p)
+            gts.append(None if sink else g)
             if g is not None:
                 if idx is None:
                     setattr(grads, field, ptr(g))
                 else:
                     getattr(grads, field)[idx] = ptr(g)
-        grads.accumulate = 0
+        grads.accumulate = 1 if sink else 0
         scratch = mod._scratch(lib.cvb_scratch_floats(netp, B, T, 1), dev)
         check(lib.cvb_gru_rnn_backward(netp, B, T, ptr(x), ptr(mask_conv_tm), ptr(mask_gru_tm), ctx.head_mode, ctx.lat_dim,
                                        None, ptr(d_trj), ptr(d_y_last), ptr(d_h_last), ptr(fe_ws), ptr(rec_ws), ptr(scratch),
@@ -339,8 +388,8 @@ def draw_dropout_masks(B, T, conv_dim, hidden, p, device):
     n1, n2 = T * B * conv_dim, T * B * hidden
     with torch.cuda.device(device):
         buf = torch.empty(n1 + n2, dtype=torch.float32, device=device)
-        seed, off = _Rng.take((n1 + n2 + 3) // 4)
-        check(lib.cvb_dropout_mask(n1 + n2, float(p), seed, off, ptr(buf), _stream()), "cvb_dropout_mask")
+        seed, off, st = _Rng.take((n1 + n2 + 3) // 4)
+        check(lib.cvb_dropout_mask(n1 + n2, float(p), seed, off, st, ptr(buf), _stream()), "cvb_dropout_mask")
     return buf[:n1].view(T, B, conv_dim), buf[n1:].view(T, B, hidden)
 
 
@@ -352,11 +401,11 @@ class _ReparamConcatFn(torch.autograd.Function):
         n_code = 0 if code is None else code.shape[-1]
         out = torch.empty(B, T, n_code + lat_dim, dtype=torch.float32, device=lat.device)
         eps_out = None
-        seed = off = 0
+        seed, off, st = 0, 0, None
         if eps is None:
             eps_out = torch.empty(B, T, lat_dim, dtype=torch.float32, device=lat.device)
-            seed, off = _Rng.take((B * T * lat_dim + 3) // 4)
-        check(lib.cvb_reparam_concat_fwd(B, T, lat_dim, n_code, ptr(lat), ptr(code), ptr(eps), seed, off, ptr(eps_out),
+            seed, off, st = _Rng.take((B * T * lat_dim + 3) // 4)
+        check(lib.cvb_reparam_concat_fwd(B, T, lat_dim, n_code, ptr(lat), ptr(code), ptr(eps), seed, off, st, ptr(eps_out),
                                          ptr(out), _stream()), "cvb_reparam_concat_fwd")
         ctx.save_for_backward(lat, eps if eps is not None else eps_out)
         ctx.n_code, ctx.lat_dim = n_code, lat_dim

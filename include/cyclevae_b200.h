@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 8
+#define CVB_ABI_VERSION 9
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -134,10 +134,11 @@ int cvb_frontend_fwd(const cvb_net* net, int B, int T, const float* x_bm, const 
 /* ---- sampling_vae_batch + torch.cat((code, z), 2) fused (gru_vae.py:85-98; train_*.py:1302) ---
  * lat_bm [B,T,2*lat] = [mu | log-var]; eps_bm [B,T,lat] or NULL (then N(0,1) is drawn in-kernel
  * from Philox4x32-10 keyed by (seed, offset) and, if eps_out != NULL, stored for backward);
- * code_bm [B,T,n_code] or NULL with n_code == 0.  out_bm [B,T,n_code+lat] = [code | mu+exp(s/2)eps] */
+ * code_bm [B,T,n_code] or NULL with n_code == 0.  out_bm [B,T,n_code+lat] = [code | mu+exp(s/2)eps]
+ * dev_state: optional device-resident generator state (see cvb_state_advance); NULL = use (seed, offset) as given */
 int cvb_reparam_concat_fwd(int B, int T, int lat, int n_code, const float* lat_bm,
                            const float* code_bm, const float* eps_bm, uint64_t seed, uint64_t offset,
-                           float* eps_out, float* out_bm, void* stream);
+                           const uint64_t* dev_state, float* eps_out, float* out_bm, void* stream);
 /* d_out_bm [B,T,n_code+lat] -> d_lat_bm [B,T,2*lat] (code gets no gradient) */
 int cvb_reparam_concat_bwd(int B, int T, int lat, int n_code, const float* lat_bm,
                            const float* eps_bm, const float* d_out_bm, float* d_lat_bm, void* stream);
@@ -164,12 +165,19 @@ int cvb_mcd_l1_bwd(int B, int T, int D, const float* x_bm, int ldx, int x_off, c
 
 /* ---- dropout masks (replacement of nn.Dropout's Bernoulli draw, gru_vae.py:303-304,312-313) ---
  * out[i] = (u_i >= p) ? 1/(1-p) : 0 with u from Philox4x32-10(seed, offset + i/4) */
-int cvb_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, float* out, void* stream);
+int cvb_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* dev_state, float* out, void* stream);
+
+/* ---- device-resident step state: uint64 dev_state[4] = {Philox seed, Philox counter, optimiser steps taken, reserved}.
+ * When a draw is given dev_state it uses seed = dev_state[0] and counters dev_state[1] + offset + i (offset = the
+ * draw's fixed base inside one step); cvb_adam_step with dev_state takes its step count from dev_state[2] + 1.
+ * cvb_state_advance adds to the counter and the step count ON THE DEVICE, so one optimisation step captured in a CUDA
+ * graph draws fresh dropout masks / noise and applies the right bias correction on every replay. */
+int cvb_state_advance(uint64_t* dev_state, uint64_t rng_delta, uint64_t step_delta, void* stream);
 
 /* ---- fused Adam over a flat fp32 buffer (caller = train_*.py:377,1420 torch.optim.Adam) ------ */
 int cvb_adam_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                  float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                  void* stream);
+                  float lr, float beta1, float beta2, float eps, int step, const uint64_t* dev_state,
+                  float grad_scale, void* stream);
 
 /* ---- parameter residency --------------------------------------------------------------------------
  * The dense products keep 16-bit operand images of PARAMETER matrices (W_x ...) across calls.  They are refreshed

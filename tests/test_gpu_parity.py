@@ -941,3 +941,63 @@ def test_wide_latent_encoder_eval_and_training(cvb):
     assert _maxabs(o.double(), o_r.detach()) < TOL
     ref = Pg["gru.weight_hh_l0"].grad
     assert _maxabs(m.gru.weight_hh_l0.grad.double(), ref) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_fused_step_driver_graph_replay(cvb):
+    """SURVEY.md §8(f)-1, cycle.CycleStep: one optimisation step (10 GRU_RNN passes, losses, BPTT, Adam) replayed as a CUDA
+    graph.  (i) a replay draws FRESH dropout masks / latent noise (device-resident Philox state) and applies the right Adam
+    bias correction (device-resident step count); (ii) from the same generator state and parameters the replayed graph and
+    the kernel-by-kernel launch give bit-identical losses and parameters; (iii) gradients accumulated by the kernels
+    straight into the flat buffer equal autograd's own accumulation."""
+    from cyclevae_vc_b200 import cycle, synth
+    lat, stdim, B, T, n_cyc = 32, 4, 6, 20, 2
+    dev = torch.device("cuda")
+
+    def build():
+        enc, dec, y0d1 = synth.build_models(1024, lat, 2, 50, stdim, seed=1, device=dev)
+        enc.train(); dec.train()
+        return enc, dec, y0d1
+
+    x, cv, sc, tc = (t.to(dev) for t in synth.make_batch(B, T, 5, 2, 50))
+    y0e = torch.zeros(B, 1, 2 * lat, device=dev)
+    runs = {}
+    for mode in ("graph", "eager"):
+        enc, dec, y0d1 = build()
+        y0d = y0d1.to(dev).repeat(B, 1, 1).contiguous()
+        opt = cycle.FlatAdam(cycle.trainable_parameters(enc, dec), lr=1e-3)
+        torch.manual_seed(77)
+        cs = cycle.CycleStep(enc, dec, opt, B=B, T=T, n_cyc=n_cyc, lat_dim=lat, stdim=stdim, n_spk=2, y0_enc=y0e, y0_dec=y0d,
+                             graph=(mode == "graph"))
+        assert (cs.graph is not None) == (mode == "graph")
+        cs.rng.state[1:3] = 0                      # the graph's warm-up steps consumed counters: same start for both modes
+        losses = []
+        for _ in range(3):
+            losses.append(float(cs.step(x, cv, sc, tc).item()))
+        torch.cuda.synchronize()
+        runs[mode] = (losses, opt.flat.clone(), cs.rng.state.clone())
+    lg, pg, sg = runs["graph"]
+    le, pe, se = runs["eager"]
+    assert len(set(lg)) == 3, "every replay must draw new masks / noise"
+    assert lg == le and torch.equal(pg, pe) and torch.equal(sg, se)
+    assert int(sg[2]) == 3 and int(sg[1]) > 0
+    # (iii) sink gradients == autograd-accumulated gradients on identical masks / noise
+    enc_a, dec_a, y0d1 = build()
+    enc_b, dec_b, _ = build()
+    y0d = y0d1.to(dev).repeat(B, 1, 1).contiguous()
+    for m in (enc_a, dec_a, enc_b, dec_b):
+        for k, p in m.named_parameters():
+            p.requires_grad_(not k.startswith("scale_"))
+    opt = cycle.FlatAdam(cycle.trainable_parameters(enc_b, dec_b), lr=1e-3)
+    eps = [[e.to(dev) for e in ec] for ec in orc.synth_noise(B, T, lat, n_cyc, 9)]
+    masks = [[(a.to(dev), b.to(dev)) for a, b in mc] for mc in orc.synth_masks(B, T, orc.encoder_spec(54, lat, 1024), orc.decoder_spec(lat, 2, 50, 1024), n_cyc, 9)]
+    grads = []
+    for enc, dec in ((enc_a, dec_a), (enc_b, dec_b)):
+        if enc is enc_b:
+            opt.zero_grad()
+        out, _ = cycle.cyc_forward(enc, dec, x=x, cv=cv, src_code=sc, trg_code=tc, n_cyc=n_cyc, lat_dim=lat, stdim=stdim, y0_enc=y0e,
+                                   y0_dec=y0d, do=True, eps=eps, masks=masks)
+        loss, _ = cycle.cyc_loss(out, x, n_cyc=n_cyc, lat_dim=lat, stdim=stdim, flen_acc=[T] * B, select_utt_idx=list(range(B)))
+        loss.backward()
+        grads.append([p.grad.clone() for p in cycle.trainable_parameters(enc, dec)])
+    for ga, gb in zip(*grads):
+        assert _maxabs(ga, gb) <= 2e-6 * max(1e-3, float(ga.abs().max()))
