@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcyclevae_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -72,9 +72,6 @@ PROTOTYPES = {
     "cvb_profile_reset": (_i, []),
     "cvb_profile_summary": (_i, [_i, C.POINTER(C.c_float), C.POINTER(_i)]),
     "cvb_launch_count": (C.c_longlong, []),
-    "cvb_selftest_umma": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
-    "cvb_bench_ingest": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "cvb_bench_allgather": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cvb_gemm_tc": (_i, [_i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp]),
     "cvb_gemm": (_i, [_i, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _f, _vp, _i, _vp]),
 }

@@ -42,6 +42,11 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
 static inline size_t round_up_sz(size_t a, size_t b) { return ceil_div_sz(a, b) * b; }
 
+// true when the persistent cluster kernels should be launched WITHOUT the cooperative attribute: CVB_TC_NOCOOP=1, or the
+// process runs under Nsight Compute (which cannot replay a cooperative cluster launch: the capture dies at the first
+// one).  Co-residency of the whole grid is then guaranteed by the occupancy query on an otherwise idle device only.
+bool launch_without_coop();
+
 struct DeviceInfo {
     int n_sm;
     int max_smem_optin;
@@ -96,11 +101,16 @@ struct GemmDesc {
     float alpha = 1.f;
     bool beta1 = false;
     bool a_const = false, b_const = false;   // the operand is a PARAMETER: its 16-bit image is kept until weights_changed()
+    // optional output map of the fused front-end: product row r = b * map_Tp + t is stored at row t * map_B + b of C
+    // (time-major) when t < map_T, dropped otherwise, and multiplied element-wise by mask (same layout as C) if given
+    int map_Tp = 0, map_T = 0, map_B = 0;
+    const float* mask = nullptr;
     bool f16 = true;             // fp16 hi/lo operands (forward products) or bf16 hi/lo (gradient products)
 };
 // up to 6 independent products in ONE persistent launch (their tiles are walked back to back; list long-K products first)
 int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n);
 void weights_changed();                 // invalidates the cached images of parameter operands
+unsigned long long weights_generation();   // bumped by weights_changed()
 int reserve_workspace(size_t bytes);    // pre-sizes the operand-image arena of the current device
 
 // elementwise / small kernels, elementwise.cu

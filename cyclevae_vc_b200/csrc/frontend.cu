@@ -9,6 +9,18 @@
 // flattened grid a tap is a row-shifted view, so each tap is ONE dense product over all R rows
 // (no im2col, no per-utterance batching); rows whose taps cross an utterance boundary hold finite
 // values that no valid output ever reads.
+//
+// COMPOSED path (every shape the tensor-core GEMM takes): the conv stack has no non-linearity, so L layers are ONE
+// k^L-tap conv  xc[t] = b_eff + sum_m E[:, m, :] x^[t + m - pad]  (verified 5.5e-7).  Forward is
+//   k_pad_scale_all (x -> normalised, zero-padded grid)  ->  ONE product over the virtual im2col of that grid whose
+//   epilogue adds b_eff, applies the dropout mask and stores time-major xc
+// -- no per-layer grids, no compaction pass.  E and b_eff are derived parameters: composed by tiny products when the
+// weights change (once per optimiser step, shared by every pass) and cached.  Backward: dE = dxc'^T im2col(x^), the
+// input gradient from G = dxc' E gathered back over the taps, and the chain rule from (dE, db_eff) to the per-layer
+// (dW_l, db_l) in parameter space (a few C_l x C_l products).  The layer-by-layer path below remains for shapes that
+// stay on cuBLAS (tiny nets, CVB_GEMM=cublas).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cvb {
@@ -46,10 +58,24 @@ static FeGeom fe_geom(const cvb_net* n, int B, int T) {
     return g;
 }
 
-size_t frontend_ws_floats(const cvb_net* n, int B, int T) { return fe_geom(n, B, T).total; }
-size_t frontend_xc_offset(const cvb_net* n, int B, int T) { return fe_geom(n, B, T).xc_off; }
-// floats of the backward's gradient grid (d buf_0..d buf_L) + one repacked weight-gradient
+// composed path (below): fe_ws = [normalised padded grid + slack | xc]
+static bool fe_composed(const cvb_net* n, int B, int T);
+static size_t fec_xp_floats(const cvb_net* n, int B, int T);
+static size_t fec_bwd_scratch_floats(const cvb_net* n, int B, int T);
+
+size_t frontend_xc_offset(const cvb_net* n, int B, int T) {
+    return fe_composed(n, B, T) ? fec_xp_floats(n, B, T) : fe_geom(n, B, T).xc_off;
+}
+size_t frontend_ws_floats(const cvb_net* n, int B, int T) {
+    if (!fe_composed(n, B, T)) return fe_geom(n, B, T).total;
+    return fec_xp_floats(n, B, T) + round_up_sz((size_t)B * T * conv_dim(n), 4);
+}
+static size_t layers_bwd_scratch_floats(const cvb_net* n, int B, int T);
 size_t frontend_bwd_scratch_floats(const cvb_net* n, int B, int T) {
+    return fe_composed(n, B, T) ? fec_bwd_scratch_floats(n, B, T) : layers_bwd_scratch_floats(n, B, T);
+}
+// floats of the backward's gradient grid (d buf_0..d buf_L) + one repacked weight-gradient
+static size_t layers_bwd_scratch_floats(const cvb_net* n, int B, int T) {
     FeGeom g = fe_geom(n, B, T);
     size_t mx = 0;
     size_t gmx = 0;   // G = dout Wcat of a tap-fused layer: [rows][k*ci]
@@ -210,12 +236,420 @@ static inline int grid1d(size_t n) {
     return (int)(g > 148 * 8 ? 148 * 8 : (g < 1 ? 1 : g));
 }
 
+// ================================================================================================
+// composed path
+// ================================================================================================
+struct FeC {   // geometry of the composed front-end
+    int k, L, in, pad, KT, Tp, CL;
+    size_t R, rows;      // padded-grid rows; product rows (windows that stay inside the grid)
+    size_t xp_floats;    // fe_ws: the padded grid (+ KT rows of slack)
+};
+static FeC fec_geom(const cvb_net* n, int B, int T) {
+    FeC g;
+    g.k = n->kernel_size;
+    g.L = n->n_conv;
+    g.in = n->in_dim;
+    g.KT = ipow(g.k, g.L);
+    g.pad = (g.KT - 1) / 2;
+    g.Tp = T + 2 * g.pad;
+    g.CL = g.in * g.KT;
+    g.R = (size_t)B * g.Tp;
+    g.rows = g.R - (size_t)(g.KT - 1);
+    g.xp_floats = round_up_sz((g.R + g.KT) * g.in, 4);
+    return g;
+}
+static size_t fec_xp_floats(const cvb_net* n, int B, int T) { return fec_geom(n, B, T).xp_floats; }
+static bool fe_composed(const cvb_net* n, int B, int T) {
+    if (B <= 0 || T <= 0) return false;
+    FeC g = fec_geom(n, B, T);
+    return want_tc_gemm() && g.R > (size_t)g.KT && gemm_tc_eligible((int)g.rows, g.CL, g.CL);
+}
+
+// xp[b, tau, i]: zero in the pad rows, scale_in(x[b, tau - pad]) (or a copy) inside; one thread per (row, 4 channels)
+__global__ void k_pad_scale_all(int B, int T, int in, int pad, const float* __restrict__ x, const float* __restrict__ Ws,
+                                const float* __restrict__ bs, float* __restrict__ xp) {
+    extern __shared__ float sW[];  // [in*in + in]
+    if (Ws) {
+        for (int i = threadIdx.x; i < in * in; i += blockDim.x) sW[i] = Ws[i];
+        for (int i = threadIdx.x; i < in; i += blockDim.x) sW[in * in + i] = bs[i];
+        __syncthreads();
+    }
+    const int Tp = T + 2 * pad;
+    const int q4 = (in + 3) / 4;
+    const size_t n = (size_t)B * Tp * q4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / q4;
+        const int i0 = (int)(idx - r * q4) * 4;
+        const int b = (int)(r / Tp), tau = (int)(r - (size_t)b * Tp), t = tau - pad;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t >= 0 && t < T) {
+            const float* xr = x + ((size_t)b * T + t) * in;
+            if (Ws) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (i0 + q < in) v[q] = sW[in * in + i0 + q];
+                for (int j = 0; j < in; ++j) {
+                    const float xv = xr[j];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (i0 + q < in) v[q] = fmaf(sW[(i0 + q) * in + j], xv, v[q]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (i0 + q < in) v[q] = xr[i0 + q];
+            }
+        }
+        float* d = xp + r * in + i0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (i0 + q < in) d[q] = v[q];
+    }
+}
+
+// dxcp[b, t, :] = dxc_tm[t, b, :] * mask_tm[t, b, :] for t < T, 0 for the Tp - T trailing rows of each utterance
+__global__ void k_expand_mask_all(int B, int T, int Tp, int C, const float* __restrict__ dxc, const float* __restrict__ mask,
+                                  float* __restrict__ dxcp) {
+    const size_t n = (size_t)B * Tp * C;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / C;
+        const int c = (int)(idx - r * C);
+        const int b = (int)(r / Tp), t = (int)(r - (size_t)b * Tp);
+        float v = 0.f;
+        if (t < T) {
+            const size_t src = ((size_t)t * B + b) * C + c;
+            v = dxc[src];
+            if (mask) v *= mask[src];
+        }
+        dxcp[idx] = v;
+    }
+}
+
+// bb_next[o] = b_layer[o] + sum_j sum_q Wt[j][o][q] bb[q]     (one warp per output)
+__global__ void k_beff(int co, int ci, int k, const float* __restrict__ Wt, const float* __restrict__ b_layer,
+                       const float* __restrict__ bb, float* __restrict__ bb_next) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= co) return;
+    float s = 0.f;
+    for (int j = 0; j < k; ++j)
+        for (int q = lane; q < ci; q += 32) s = fmaf(Wt[((size_t)j * co + o) * ci + q], bb[q], s);
+    s = warp_sum(s);
+    if (lane == 0) bb_next[o] = b_layer[o] + s;
+}
+// dbb[q] = sum_j sum_o Wt[j][o][q] dbb_next[o]: 32 columns q per block, the (j, o) rows spread over 32 warps, fixed-order tree
+__global__ void __launch_bounds__(1024) k_beff_bwd(int co, int ci, int k, const float* __restrict__ Wt, const float* __restrict__ dbb_next,
+                                                   float* __restrict__ dbb) {
+    __shared__ float red[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (q < ci)
+        for (int r = w; r < k * co; r += 32) s = fmaf(Wt[(size_t)r * ci + q], dbb_next[r % co], s);
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && q < ci) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t += red[i][lane];
+        dbb[q] = t;
+    }
+}
+// dWt[j][o][q] += dbb_next[o] * bb[q] for every tap j
+__global__ void k_rank1_add(int co, int ci, int k, const float* __restrict__ dbb_next, const float* __restrict__ bb, float* __restrict__ dWt) {
+    const size_t n = (size_t)k * co * ci;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(idx % ci);
+        const int o = (int)((idx / ci) % co);
+        dWt[idx] += dbb_next[o] * bb[q];
+    }
+}
+// Tm[j][o][n] = E[o][j * Cl + n]: the k column blocks of a C_{l+1} x C_{l+1} matrix stacked as one [k * C_{l+1}, C_l] matrix
+__global__ void k_tapmajor(int Cn, int Cl, int k, const float* __restrict__ E, float* __restrict__ Tm) {
+    const size_t n = (size_t)k * Cn * Cl;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % Cl);
+        const int o = (int)((idx / Cl) % Cn);
+        const int j = (int)(idx / ((size_t)Cl * Cn));
+        Tm[idx] = E[(size_t)o * Cn + (size_t)j * Cl + c];
+    }
+}
+
+// dst = src (+ dst)
+__global__ void k_copy_acc(size_t n, const float* __restrict__ src, float* __restrict__ dst, int accumulate) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = accumulate ? dst[i] + src[i] : src[i];
+}
+
+// ---- derived parameters of the composed conv, cached until the weights change --------------------------------------
+// buffer layout (floats): E_1 .. E_L (C_l x C_l, column = tap * in + channel), bb_1 .. bb_L (C_l), Wt_1 .. Wt_{L-1}
+// ([k][C_{l+1}][C_l]).  E_1 = wcat(W_0), bb_1 = b_0;  E_{l+1}[:, block j] = Wt_l[j] E_l,  bb_{l+1} = b_l + sum_j Wt_l[j] bb_l.
+struct FeDerived {
+    const float* key_w[4] = {nullptr, nullptr, nullptr, nullptr};
+    int k = 0, L = 0, in = 0;
+    unsigned long long gen = 0, last_use = 0;
+    float* buf = nullptr;
+    size_t floats = 0;
+    bool pinned = false;
+};
+struct FeDLayout {
+    size_t E[6], bb[6], Wt[5], total;
+};
+static FeDLayout fed_layout(int in, int k, int L) {
+    FeDLayout D;
+    size_t off = 0;
+    for (int l = 1; l <= L; ++l) {
+        size_t C = (size_t)in * ipow(k, l);
+        D.E[l] = off;
+        off += round_up_sz(C * C, 4);
+    }
+    for (int l = 1; l <= L; ++l) {
+        D.bb[l] = off;
+        off += round_up_sz((size_t)in * ipow(k, l), 4);
+    }
+    for (int l = 1; l < L; ++l) {
+        D.Wt[l] = off;
+        off += round_up_sz((size_t)k * in * ipow(k, l + 1) * in * ipow(k, l), 4);
+    }
+    D.total = off;
+    return D;
+}
+static std::mutex g_fed_mu;
+static FeDerived g_fed[64][8];
+static unsigned long long g_fed_clock = 0;
+
+// -> *out = buffer holding the derived parameters of `net`, recomputed on stream s if the weights changed
+static int fe_derived(const cvb_net* net, cudaStream_t s, const float** out) {
+    int dev = 0;
+    CVB_CHECK(cudaGetDevice(&dev));
+    CVB_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    const int in = net->in_dim, k = net->kernel_size, L = net->n_conv;
+    const FeDLayout D = fed_layout(in, k, L);
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    CVB_CHECK(cudaStreamIsCapturing(s, &cap_st));
+    const bool capturing = cap_st != cudaStreamCaptureStatusNone;
+    const unsigned long long gen = weights_generation();
+    std::lock_guard<std::mutex> lk(g_fed_mu);
+    FeDerived* e = nullptr;
+    for (auto& c : g_fed[dev]) {
+        bool same = c.buf && c.k == k && c.L == L && c.in == in;
+        for (int i = 0; i < L && same; ++i) same = c.key_w[i] == net->conv_w[i];
+        if (same) e = &c;
+    }
+    if (!e) {
+        for (auto& c : g_fed[dev])
+            if (!c.pinned && !(capturing && c.floats < D.total) && (!e || c.last_use < e->last_use)) e = &c;
+        CVB_REQUIRE(e, "no free slot for the composed conv parameters (8 front-ends are pinned by captured CUDA graphs)");
+        if (e->floats < D.total) {
+            if (e->buf) CVB_CHECK(cudaFree(e->buf));
+            e->buf = nullptr;
+            e->floats = 0;
+            CVB_CHECK(cudaMalloc(&e->buf, D.total * sizeof(float)));
+            e->floats = D.total;
+        }
+        for (int i = 0; i < 4; ++i) e->key_w[i] = i < L ? net->conv_w[i] : nullptr;
+        e->k = k;
+        e->L = L;
+        e->in = in;
+        e->gen = 0;
+    }
+    e->last_use = ++g_fed_clock;
+    if (capturing) e->pinned = true;
+    *out = e->buf;
+    if (e->gen == gen) return 0;
+    e->gen = gen;
+    float* buf = e->buf;
+    const int C1 = in * k;
+    k_repack_wcat<<<grid1d((size_t)C1 * in * k), 256, 0, s>>>(C1, in, k, net->conv_w[0], buf + D.E[1]);
+    CVB_LAUNCH_CHECK();
+    CVB_CHECK(cudaMemcpyAsync(buf + D.bb[1], net->conv_b[0], (size_t)C1 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (int l = 1; l < L; ++l) {
+        const int Cl = in * ipow(k, l), Cn = Cl * k;
+        float* Wt = buf + D.Wt[l];
+        k_repack_w<<<grid1d((size_t)Cn * Cl * k), 256, 0, s>>>(Cn, Cl, k, net->conv_w[l], Wt);
+        CVB_LAUNCH_CHECK();
+        for (int j0 = 0; j0 < k; j0 += 6) {   // E_{l+1}[:, block j] = Wt[j] E_l, up to 6 taps per launch
+            GemmDesc d[6];
+            int n = 0;
+            for (int j = j0; j < k && n < 6; ++j) {
+                GemmDesc& g = d[n++];
+                g.M = Cn; g.N = Cl; g.K = Cl;
+                g.A = Wt + (size_t)j * Cn * Cl; g.lda = Cl;
+                g.B = buf + D.E[l]; g.ldb = Cl;
+                g.C = buf + D.E[l + 1] + (size_t)j * Cl; g.ldc = Cn;
+            }
+            if (gemm_tc_eligible(Cn, Cl, Cl)) {
+                if (int rc = gemm_tc_group(s, d, n)) return rc;
+            } else {
+                for (int i = 0; i < n; ++i)
+                    if (int rc = gemm_rm(s, false, false, Cn, Cl, Cl, 1.f, d[i].A, Cl, d[i].B, Cl, 0.f, d[i].C, Cn)) return rc;
+            }
+        }
+        k_beff<<<ceil_div(Cn, 8), 256, 0, s>>>(Cn, Cl, k, Wt, net->conv_b[l], buf + D.bb[l], buf + D.bb[l + 1]);
+        CVB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static size_t fec_bwd_scratch_floats(const cvb_net* n, int B, int T) {
+    FeC g = fec_geom(n, B, T);
+    FeDLayout D = fed_layout(g.in, g.k, g.L);
+    // dxcp [R, CL] | G [rows, CL] | dxp [R + KT, in] | dE_1..dE_L, dbb_1..dbb_L, dWt_1..dWt_{L-1} (same layout as the derived parameters)
+    return round_up_sz(g.R * g.CL, 4) + round_up_sz(g.rows * g.CL, 4) + g.xp_floats + D.total + round_up_sz((size_t)g.CL * g.CL, 4);
+}
+
+static int fec_fwd(const cvb_net* net, int B, int T, const float* x_bm, const float* mask_conv_tm, float* fe_ws, float* xc_tm,
+                   cudaStream_t s) {
+    const FeC g = fec_geom(net, B, T);
+    const FeDLayout D = fed_layout(g.in, g.k, g.L);
+    const float* der = nullptr;
+    if (int rc = fe_derived(net, s, &der)) return rc;
+    const float* Ws = net->has_scale_in ? net->scale_in_w : nullptr;
+    const size_t smem = Ws ? (size_t)(g.in * g.in + g.in) * sizeof(float) : 0;
+    CVB_REQUIRE(smem <= 48 * 1024, "scale_in matrix too large for shared memory (in_dim=%d)", g.in);
+    float* xp = fe_ws;
+    k_pad_scale_all<<<grid1d(g.R * ((g.in + 3) / 4)), 256, smem, s>>>(B, T, g.in, g.pad, x_bm, Ws, net->scale_in_b, xp);
+    CVB_LAUNCH_CHECK();
+    if (int rc = zero_floats(s, xp + g.R * g.in, (size_t)g.KT * g.in)) return rc;   // slack rows behind the last window
+    ConvGather ga{g.in, 1};
+    GemmDesc d;
+    d.transB = true;
+    d.M = (int)g.rows; d.N = g.CL; d.K = g.CL;
+    d.A = xp; d.lda = g.in; d.gA = &ga;
+    d.B = der + D.E[g.L]; d.ldb = g.CL; d.b_const = true;
+    d.bias = der + D.bb[g.L];
+    d.C = xc_tm; d.ldc = g.CL;
+    d.map_Tp = g.Tp; d.map_T = T; d.map_B = B; d.mask = mask_conv_tm;
+    return gemm_tc_group(s, &d, 1);
+}
+
+static int fec_bwd(const cvb_net* net, int B, int T, const float* x_bm, const float* mask_conv_tm, const float* fe_ws,
+                   const float* dxc_tm, float* scratch, float* dx_bm, const cvb_net_grads* gr, cudaStream_t s) {
+    const FeC g = fec_geom(net, B, T);
+    const FeDLayout D = fed_layout(g.in, g.k, g.L);
+    const float* der = nullptr;
+    if (int rc = fe_derived(net, s, &der)) return rc;
+    const int acc = gr ? gr->accumulate : 0;
+    const float* xp = fe_ws;
+    float* dxcp = scratch;
+    float* G = dxcp + round_up_sz(g.R * g.CL, 4);
+    float* dxp = G + round_up_sz(g.rows * g.CL, 4);
+    float* dd = dxp + g.xp_floats;   // gradients of the derived parameters, same layout as `der`
+    k_expand_mask_all<<<grid1d(g.R * g.CL), 256, 0, s>>>(B, T, g.Tp, g.CL, dxc_tm, mask_conv_tm, dxcp);
+    CVB_LAUNCH_CHECK();
+    bool want_w = false;
+    if (gr)
+        for (int i = 0; i < g.L; ++i) want_w = want_w || gr->conv_w[i] || gr->conv_b[i];
+    const bool need_dx = dx_bm || (gr && (gr->scale_in_w || gr->scale_in_b));
+    GemmDesc d[2];
+    int n = 0;
+    ConvGather gb{g.in, 1};
+    if (want_w) {   // dE_L = dxc'^T im2col(x^)
+        GemmDesc& q = d[n++];
+        q.transA = true;
+        q.M = g.CL; q.N = g.CL; q.K = (int)g.rows;
+        q.A = dxcp; q.lda = g.CL;
+        q.B = xp; q.ldb = g.in; q.gB = &gb;
+        q.C = dd + D.E[g.L]; q.ldc = g.CL; q.f16 = false;
+    }
+    if (need_dx) {   // G = dxc' E_L: per window row the gradient of its KT x in inputs
+        GemmDesc& q = d[n++];
+        q.M = (int)g.rows; q.N = g.CL; q.K = g.CL;
+        q.A = dxcp; q.lda = g.CL;
+        q.B = der + D.E[g.L]; q.ldb = g.CL; q.b_const = true;
+        q.C = G; q.ldc = g.CL; q.f16 = false;
+    }
+    if (n)
+        if (int rc = gemm_tc_group(s, d, n)) return rc;
+    if (need_dx) {
+        if (int rc = zero_floats(s, dxp, g.R * g.in)) return rc;
+        k_col2im_add<<<grid1d(g.R * g.in), 256, 0, s>>>(g.R, g.rows, (size_t)g.pad, g.in, g.KT, 1, G, dxp);
+        CVB_LAUNCH_CHECK();
+    }
+    if (want_w) {
+        if (int rc = colsum(s, dxcp, (int)g.rows, g.CL, g.CL, dd + D.bb[g.L], false)) return rc;
+        // chain rule from (dE_L, dbb_L) down to the layers
+        for (int l = g.L - 1; l >= 1; --l) {
+            const int Cl = g.in * ipow(g.k, l), Cn = Cl * g.k;
+            const float* Wt = der + D.Wt[l];
+            float* dWt = dd + D.Wt[l];
+            {
+                // dWt[j] = dE_{l+1}[:, block j] E_l^T for every tap j, and dE_l = sum_j Wt[j]^T dE_{l+1}[:, block j] as ONE
+                // contraction over (j, o) against the tap-major copy of dE_{l+1}: one grouped launch
+                float* Tm = dd + D.total;   // [k * Cn, Cl]
+                k_tapmajor<<<grid1d((size_t)g.k * Cn * Cl), 256, 0, s>>>(Cn, Cl, g.k, dd + D.E[l + 1], Tm);
+                CVB_LAUNCH_CHECK();
+                GemmDesc q[6];
+                int nq = 0;
+                CVB_REQUIRE(g.k <= 5, "kernel_size %d: at most 5 taps per grouped launch", g.k);
+                for (int j = 0; j < g.k; ++j) {
+                    GemmDesc& a = q[nq++];
+                    a.transB = true;
+                    a.M = Cn; a.N = Cl; a.K = Cl;
+                    a.A = dd + D.E[l + 1] + (size_t)j * Cl; a.lda = Cn;
+                    a.B = der + D.E[l]; a.ldb = Cl;
+                    a.C = dWt + (size_t)j * Cn * Cl; a.ldc = Cl; a.f16 = false;
+                }
+                GemmDesc& b = q[nq++];
+                b.transA = true;
+                b.M = Cl; b.N = Cl; b.K = g.k * Cn;
+                b.A = Wt; b.lda = Cl;
+                b.B = Tm; b.ldb = Cl;
+                b.C = dd + D.E[l]; b.ldc = Cl; b.f16 = false;
+                if (int rc = gemm_tc_group(s, q, nq)) return rc;
+            }
+            k_rank1_add<<<grid1d((size_t)g.k * Cn * Cl), 256, 0, s>>>(Cn, Cl, g.k, dd + D.bb[l + 1], der + D.bb[l], dWt);
+            CVB_LAUNCH_CHECK();
+            k_beff_bwd<<<ceil_div(Cl, 32), 1024, 0, s>>>(Cn, Cl, g.k, Wt, dd + D.bb[l + 1], dd + D.bb[l]);
+            CVB_LAUNCH_CHECK();
+            if (gr->conv_w[l]) {
+                k_unrepack_dw<<<grid1d((size_t)Cn * Cl * g.k), 256, 0, s>>>(Cn, Cl, g.k, dWt, gr->conv_w[l], acc);
+                CVB_LAUNCH_CHECK();
+            }
+            if (gr->conv_b[l]) {
+                k_copy_acc<<<grid1d((size_t)Cn), 256, 0, s>>>((size_t)Cn, dd + D.bb[l + 1], gr->conv_b[l], acc);
+                CVB_LAUNCH_CHECK();
+            }
+        }
+        const int C1 = g.in * g.k;
+        if (gr->conv_w[0]) {
+            k_unrepack_dwcat<<<grid1d((size_t)C1 * g.in * g.k), 256, 0, s>>>(C1, g.in, g.k, dd + D.E[1], gr->conv_w[0], acc);
+            CVB_LAUNCH_CHECK();
+        }
+        if (gr->conv_b[0]) {
+            k_copy_acc<<<grid1d((size_t)C1), 256, 0, s>>>((size_t)C1, dd + D.bb[1], gr->conv_b[0], acc);
+            CVB_LAUNCH_CHECK();
+        }
+    }
+    const float* Ws = net->has_scale_in ? net->scale_in_w : nullptr;
+    const int in_dim = g.in;
+    if (dx_bm) {
+        size_t smem = Ws ? (size_t)in_dim * in_dim * sizeof(float) : 0;
+        k_unpad_scale_bwd<<<grid1d((size_t)B * T * in_dim), 256, smem, s>>>(B, T, in_dim, g.pad, dxp, Ws, dx_bm);
+        CVB_LAUNCH_CHECK();
+    }
+    if (Ws && gr && (gr->scale_in_w || gr->scale_in_b)) {
+        // frozen in the trainer (train_*.py:369-370); provided for completeness, one product per utterance
+        for (int b = 0; b < B; ++b) {
+            const float* dxh = dxp + ((size_t)b * g.Tp + g.pad) * in_dim;
+            bool first = (b == 0) && !acc;
+            if (gr->scale_in_w)
+                if (int rc = gemm_rm(s, true, false, in_dim, in_dim, T, 1.f, dxh, in_dim, x_bm + (size_t)b * T * in_dim, in_dim,
+                                     first ? 0.f : 1.f, gr->scale_in_w, in_dim, true))
+                    return rc;
+            if (gr->scale_in_b)
+                if (int rc = colsum(s, dxh, T, in_dim, in_dim, gr->scale_in_b, !first)) return rc;
+        }
+    }
+    return 0;
+}
+
 int frontend_fwd(const cvb_net* net, int B, int T, const float* x_bm, const float* mask_conv_tm, float* fe_ws,
                  float* xc_tm, cudaStream_t s) {
     CVB_REQUIRE(net->kernel_size % 2 == 1, "kernel_size must be odd (got %d)", net->kernel_size);
     CVB_REQUIRE(net->n_conv >= 1 && net->n_conv <= 4, "dilation_size (conv layers) must be 1..4 (got %d)", net->n_conv);
     FeGeom g = fe_geom(net, B, T);
     if (g.R == 0 || T == 0) return 0;
+    if (fe_composed(net, B, T)) return fec_fwd(net, B, T, x_bm, mask_conv_tm, fe_ws, xc_tm, s);
     // zero the padded grids (pads of buf_0 are the reference's zero padding; the rest keeps
     // never-computed edge rows finite)
     if (int rc = zero_floats(s, fe_ws, g.wr_off[0])) return rc;
@@ -263,6 +697,7 @@ int frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const floa
                  const float* dxc_tm, float* scratch, float* dx_bm, const cvb_net_grads* gr, cudaStream_t s) {
     FeGeom g = fe_geom(net, B, T);
     if (g.R == 0 || T == 0) return 0;
+    if (fe_composed(net, B, T)) return fec_bwd(net, B, T, x_bm, mask_conv_tm, fe_ws, dxc_tm, scratch, dx_bm, gr, s);
     int acc = gr ? gr->accumulate : 0;
     float* dbuf = scratch;  // same offsets as buf_i
     float* dWr = scratch + g.wr_off[0];

@@ -4,6 +4,7 @@
 #include <cublas_v2.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <mutex>
@@ -64,6 +65,21 @@ static int get_handle(cublasHandle_t* out) {
     }
     *out = g_handles[dev];
     return 0;
+}
+
+extern "C" char** environ;
+bool launch_without_coop() {
+    static int cached = -1;
+    if (cached < 0) {
+        cached = 0;
+        const char* e = getenv("CVB_TC_NOCOOP");
+        if (e && e[0] == '1') cached = 1;
+        // Nsight Compute injects itself through these variables
+        for (char** v = environ; v && *v && !cached; ++v)
+            if (!strncmp(*v, "NV_COMPUTE_PROFILER", 19) || !strncmp(*v, "NV_NSIGHT_INJECTION", 19) || !strncmp(*v, "CUDA_INJECTION64_PATH", 21))
+                cached = 1;
+    }
+    return cached == 1;
 }
 
 bool want_tc_gemm() {

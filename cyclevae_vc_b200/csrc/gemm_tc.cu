@@ -220,6 +220,11 @@ struct GtProblem {
     int M, N, ldc, MT, NT, KC;
     int beta1, f16;
     int tile_end;      // running tile count up to and including this product
+    int map_Tp, map_T, map_B;   // output row map (GemmDesc), 0 = identity
+    const float* mask;
+    // split-K (few tiles, deep K): split s sums chunks [s * kc_split, ...) into part[s][M][N]; k_splitk_reduce finishes
+    int S, kc_split;
+    float* part;
 };
 struct GemmTcArgs {
     GtProblem p[GT_MAXP];
@@ -230,7 +235,7 @@ struct GemmTcArgs {
 // boustrophedon order (wave w of gridDim tiles forwards, wave w+1 backwards): with the long-K products listed first the
 // CTAs that got an extra long tile are the last to be handed a short one.
 struct GtWalk {
-    int wave, tile, prob, mt, nt;
+    int wave, tile, prob, mt, nt, sp, kc0, kc1;   // the tile's chunk range [kc0, kc1) (split sp of a split-K product)
     __device__ __forceinline__ void start() { wave = -1; }
     __device__ __forceinline__ bool next(const GemmTcArgs& g) {
         ++wave;
@@ -238,9 +243,15 @@ struct GtWalk {
         if (tile >= g.p[g.n_prob - 1].tile_end) return false;
         prob = 0;
         while (tile >= g.p[prob].tile_end) ++prob;
-        const int local = tile - (prob ? g.p[prob - 1].tile_end : 0);
-        nt = local / g.p[prob].MT;
-        mt = local - nt * g.p[prob].MT;
+        const GtProblem& P = g.p[prob];
+        int local = tile - (prob ? g.p[prob - 1].tile_end : 0);
+        const int per = P.MT * P.NT;
+        sp = local / per;
+        local -= sp * per;
+        nt = local / P.MT;
+        mt = local - nt * P.MT;
+        kc0 = sp * P.kc_split;
+        kc1 = kc0 + P.kc_split < P.KC ? kc0 + P.kc_split : P.KC;
         return true;
     }
 };
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             const GtProblem& P = g.p[w.prob];
             const uint8_t* a_src = reinterpret_cast<const uint8_t*>(P.At) + (size_t)w.mt * P.KC * GT_BLOCK_BYTES;
             const uint8_t* b_src = reinterpret_cast<const uint8_t*>(P.Bt) + (size_t)w.nt * P.KC * GT_BLOCK_BYTES;
-            for (int kc = 0; kc < P.KC; ++kc) {
+            for (int kc = w.kc0; kc < w.kc1; ++kc) {
                 if (lane == 0) {
                     mbar_wait(&empty[s], ph);
                     uint8_t* dst = smem + (size_t)s * GT_STAGE_BYTES;
@@ -306,9 +317,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             const GtProblem& P = g.p[w.prob];
             const uint32_t idesc_s = P.f16 ? idesc_f16_f32(128, 256) : idesc_bf16_f32(128, 256);   // B rows [hi | lo]
             const uint32_t idesc_h = P.f16 ? idesc_f16_f32(128, 128) : idesc_bf16_f32(128, 128);   // B hi rows only
-            for (int kc = 0; kc < P.KC; ++kc) {
+            const int nkc = w.kc1 - w.kc0;
+            for (int kc = 0; kc < nkc; ++kc) {
                 const bool slice_start = (kc % GT_KD) == 0;
-                const bool slice_end = ((kc + 1) % GT_KD) == 0 || kc == P.KC - 1;
+                const bool slice_end = ((kc + 1) % GT_KD) == 0 || kc == nkc - 1;
                 if (slice_start) {
                     if (lane == 0) mbar_wait(&tmem_empty[acc], acc_ph);
                     __syncwarp();
@@ -348,7 +360,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             // both cross products sit in the second 128 columns; fp16 lo planes are stored scaled by 2^11 (umma.cuh)
             const float lo_inv = P.f16 ? F16_LO_INV : 1.0f;
             const bool vec_ok = (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
-            const int n_slices = (P.KC + GT_KD - 1) / GT_KD;
+            const int n_slices = (w.kc1 - w.kc0 + GT_KD - 1) / GT_KD;
             const int row = w.mt * GT_BM + (warp - 4) * 32 + lane;
             const int n0 = w.nt * GT_BN;
             float sum[GT_BN];
@@ -374,8 +386,25 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                     acc_ph ^= 1;
                 }
             }
-            if (row < P.M) {
-                float* crow = P.C + (size_t)row * P.ldc + n0;
+            if (P.S > 1) {   // raw partial sums of this split; alpha / bias / accumulate are applied by the reduction
+                if (row < P.M) {
+                    float* prow = P.part + ((size_t)w.sp * P.M + row) * P.N + n0;
+#pragma unroll
+                    for (int c0 = 0; c0 < GT_BN; ++c0)
+                        if (n0 + c0 < P.N) prow[c0] = sum[c0];
+                }
+                continue;
+            }
+            size_t orow = (size_t)row;
+            bool row_ok = row < P.M;
+            if (P.map_Tp) {   // padded-grid row (b, t) -> time-major row t * B + b; rows of the padding are dropped
+                const int bb = row / P.map_Tp, tt = row - bb * P.map_Tp;
+                row_ok = row_ok && tt < P.map_T;
+                orow = (size_t)tt * P.map_B + bb;
+            }
+            if (row_ok) {
+                float* crow = P.C + orow * P.ldc + n0;
+                const float* mrow = P.mask ? P.mask + orow * P.ldc + n0 : nullptr;
 #pragma unroll
                 for (int c0 = 0; c0 < GT_BN; c0 += 4) {
                     if (n0 + c0 < P.N) {
@@ -384,6 +413,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                         for (int q = 0; q < 4; ++q) {
                             o[q] = P.alpha * sum[c0 + q];
                             if (P.bias && n0 + c0 + q < P.N) o[q] += P.bias[n0 + c0 + q];
+                            if (mrow && n0 + c0 + q < P.N) o[q] *= mrow[c0 + q];
                         }
                         if (vec_ok && n0 + c0 + 4 <= P.N) {
                             float4 wv = make_float4(o[0], o[1], o[2], o[3]);
@@ -405,6 +435,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// C = alpha * sum_s part[s] (+ bias) (+ C), splits added in index order (deterministic)
+__global__ void k_splitk_reduce(int M, int N, int S, const float* __restrict__ part, float* __restrict__ C, int ldc, float alpha,
+                                const float* __restrict__ bias, int beta1) {
+    const size_t n = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / N), c = (int)(i - (size_t)r * N);
+        float v = 0.f;
+        for (int s = 0; s < S; ++s) v += part[(size_t)s * n + i];
+        v *= alpha;
+        if (bias) v += bias[c];
+        float* d = C + (size_t)r * ldc + c;
+        *d = beta1 ? *d + v : v;
+    }
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------
@@ -435,6 +480,10 @@ static unsigned long long g_weights_gen = 1, g_use_clock = 0;
 void weights_changed() {
     std::lock_guard<std::mutex> lk(g_ws_mu);
     ++g_weights_gen;
+}
+unsigned long long weights_generation() {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    return g_weights_gen;
 }
 
 static int arena_reserve(int dev, size_t bytes, bool capturing) {
@@ -482,6 +531,9 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
     GemmTcArgs g;
     memset(&g, 0, sizeof(g));
     g.n_prob = n;
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+    const int di_sm = di.n_sm;
     GtOperand ops[GT_MAXO];       // distinct operands of this group
     bool is_const[GT_MAXO];
     int n_ops = 0, which[GT_MAXP][2];
@@ -541,7 +593,22 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
         P.KC = ceil_div(D.K, GT_BK);
         P.beta1 = D.beta1 ? 1 : 0;
         P.f16 = D.f16 ? 1 : 0;
-        tiles += P.MT * P.NT;
+        P.map_Tp = D.map_Tp;
+        P.map_T = D.map_T;
+        P.map_B = D.map_B;
+        P.mask = D.mask;
+        // split-K: a product with few output tiles and a deep K would keep a handful of CTAs busy for its whole length
+        P.S = 1;
+        P.kc_split = P.KC;
+        if (!D.map_Tp && P.MT * P.NT <= 48 && P.KC >= 16) {
+            int want = di_sm / (P.MT * P.NT);
+            if (want > P.KC / 4) want = P.KC / 4;
+            if (want > 1) {
+                P.kc_split = ceil_div(P.KC, want);
+                P.S = ceil_div(P.KC, P.kc_split);
+            }
+        }
+        tiles += P.MT * P.NT * P.S;
         P.tile_end = tiles;
     }
     // place the images: cached parameter images in their own buffers, the rest bump-allocated in the arena
@@ -566,8 +633,15 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
         size_t need = 0;
         for (int j = 0; j < n_ops; ++j)
             if (!is_const[j]) need += image_bytes(ops[j].rows, ops[j].K);
+        for (int i = 0; i < n; ++i)
+            if (g.p[i].S > 1) need += round_up_sz((size_t)g.p[i].S * g.p[i].M * g.p[i].N * sizeof(float), 256);
         if (int rc = arena_reserve(dev, need, capturing)) return rc;
         size_t off = 0;
+        for (int i = 0; i < n; ++i)
+            if (g.p[i].S > 1) {
+                g.p[i].part = reinterpret_cast<float*>(g_arena[dev].buf + off);
+                off += round_up_sz((size_t)g.p[i].S * g.p[i].M * g.p[i].N * sizeof(float), 256);
+            }
         int blocks = 0;
         for (int j = 0; j < n_ops; ++j) {
             GtOperand& o = ops[j];
@@ -616,8 +690,6 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
         g.p[i].At = ops[which[i][0]].img;
         g.p[i].Bt = ops[which[i][1]].img;
     }
-    DeviceInfo di;
-    if (int rc = get_device_info(&di)) return rc;
     const int smem = GT_NS * GT_STAGE_BYTES + 256;
     static bool attr_set[64] = {};   // function attributes are per device
     if (!attr_set[dev]) {
@@ -627,8 +699,16 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
     const int grid = tiles < di.n_sm ? tiles : di.n_sm;
     prof_begin(s, CVB_PROF_GEMM);
     k_gemm_tc<<<grid, GT_THREADS, smem, s>>>(g);
-    prof_end(s, CVB_PROF_GEMM);
     CVB_LAUNCH_CHECK();
+    for (int i = 0; i < n; ++i)
+        if (g.p[i].S > 1) {
+            const GtProblem& P = g.p[i];
+            const size_t mn = (size_t)P.M * P.N;
+            k_splitk_reduce<<<(int)(ceil_div_sz(mn, 256) > 1184 ? 1184 : ceil_div_sz(mn, 256)), 256, 0, s>>>(P.M, P.N, P.S, P.part, P.C, P.ldc, P.alpha,
+                                                                                                         P.bias, P.beta1);
+            CVB_LAUNCH_CHECK();
+        }
+    prof_end(s, CVB_PROF_GEMM);
     return 0;
 }
 

@@ -767,8 +767,7 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     cfg.attrs = at;
     // CVB_TC_NOCOOP=1 drops the cooperative attribute (profilers that cannot replay a cooperative cluster launch; the
     // grid still fits one wave, but co-residency is then only true on an otherwise idle device)
-    const char* nocoop = getenv("CVB_TC_NOCOOP");
-    cfg.numAttrs = (nocoop && nocoop[0] == '1') ? 1 : 2;
+    cfg.numAttrs = launch_without_coop() ? 1 : 2;
     prof_begin(s, CVB_PROF_GRU_BWD);
     CVB_CHECK(cudaLaunchKernelEx(&cfg, k_gru_bwd_tc, a));
     prof_end(s, CVB_PROF_GRU_BWD);

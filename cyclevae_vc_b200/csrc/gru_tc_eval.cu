@@ -566,8 +566,7 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStre
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
     cfg.attrs = at;
-    const char* nocoop = getenv("CVB_TC_NOCOOP");
-    cfg.numAttrs = (nocoop && nocoop[0] == '1') ? 1 : 2;
+    cfg.numAttrs = launch_without_coop() ? 1 : 2;
     prof_begin(s, CVB_PROF_GRU_FWD);
     CVB_CHECK(cudaLaunchKernelEx(&cfg, k_gru_fwd_tc_eval, a));
     prof_end(s, CVB_PROF_GRU_FWD);

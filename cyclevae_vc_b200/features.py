@@ -196,24 +196,36 @@ class DeviceStager:
         return buf[:like.numel()].view(like.shape)
 
     def put(self, batch: dict) -> dict:
+        """Enqueue the copies of `batch` and return the device-side dictionary.  With a side `stream` the CONSUMER stream
+        (the stream current at the call) is made to wait for the copies before it may touch the tensors, and the tensors
+        are recorded on it so the caching allocator does not hand their memory out while it still reads them."""
         s = self._turn
         self._turn ^= 1
         if self._events[s] is not None:
             self._events[s].synchronize()
         out = {}
-        ctx = torch.cuda.stream(self.stream) if (self.stream is not None and self.device.type == "cuda") else _null()
-        with ctx:
+        cuda = self.device.type == "cuda"
+        consumer = torch.cuda.current_stream(self.device) if cuda else None
+        side = self.stream if (cuda and self.stream is not None) else None
+        if side is not None:
+            side.wait_stream(consumer)   # the pinned slot / earlier device work of the consumer is ordered before the copies
+        with (torch.cuda.stream(side) if side is not None else _null()):
             for k, v in batch.items():
                 if torch.is_tensor(v) and v.dim() > 1:
                     h = self._pinned(self._slots[s], k, v)
                     h.copy_(v)
-                    out[k] = h.to(self.device, non_blocking=True)
+                    d = h.to(self.device, non_blocking=True)
+                    if side is not None:
+                        d.record_stream(consumer)
+                    out[k] = d
                 else:
                     out[k] = v
-            if self.device.type == "cuda":
+            if cuda:
                 ev = torch.cuda.Event()
                 ev.record()
                 self._events[s] = ev
+        if side is not None:
+            consumer.wait_event(self._events[s])
         return out
 
 

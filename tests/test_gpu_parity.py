@@ -1001,3 +1001,22 @@ def test_fused_step_driver_graph_replay(cvb):
         grads.append([p.grad.clone() for p in cycle.trainable_parameters(enc, dec)])
     for ga, gb in zip(*grads):
         assert _maxabs(ga, gb) <= 2e-6 * max(1e-3, float(ga.abs().max()))
+
+
+def test_device_stager_side_stream(cvb):
+    """features.DeviceStager with a side copy stream: the consumer stream must see complete batches (it waits on the copy
+    event) even when it is busy, and alternating pinned slots must not be overwritten while their copies are in flight."""
+    from cyclevae_vc_b200.features import DeviceStager
+    dev = torch.device("cuda")
+    st = DeviceStager(dev, stream=torch.cuda.Stream())
+    busy = torch.randn(4096, 4096, device=dev)
+    ok = True
+    for it in range(6):
+        batch = {"h_src": torch.full((8, 2200, 54), float(it)), "flen_src": torch.full((8,), it), "featfile_src": ["a"] * 8,
+                 "spcidx_src": torch.full((8, 2200), it, dtype=torch.int64)}
+        busy = busy @ busy * 1e-4          # keep the consumer stream occupied while the copies run on the side stream
+        d = st.put(batch)
+        ok = ok and bool((d["h_src"] == float(it)).all()) and bool((d["spcidx_src"] == it).all()) and d["h_src"].is_cuda
+        assert d["featfile_src"] == ["a"] * 8 and not d["flen_src"].is_cuda
+    torch.cuda.synchronize()
+    assert ok

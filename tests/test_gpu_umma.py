@@ -14,7 +14,9 @@ def _arrange(X):
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("N,K", [(32, 64), (16, 256), (64, 128)])
 def test_umma_selftest(mode, N, K):
-    from cyclevae_vc_b200._lib import check, lib, ptr
+    from cyclevae_vc_b200._lib import check, ptr
+    from tests.native.hooks import load
+    lib = load()
     g = torch.Generator().manual_seed(N * 1000 + K + mode)
     A = torch.randn(128, K, generator=g).cuda()
     B = torch.randn(N, K, generator=g).cuda()

@@ -47,7 +47,13 @@ def test_workspace_sizing_is_host_arithmetic(pkg):
     B, T = 8, 80
     fe = _lib.lib.cvb_frontend_ws_floats(C.byref(net), B, T)
     R = B * (T + 8)
-    assert fe >= R * (54 + 162 + 486) + 3 * (162 * 54 + 486 * 162) + B * T * 486
+    # composed front-end (every shape the tensor-core GEMM takes): the normalised padded grid + 9 slack rows, and xc;
+    # the layer-by-layer path of tiny shapes keeps every layer's grid and the repacked weights
+    assert R * 54 + 9 * 54 + B * T * 486 <= fe < R * (54 + 162) + B * T * 486
+    net.in_dim, net.hidden = 3, 8
+    fe_tiny = _lib.lib.cvb_frontend_ws_floats(C.byref(net), 2, 5)
+    assert fe_tiny >= 2 * 13 * (3 + 9 + 27) + 3 * (9 * 3 + 27 * 9) + 2 * 5 * 27
+    net.in_dim, net.hidden = 54, 1024
     rec = _lib.lib.cvb_recurrent_ws_floats(C.byref(net), B, T, 1, 1)
     assert rec >= (T + 1) * B * (1024 + 64) + 5 * T * B * 1024
     # the forward scratch holds gx (+ the folded-feedback matrix of the inference kernel); training adds the BPTT scratch (max of both)

@@ -6,7 +6,10 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from cyclevae_vc_b200._lib import check, lib  # noqa: E402
+from cyclevae_vc_b200._lib import check  # noqa: E402
+from tests.native.hooks import load  # noqa: E402
+
+lib = load()
 
 MHZ = 1965.0
 src = torch.randint(0, 255, (64 << 20,), dtype=torch.uint8, device="cuda")
