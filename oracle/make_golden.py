@@ -374,6 +374,45 @@ def golden_decode512():
     print("decode512.npz", len(DECODE512_ROWS), "rows")
 
 
+def golden_callers():
+    """The reference's own caller code, cut out of the scripts' ASTs (tests/ref_callers.py), run with the reference's own
+    classes on the CPU: three 80-frame chunks of one utterance batch through the trainer's frame-chunk branch
+    (train_*.py:1293-1474, carried state, its loss assembly, its torch.optim.Adam) with a save_checkpoint round trip after
+    the second chunk, and the conversion block of the decoder (decode_*.py:302-323).  do_prob = 0 and seeded noise, so
+    the GPU run of the same code against the drop-in must reproduce the numbers."""
+    import tempfile
+    from tests import ref_callers as rc
+    lat, stdim, n_cyc = 32, 4, 2
+    mean, std = orc.synth_stats(50)
+    enc = orc.NetSpec(54, 2 * lat, 1024, 3, 2, 0.0, True, False)
+    dec = orc.NetSpec(lat + 2, 50, 1024, 3, 2, 0.0, False, True)
+    Pe = orc.init_params(enc, 401, mean=mean, scale=std)
+    Pd = orc.init_params(dec, 402, mean=mean[stdim:], scale=std[stdim:])
+    me, md = build_ref(enc, Pe).train(), build_ref(dec, Pd).train()
+    for m in (me, md):
+        for k, p in m.named_parameters():
+            p.requires_grad_(not k.startswith("scale_"))
+    flens = [200, 170]
+    x, cv, sc, tc = orc.synth_batch(2, 200, 31)
+    y0d1 = torch.tensor(((0 - mean[stdim:]) / std[stdim:]), dtype=torch.float32).reshape(1, 1, -1)
+    dev = torch.device("cpu")
+    with tempfile.TemporaryDirectory() as td:
+        r = rc.run_trainer_chunks(ref, me, md, dev, x=x, cv=cv, sc=sc, tc=tc, flens=flens, lat_dim=lat, n_cyc=n_cyc, y0_dec=y0d1,
+                                  sample=rc.seeded_sampler(ref, lat, 5, dev, native=False), checkpoint_dir=td, checkpoint_after=2)
+    g = {"losses": np.array(r["losses"]), "y_pp": r["y_pp"], "h_dec": r["h_dec"][:, :, ::8].copy(), "trj": r["trj"][:, ::4].copy(),
+         "iter_count": r["iter_count"], "flens": np.array(flens)}
+    # decoder block on fresh (untrained) copies, eval mode
+    me, md = build_ref(enc, Pe).eval(), build_ref(dec, Pd).eval()
+    T = 120
+    f, _, _, _ = orc.synth_batch(2, T, 33)
+    d = rc.run_decoder_block(me, md, dev, feat=f[0].numpy(), feat_trg=f[1].numpy(), lat_dim=lat, n_smpl=300, y0_dec=y0d1,
+                             sample=rc.seeded_sampler(ref, lat, 6, dev, native=False))
+    for k, v in d.items():
+        g["dec_" + k] = v[::3].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "callers.npz"), **g)
+    print("callers.npz losses", r["losses"])
+
+
 def golden_chunks():
     """Bit-exact integer bookkeeping: exec the reference's own train_generator on fake loader batches."""
     src = open(os.path.join(REF, "src", "bin", "train_gru_cyclevae_gauss_batch.py")).read()
@@ -438,6 +477,6 @@ def golden_init():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["tiny", "cfg0", "flagship", "spk4", "spk4_cyc2", "decode512", "chunks", "init"]
+    which = sys.argv[1:] or ["tiny", "cfg0", "flagship", "spk4", "spk4_cyc2", "decode512", "callers", "chunks", "init"]
     for w in which:
         globals()["golden_" + w]()
