@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcyclevae_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -63,6 +63,9 @@ PROTOTYPES = {
     "cvb_kl_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cvb_mcd_l1_fwd": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "cvb_mcd_l1_bwd": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cvb_dtw_ws_bytes": (_sz, [_i, _i]),
+    "cvb_dtw_mcd": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "cvb_mcd_aligned": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "cvb_dropout_mask": (_i, [_sz, _f, _u64, _u64, _vp, _vp, _vp]),
     "cvb_state_advance": (_i, [_vp, _u64, _u64, _vp]),
     "cvb_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _f, _vp]),

@@ -11,6 +11,8 @@ cannot run here: h5py / dtw_c / pysptk are absent).
     convert          stage-6 conversion composition                 decode_*.py:303-305,318
     convert_utterances  the same for a list of ragged utterances, packed    new
     gv_postfilter    global-variance post-filter on the device      decode_*.py:419-420
+    mcd_aligned      mean / std MCD of aligned frames on the device  train_*.py:1435-1439 (dtw.calc_mcd)
+    dtw_org_to_trg   DTW of a trajectory onto the target, on device train_*.py:679-688   (dtw.dtw_org_to_trg)
     cvgv_stats       GV statistics of converted utterances          calc_cvgv_*.py:203,320-321
 """
 from __future__ import annotations
@@ -385,3 +387,35 @@ def cvgv_stats(converted: Sequence[torch.Tensor]):
     `gv_postfilter` divides the target speaker's GV by.  Stays on the device of the inputs (float64 accumulation)."""
     per_utt = torch.stack([c[:, 1:].double().var(dim=0, unbiased=False) for c in converted])
     return per_utt.mean(0), per_utt.var(dim=0, unbiased=False)
+
+
+# ------------------------------------------------------------------------------------------------
+def mcd_aligned(x: torch.Tensor, y: torch.Tensor, idx_x: Optional[torch.Tensor] = None, idx_y: Optional[torch.Tensor] = None):
+    """Mean and population std [dB] of the frame-wise mel-cepstral distortion of two aligned [T, D] CUDA tensors -- the
+    device-side replacement of `dtw.calc_mcd` at train_*.py:1435-1439 (no trajectory leaves the GPU).  idx_x / idx_y:
+    optional int64 frame indices (the speech-frame index_select of the call sites).  Returns a [2] tensor {mean, std}."""
+    assert x.is_cuda and y.is_cuda and x.shape[1] == y.shape[1]
+    xs, ys = x if x.stride(1) == 1 else x.contiguous(), y if y.stride(1) == 1 else y.contiguous()
+    n = int(idx_x.numel()) if idx_x is not None else int(xs.shape[0])
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.cvb_mcd_aligned(n, int(xs.shape[1]), xs.data_ptr(), int(xs.stride(0)), ys.data_ptr(), int(ys.stride(0)),
+                                  None if idx_x is None else idx_x.contiguous().data_ptr(), None if idx_y is None else idx_y.contiguous().data_ptr(),
+                                  ptr(out), torch.cuda.current_stream().cuda_stream), "cvb_mcd_aligned")
+    return out
+
+
+def dtw_org_to_trg(org: torch.Tensor, trg: torch.Tensor):
+    """Dynamic time warping of org [N, D] onto the time axis of trg [M, D] on the device (replaces `dtw.dtw_org_to_trg`,
+    train_*.py:679-688): MCD frame distance, symmetric step pattern.  Returns (aligned_org [M, D], path [M] int32 = the
+    source frame paired with each target frame, stats [3] = {mean MCD over target frames [dB], path steps, accumulated cost})."""
+    assert org.is_cuda and trg.is_cuda and org.shape[1] == trg.shape[1]
+    o, t = org.contiguous().float(), trg.contiguous().float()
+    N, M, D = int(o.shape[0]), int(t.shape[0]), int(o.shape[1])
+    ws = torch.empty(int(lib.cvb_dtw_ws_bytes(N, M)), dtype=torch.uint8, device=o.device)
+    path = torch.empty(M, dtype=torch.int32, device=o.device)
+    stats = torch.empty(3, dtype=torch.float32, device=o.device)
+    with torch.cuda.device(o.device):
+        check(lib.cvb_dtw_mcd(N, M, D, ptr(o), D, ptr(t), D, ws.data_ptr(), path.data_ptr(), ptr(stats),
+                              torch.cuda.current_stream().cuda_stream), "cvb_dtw_mcd")
+    return o[path.long()], path, stats

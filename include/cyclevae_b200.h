@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 10
+#define CVB_ABI_VERSION 11
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -162,6 +162,20 @@ int cvb_mcd_l1_fwd(int B, int T, int D, const float* x_bm, int ldx, int x_off, c
 int cvb_mcd_l1_bwd(int B, int T, int D, const float* x_bm, int ldx, int x_off, const float* y_bm,
                    int ldy, int y_off, const int32_t* flens, const float* d_sum,
                    const float* d_mean, float* dx_bm, void* stream);
+
+/* ---- evaluation metrics on the device (the reference calls the third-party dtw_c on the CPU) ------
+ * cvb_mcd_aligned: mean and population std of the frame distance MCD(x_t, y_t) = (10/ln10) sqrt(2 sum_d (x-y)^2) [dB] over
+ * n aligned frames (replaces dtw.calc_mcd at train_*.py:1435-1439).  idx_x / idx_y: optional int64 frame indices
+ * (the speech-frame gathers of the call sites), NULL = frames 0..n-1.  out2 = {mean, std}.
+ * cvb_dtw_mcd: dynamic time warping of org [N,D] onto trg [M,D] (replaces dtw.dtw_org_to_trg at train_*.py:679-688) with
+ * the MCD frame distance and the symmetric step pattern {(1,1),(1,0),(0,1)}, ties resolved in that order.
+ * path [M] (int32): the last org frame aligned with each target frame; out3 = {mean over target frames of
+ * MCD(org[path[j]], trg[j]), number of path steps, accumulated cost}.  ws: cvb_dtw_ws_bytes(N, M) bytes of scratch. */
+size_t cvb_dtw_ws_bytes(int N, int M);
+int cvb_dtw_mcd(int N, int M, int D, const float* org, int ldo, const float* trg, int ldt, void* ws,
+                int32_t* path, float* out3, void* stream);
+int cvb_mcd_aligned(int n, int D, const float* x, int ldx, const float* y, int ldy, const int64_t* idx_x,
+                    const int64_t* idx_y, float* out2, void* stream);
 
 /* ---- dropout masks (replacement of nn.Dropout's Bernoulli draw, gru_vae.py:303-304,312-313) ---
  * out[i] = (u_i >= p) ? 1/(1-p) : 0 with u from Philox4x32-10(seed, offset + i/4) */

@@ -1082,3 +1082,38 @@ def test_reference_caller_code_through_the_dropin(golden_dir, cvb, tmp_path):
     assert _paths()[0] == PATH_TC_FOLDED
     for k in ("cvmcep", "cvmcep_src", "cvmcep_trg"):
         assert d[k].dtype == np.float64 and _maxabs(d[k][::3].astype(np.float32), g["dec_" + k]) < TOL, k
+
+
+def test_device_mcd_and_dtw_metrics(cvb):
+    """the evaluation metrics of the training loop on the device against oracle/dtw_oracle.py
+    (dtw_c itself is not in the reference tree: parity unpinned, the published definitions are what is checked)."""
+    from cyclevae_vc_b200 import cycle
+    from oracle import dtw_oracle as dto
+    rng = np.random.default_rng(0)
+    x, y = rng.normal(size=(300, 50)).astype(np.float32), rng.normal(size=(300, 50)).astype(np.float32)
+    m = cycle.mcd_aligned(torch.tensor(x).cuda(), torch.tensor(y).cuda()).cpu().numpy()
+    rm, rs = dto.calc_mcd(x, y)
+    assert abs(m[0] - rm) < 1e-4 * rm and abs(m[1] - rs) < 1e-3 * rs
+    idx = np.sort(rng.choice(300, size=120, replace=False))
+    big = torch.tensor(np.c_[np.zeros((300, 4), np.float32), x]).cuda()            # [T, 54]: the call sites slice [:, stdim:]
+    m = cycle.mcd_aligned(big[:, 4:], torch.tensor(y).cuda(), torch.tensor(idx).cuda(), torch.tensor(idx).cuda()).cpu().numpy()
+    assert abs(m[0] - dto.calc_mcd(x[idx], y[idx])[0]) < 1e-4 * rm
+    # DTW: a time-warped, noisy copy must be aligned back; cost and path against the numpy dynamic programme
+    N, M = 173, 141
+    trg = np.cumsum(rng.normal(size=(M, 50)).astype(np.float32) * 0.3, axis=0)
+    warp = np.clip(np.round(np.linspace(0, M - 1, N) + rng.normal(size=N) * 1.5), 0, M - 1).astype(int)
+    warp.sort()
+    org = trg[warp] + 0.02 * rng.normal(size=(N, 50)).astype(np.float32)
+    al, path, st = cycle.dtw_org_to_trg(torch.tensor(org).cuda(), torch.tensor(trg).cuda())
+    path, st = path.cpu().numpy(), st.cpu().numpy()
+    ral, rpath, rmean, rsteps, rcost = dto.dtw_org_to_trg(org, trg)
+    assert path[0] >= 0 and path[-1] == N - 1 and (np.diff(path) >= 0).all()
+    assert st[2] == pytest.approx(rcost, rel=1e-4) and st[0] == pytest.approx(rmean, rel=1e-3)
+    assert (path == rpath).mean() > 0.98 and int(st[1]) == rsteps
+    assert _maxabs(al, org[path]) == 0.0
+    # exact case (integer-valued distances: no rounding differences, ties resolved in the same order)
+    a = rng.integers(0, 4, size=(40, 2)).astype(np.float32)
+    b = rng.integers(0, 4, size=(33, 2)).astype(np.float32)
+    _, p2, s2 = cycle.dtw_org_to_trg(torch.tensor(a).cuda(), torch.tensor(b).cuda())
+    _, rp2, _, rsteps2, _ = dto.dtw_org_to_trg(a, b)
+    assert (p2.cpu().numpy() == rp2).all() and int(s2[1]) == rsteps2

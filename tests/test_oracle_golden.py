@@ -321,3 +321,19 @@ def test_oracle_gradcheck_fp64():
         return o.sum() + (y * y).sum() + h.sum()
 
     assert torch.autograd.gradcheck(f, (x, y0, h0, w), eps=1e-6, atol=1e-6)
+
+
+def test_dtw_oracle_properties():
+    """oracle/dtw_oracle.py (the checker of the device metrics; dtw_c is not in the reference tree): identity alignment,
+    recovery of a pure time-stretch, MCD against its closed form."""
+    from oracle import dtw_oracle as dto
+    rng = np.random.default_rng(1)
+    x = np.cumsum(rng.normal(size=(60, 8)), axis=0)
+    al, path, mean, steps, cost = dto.dtw_org_to_trg(x, x)
+    assert (path == np.arange(60)).all() and mean == 0.0 and steps == 60 and cost == 0.0
+    stretched = np.repeat(x, 2, axis=0)
+    al, path, mean, steps, cost = dto.dtw_org_to_trg(stretched, x)
+    assert mean == 0.0 and (path == 2 * np.arange(60) + 1).all()      # the LAST source frame paired with each target frame
+    y = x + 0.5
+    m, s = dto.calc_mcd(x, y)
+    assert m == pytest.approx((10 / np.log(10)) * np.sqrt(2 * 8 * 0.25)) and s == pytest.approx(0.0, abs=1e-9)
