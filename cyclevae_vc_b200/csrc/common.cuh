@@ -46,6 +46,7 @@ static inline size_t round_up_sz(size_t a, size_t b) { return ceil_div_sz(a, b) 
 // process runs under Nsight Compute (which cannot replay a cooperative cluster launch: the capture dies at the first
 // one).  Co-residency of the whole grid is then guaranteed by the occupancy query on an otherwise idle device only.
 bool launch_without_coop();
+bool relaxed_polling();   // CVB_TC_POLL=relaxed: relaxed loads + one acquire fence instead of ld.acquire.gpu per poll (A/B; slower)
 
 struct DeviceInfo {
     int n_sm;
@@ -143,6 +144,24 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// polling without an acquire per poll (ld.acquire.gpu invalidates L1 on every iteration): relaxed loads, ONE acquire
+// fence once the value is seen -- the release / relaxed-read + fence pattern of the PTX memory model
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void spin_until_ge(const unsigned* ctr, unsigned target, bool relaxed) {
+    if (relaxed) {
+        while (ld_relaxed_gpu(ctr) < target) {
+        }
+        fence_acq_rel_gpu();
+    } else {
+        while (ld_acquire_gpu(ctr) < target) {
+        }
+    }
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

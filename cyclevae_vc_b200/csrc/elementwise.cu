@@ -47,27 +47,44 @@ int fill_rows(cudaStream_t s, float* dst, size_t rows, int cols, int ld, const f
     return 0;
 }
 
-// out[c] (+)= sum_r A[r, c]; block = 32 columns x 32 row-lanes, fixed reduction order
+// out[c] (+)= sum_r A[r, c]; block = 8 columns x 128 row-lanes (32-byte row segments, many blocks even for narrow
+// matrices), fixed reduction order: lane-strided partial sums, then a sequential sum over the 128 lanes
 __global__ void __launch_bounds__(1024) k_colsum(const float* __restrict__ A, int rows, int cols, int lda,
                                                  float* __restrict__ out, int accumulate) {
-    __shared__ float red[32][33];
-    int cx = threadIdx.x, ry = threadIdx.y;
-    int c = blockIdx.x * 32 + cx;
-    float acc = 0.f;
-    if (c < cols)
-        for (int r = ry; r < rows; r += 32) acc += A[(size_t)r * lda + c];
-    red[ry][cx] = acc;
+    __shared__ float red[128][9];
+    const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < cols) {
+        const float* p = A + c;
+        int r = ry;
+        for (; r + 384 < rows; r += 512) {
+            a0 += p[(size_t)r * lda];
+            a1 += p[(size_t)(r + 128) * lda];
+            a2 += p[(size_t)(r + 256) * lda];
+            a3 += p[(size_t)(r + 384) * lda];
+        }
+        for (; r < rows; r += 128) a0 += p[(size_t)r * lda];
+    }
+    red[ry][cx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ry < 8) {   // 16 lanes per thread, then 8 partials per column
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += red[ry * 16 + i][cx];
+        red[ry * 16][cx] = s;
+    }
     __syncthreads();
     if (ry == 0 && c < cols) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s += red[i][cx];
+        for (int i = 0; i < 8; ++i) s += red[i * 16][cx];
         out[c] = accumulate ? out[c] + s : s;
     }
 }
 int colsum(cudaStream_t s, const float* A, int rows, int cols, int lda, float* out, bool accumulate) {
     if (cols <= 0) return 0;
-    k_colsum<<<ceil_div(cols, 32), dim3(32, 32), 0, s>>>(A, rows, cols, lda, out, accumulate ? 1 : 0);
+    k_colsum<<<ceil_div(cols, 8), 1024, 0, s>>>(A, rows, cols, lda, out, accumulate ? 1 : 0);
     CVB_LAUNCH_CHECK();
     return 0;
 }

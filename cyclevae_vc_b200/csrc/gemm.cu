@@ -82,6 +82,13 @@ bool launch_without_coop() {
     return cached == 1;
 }
 
+bool relaxed_polling() {
+    // measured (round 2, B200, bench step): ld.acquire.gpu polling 25.69 ms, relaxed loads + one acquire fence 27.29 ms --
+    // the counter hop got slower (arrive -> seen 2000 -> 5000 cycles in the BPTT kernel), so acquire polling stays the default
+    const char* e = getenv("CVB_TC_POLL");
+    return e && (e[0] == 'r' || e[0] == 'R');
+}
+
 bool want_tc_gemm() {
     const char* e = getenv("CVB_GEMM");
     return !(e && (e[0] == 'c' || e[0] == 'C'));

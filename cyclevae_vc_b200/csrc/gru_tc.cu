@@ -85,6 +85,7 @@ struct GruTcArgs {
     unsigned* ctr;       // [0] = A, [32] = B (separate 128-B lines), zero-initialised
     int smem_max;
     int keepalive;
+    int relaxed;         // CVB_TC_POLL=relaxed: poll the arrival counters with relaxed loads + one acquire fence instead of ld.acquire
     long long* trace;    // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE_FWD), else null
 };
 
@@ -103,10 +104,6 @@ static __device__ __forceinline__ long long globaltimer_ns() {
         if (a.trace && c == 0) a.trace[(size_t)t * 64 + (ev)] = clock64(); \
     } while (0)
 
-static __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
-    while (ld_acquire_gpu(ctr) < target) {
-    }
-}
 static __device__ __forceinline__ void split8_f16(const float* x, uint4& hi, uint4& lo) {
     uint16_t h[8], l[8];
 #pragma unroll
@@ -183,40 +180,74 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         // threads take consecutive rows, so a quarter warp's stores cover 128 contiguous bytes (no bank conflicts) and
         // every global read is a full 32-byte sector
         const int n_items = TF_NW * L.nch * (TF_KC / 8);
-        for (int i = threadIdx.x; i < n_items; i += TF_NT) {
-            const int kg = i / TF_NW, n = i - kg * TF_NW;   // n = g*32 + unit of the block
-            const int g = n / TF_UB, ul = n - g * TF_UB;
-            const int kl = kg * 8;
-            const float4* src = reinterpret_cast<const float4*>(f.Whh + (size_t)(g * H + ublk0 + ul) * H + k0 + kl);
-            const float4 w0 = __ldg(src), w1 = __ldg(src + 1);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            uint4 hi, lo;
-            split8_f16(w, hi, lo);
-            const uint32_t off = (uint32_t)(kl / TF_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TF_KC) >> 3) * 128u +
-                                 (uint32_t)(n & 7) * 16u;
-            // chunks of the second half of the K walk are stored [lo rows | hi rows]: their stacked MMA starts at the
-            // correction columns and runs on into main1
-            const bool swapped = (kl / TF_KC) >= half1;
-            *reinterpret_cast<uint4*>(sW + off + (swapped ? (TF_NW / 8) * 1024u : 0u)) = hi;
-            *reinterpret_cast<uint4*>(sW + off + (swapped ? 0u : (TF_NW / 8) * 1024u)) = lo;
+        // batches of 8 items per thread with all 16 loads of a batch in flight before the first conversion (the loop used
+        // to expose one HBM round trip per item: 27 us of set-up per launch)
+        for (int i0 = threadIdx.x; i0 < n_items; i0 += 8 * TF_NT) {
+            float4 wv[16];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int i = i0 + m * TF_NT;
+                if (i < n_items) {
+                    const int kg = i / TF_NW, n = i - kg * TF_NW;   // n = g*32 + unit of the block
+                    const int g = n / TF_UB, ul = n - g * TF_UB;
+                    const float4* src = reinterpret_cast<const float4*>(f.Whh + (size_t)(g * H + ublk0 + ul) * H + k0 + kg * 8);
+                    wv[2 * m] = __ldg(src);
+                    wv[2 * m + 1] = __ldg(src + 1);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int i = i0 + m * TF_NT;
+                if (i < n_items) {
+                    const int kg = i / TF_NW, n = i - kg * TF_NW;
+                    const int kl = kg * 8;
+                    const float w[8] = {wv[2 * m].x, wv[2 * m].y, wv[2 * m].z, wv[2 * m].w, wv[2 * m + 1].x, wv[2 * m + 1].y, wv[2 * m + 1].z, wv[2 * m + 1].w};
+                    uint4 hi, lo;
+                    split8_f16(w, hi, lo);
+                    const uint32_t off = (uint32_t)(kl / TF_KC) * L.w_chunk_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)((kl % TF_KC) >> 3) * 128u +
+                                         (uint32_t)(n & 7) * 16u;
+                    // chunks of the second half of the K walk are stored [lo rows | hi rows]: their stacked MMA starts at the
+                    // correction columns and runs on into main1
+                    const bool swapped = (kl / TF_KC) >= half1;
+                    *reinterpret_cast<uint4*>(sW + off + (swapped ? (TF_NW / 8) * 1024u : 0u)) = hi;
+                    *reinterpret_cast<uint4*>(sW + off + (swapped ? 0u : (TF_NW / 8) * 1024u)) = lo;
+                }
+            }
         }
-        for (int i = threadIdx.x; i < 32 * 64; i += TF_NT) {   // B2[n = g*8+uu][k] = W_y[g*H + u0 + uu][k]; rows 24..31 zero
-            const int n = i >> 6, k = i & 63;
-            const float w = (n < 24 && k < out) ? f.Wy[(size_t)((n >> 3) * H + u0 + (n & 7)) * f.ldwy + k] : 0.f;
-            uint16_t hi, lo;
-            split_f16(w, hi, lo);
-            const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sB2 + off) = hi;
-            *reinterpret_cast<uint16_t*>(sB2 + 4096 + off) = lo;
-        }
-        for (int i = threadIdx.x; i < 64 * 16; i += TF_NT) {   // B3[n = o][k = uu] = W_o[o][u0 + uu]; k 8..15 zero
-            const int n = i >> 4, k = i & 15;
-            const float w = (k < 8 && n < out) ? f.Wo[(size_t)n * H + u0 + k] : 0.f;
-            uint16_t hi, lo;
-            split_f16(w, hi, lo);
-            const uint32_t off = (uint32_t)(n >> 3) * 256u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sB3 + off) = hi;
-            *reinterpret_cast<uint16_t*>(sB3 + 2048 + off) = lo;
+        {   // B2[n = g*8+uu][k] = W_y[g*H + u0 + uu][k]; rows 24..31 zero.  B3[n = o][k = uu] = W_o[o][u0 + uu]; k 8..15 zero
+            float w2[6], w3[3];   // all loads in flight before the first conversion
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const int i = threadIdx.x + m * TF_NT, n = i >> 6, k = i & 63;
+                w2[m] = (i < 32 * 64 && n < 24 && k < out) ? __ldg(f.Wy + (size_t)((n >> 3) * H + u0 + (n & 7)) * f.ldwy + k) : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int i = threadIdx.x + m * TF_NT, n = i >> 4, k = i & 15;
+                w3[m] = (i < 64 * 16 && k < 8 && n < out) ? __ldg(f.Wo + (size_t)n * H + u0 + k) : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const int i = threadIdx.x + m * TF_NT, n = i >> 6, k = i & 63;
+                if (i < 32 * 64) {
+                    uint16_t hi, lo;
+                    split_f16(w2[m], hi, lo);
+                    const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+                    *reinterpret_cast<uint16_t*>(sB2 + off) = hi;
+                    *reinterpret_cast<uint16_t*>(sB2 + 4096 + off) = lo;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int i = threadIdx.x + m * TF_NT, n = i >> 4, k = i & 15;
+                if (i < 64 * 16) {
+                    uint16_t hi, lo;
+                    split_f16(w3[m], hi, lo);
+                    const uint32_t off = (uint32_t)(n >> 3) * 256u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+                    *reinterpret_cast<uint16_t*>(sB3 + off) = hi;
+                    *reinterpret_cast<uint16_t*>(sB3 + 2048 + off) = lo;
+                }
+            }
         }
         for (int i = threadIdx.x; i < 8192 / 16; i += TF_NT) reinterpret_cast<uint4*>(sA2)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x < 24) sBh[threadIdx.x] = f.bhh[(threadIdx.x >> 3) * H + u0 + (threadIdx.x & 7)];
@@ -252,7 +283,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
             const uint16_t* srcy = a.yx + (size_t)(t & 1) * 2 * yx_part;
             if (lane == 0) {
-                spin_until(ctrA, (unsigned)G * (unsigned)(t + 1));   // the writers fenced generic -> async proxy before their release
+                spin_until_ge(ctrA, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);   // the writers fenced generic -> async proxy before their release
                 TF_TRACE(14);
                 TF_SKEW(4);
             }
@@ -273,7 +304,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 }
             }
             if (lane == 0) {
-                spin_until(ctrB, (unsigned)G * (unsigned)(t + 1));
+                spin_until_ge(ctrB, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);
                 TF_TRACE(13);
                 TF_SKEW(5);
                 mbar_wait(y_empty, ((uint32_t)t & 1) ^ 1);
@@ -587,7 +618,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 tc_fence_before();
                 if (rt == 0) TF_TRACE(26);
                 named_bar_sync(7, 256);   // a full barrier, not an arrive: thread 0's release after it must cover these warps' stores to `part`
-                if (rt == 0) spin_until(ctrA, (unsigned)G * (unsigned)(round + 1));
+                if (rt == 0) spin_until_ge(ctrA, (unsigned)G * (unsigned)(round + 1), a.relaxed != 0);
                 if (rt == 0) TF_TRACE(20);
                 named_bar_sync(2, 128);
             }
@@ -595,63 +626,32 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             uint16_t* yx = a.yx + (size_t)(round & 1) * 2 * yx_part;
             for (int qb = 0; qb < q_n; qb += 128) {
                 const int w = min(128, q_n - qb);
-                if (round > 0) {
-                    // stage the [G][w] block of partials of this CTA's pairs
-                    if (((n_pairs | Q | w) & 3) == 0) {
-                        const int w4 = w >> 2;
-                        const int dcc = 128 / w4, dpc = 128 - dcc * w4;
-                        int cc = rt / w4, pc = rt - cc * w4;
-                        const float* src = f.part + q_lo + qb;
-                        while (cc < G) {
-                            cp_async16(sRed + cc * w + 4 * pc, src + (size_t)cc * n_pairs + 4 * pc, true);
-                            cc += dcc;
-                            pc += dpc;
-                            if (pc >= w4) {
-                                pc -= w4;
-                                ++cc;
-                            }
-                        }
-                        cp_async_commit();
-                        cp_async_wait<0>();
-                    } else {
-                        const int RP = 128 / w;
-                        const int r0 = rt / w, qc = rt - r0 * w;
-                        if (r0 < RP) {
-                            const float* src = f.part + (size_t)r0 * n_pairs + q_lo + qb + qc;
-                            float* dstp = sRed + r0 * w + qc;
-                            for (int cc0 = 0; cc0 < G; cc0 += RP * LB) {
-                                float v[LB];
-#pragma unroll
-                                for (int k = 0; k < LB; ++k)
-                                    if (cc0 + k * RP + r0 < G) v[k] = __ldcg(src + (size_t)(cc0 + k * RP) * n_pairs);
-#pragma unroll
-                                for (int k = 0; k < LB; ++k)
-                                    if (cc0 + k * RP + r0 < G) dstp[(cc0 + k * RP) * w] = v[k];
-                            }
-                        }
-                    }
-                    if (rt == 0) TF_TRACE(27);
-                    named_bar_sync(2, 128);
-                }
-                // sum over the CTAs: nsub threads per pair, each a fixed subset, combined in fixed order (deterministic)
+                // sum over the CTAs: nsub threads per pair, each a fixed subset of the CTAs, combined in fixed order
+                // (deterministic).  The partials are read straight from L2 into registers, every load of a thread in
+                // flight at once (staging them through shared memory first cost a second round trip and a barrier).
                 const bool hoisted = (qb == 0);
                 const int nsub = hoisted ? nsub0 : 128 / w;
                 const int sub = hoisted ? sub0 : rt / w, qi = hoisted ? qi0 : rt - (rt / w) * w;
                 if (round > 0) {
                     if (sub < nsub) {
+                        const float* p = f.part + (size_t)sub * n_pairs + q_lo + qb + qi;
+                        const size_t stp = (size_t)nsub * n_pairs;
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        const float* p = sRed + sub * w + qi;
-                        const int stp = nsub * w;
-                        int cc = sub;
-                        for (; cc + 3 * nsub < G; cc += 4 * nsub, p += 4 * stp) {
-                            s0 += p[0];
-                            s1 += p[stp];
-                            s2 += p[2 * stp];
-                            s3 += p[3 * stp];
+                        for (int cc = sub; cc < G; cc += 48 * nsub, p += 48 * stp) {
+                            float v[48];
+#pragma unroll
+                            for (int k = 0; k < 48; ++k) v[k] = (cc + k * nsub < G) ? __ldcg(p + (size_t)k * stp) : 0.f;
+#pragma unroll
+                            for (int k = 0; k < 48; k += 4) {
+                                s0 += v[k];
+                                s1 += v[k + 1];
+                                s2 += v[k + 2];
+                                s3 += v[k + 3];
+                            }
                         }
-                        for (; cc < G; cc += nsub, p += stp) s0 += p[0];
                         sPs[sub * w + qi] = (s0 + s1) + (s2 + s3);
                     }
+                    if (rt == 0) TF_TRACE(27);
                     named_bar_sync(2, 128);
                 }
                 if (rt < w) {
@@ -774,6 +774,7 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + hx_f + yx_f);
     a.smem_max = di.max_smem_optin;
     a.keepalive = 1;
+    a.relaxed = relaxed_polling() ? 1 : 0;
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     a.trace = nullptr;
     const char* trace_file = getenv("CVB_TRACE_FILE_FWD");

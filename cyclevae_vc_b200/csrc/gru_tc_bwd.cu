@@ -81,6 +81,7 @@ struct GruTcBwdArgs {
     int S;
     int smem_max;
     int keepalive;      // CVB_TC_KEEPALIVE (default 1): dummy MMAs while the issuer polls
+    int relaxed;        // CVB_TC_POLL=relaxed: poll the arrival counters with relaxed loads + one acquire fence instead of ld.acquire
     long long* trace;   // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE), else null
 };
 
@@ -90,10 +91,6 @@ struct GruTcBwdArgs {
         if (a.trace && c == 0) a.trace[(size_t)n * 64 + (ev)] = clock64(); \
     } while (0)
 
-static __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
-    while (ld_acquire_gpu(ctr) < target) {
-    }
-}
 static __device__ __forceinline__ uint4 pack_bf16x8(const uint16_t* v) {
     return make_uint4((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16),
                       (uint32_t)v[4] | ((uint32_t)v[5] << 16), (uint32_t)v[6] | ((uint32_t)v[7] << 16));
@@ -180,23 +177,41 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 *reinterpret_cast<uint4*>(sW + (uint32_t)S * 1024u + o2) = lo;
             }
         }
-        for (int i = threadIdx.x; i < 16 * 64; i += TB_NT) {   // B2[n][k] = W_o[k][u0 + n]
-            const int n = i >> 6, k = i & 63;
-            const float w = (n < 8 && k < out) ? f.Wo[(size_t)k * H + u0 + n] : 0.f;
-            uint16_t hi, lo;
-            split_bf16(w, hi, lo);
-            const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sB2 + off) = hi;
-            *reinterpret_cast<uint16_t*>(sB2 + 2048 + off) = lo;
-        }
-        for (int i = threadIdx.x; i < 64 * 32; i += TB_NT) {   // B3[n = o][k = g*8+uu] = W_y[g*H + u0 + uu][o]
-            const int k = i >> 6, n = i & 63;
-            const float w = (k < 24 && n < out) ? f.Wy[(size_t)((k >> 3) * H + u0 + (k & 7)) * f.ldwy + n] : 0.f;
-            uint16_t hi, lo;
-            split_bf16(w, hi, lo);
-            const uint32_t off = (uint32_t)(n >> 3) * 512u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
-            *reinterpret_cast<uint16_t*>(sB3 + off) = hi;
-            *reinterpret_cast<uint16_t*>(sB3 + 4096 + off) = lo;
+        {   // B2[n][k] = W_o[k][u0 + n];  B3[n = o][k = g*8+uu] = W_y[g*H + u0 + uu][o]   (all loads in flight before the first conversion)
+            constexpr int M2 = (16 * 64 + TB_NT - 1) / TB_NT, M3 = (64 * 32 + TB_NT - 1) / TB_NT;
+            float w2[M2], w3[M3];
+#pragma unroll
+            for (int m = 0; m < M2; ++m) {
+                const int i = threadIdx.x + m * TB_NT, n = i >> 6, k = i & 63;
+                w2[m] = (i < 16 * 64 && n < 8 && k < out) ? __ldg(f.Wo + (size_t)k * H + u0 + n) : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < M3; ++m) {
+                const int i = threadIdx.x + m * TB_NT, k = i >> 6, n = i & 63;
+                w3[m] = (i < 64 * 32 && k < 24 && n < out) ? __ldg(f.Wy + (size_t)((k >> 3) * H + u0 + (k & 7)) * f.ldwy + n) : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < M2; ++m) {
+                const int i = threadIdx.x + m * TB_NT, n = i >> 6, k = i & 63;
+                if (i < 16 * 64) {
+                    uint16_t hi, lo;
+                    split_bf16(w2[m], hi, lo);
+                    const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+                    *reinterpret_cast<uint16_t*>(sB2 + off) = hi;
+                    *reinterpret_cast<uint16_t*>(sB2 + 2048 + off) = lo;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < M3; ++m) {
+                const int i = threadIdx.x + m * TB_NT, k = i >> 6, n = i & 63;
+                if (i < 64 * 32) {
+                    uint16_t hi, lo;
+                    split_bf16(w3[m], hi, lo);
+                    const uint32_t off = (uint32_t)(n >> 3) * 512u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+                    *reinterpret_cast<uint16_t*>(sB3 + off) = hi;
+                    *reinterpret_cast<uint16_t*>(sB3 + 4096 + off) = lo;
+                }
+            }
         }
         for (int i = threadIdx.x; i < 16384 / 16; i += TB_NT) reinterpret_cast<uint4*>(sA2)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x == 0) {
@@ -229,7 +244,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             const uint16_t* srcy = a.dyx + (size_t)(n & 1) * 2 * dy_part;
             if (n >= 1) {
                 if (lane == 0) {
-                    spin_until(ctrA, (unsigned)G * (unsigned)n);
+                    spin_until_ge(ctrA, (unsigned)G * (unsigned)n, a.relaxed != 0);
                         TB_TRACE(14);
                 }
                 __syncwarp();
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 const bool is_dy = (ch == nchunks - 1) && (n < T);
                 if (lane == 0) {
                     if (is_dy) {
-                        spin_until(ctrB, (unsigned)G * (unsigned)(n + 1));
+                        spin_until_ge(ctrB, (unsigned)G * (unsigned)(n + 1), a.relaxed != 0);
                         TB_TRACE(13);
                     }
                     mbar_wait(&empty[s], ph);
@@ -542,71 +557,39 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             float dy_deferred = 0.f;
             uint16_t* dyx = a.dyx + (size_t)(n & 1) * 2 * dy_part;
             if (n > 0) {
-                if (rt == 0) spin_until(ctrA, (unsigned)G * (unsigned)n);
+                if (rt == 0) spin_until_ge(ctrA, (unsigned)G * (unsigned)n, a.relaxed != 0);
                 if (rt == 0) TB_TRACE(20);
                 named_bar_sync(2, 128);
             }
             // dy_tot[t+1] += sum over the CTAs of the partials of step t+1 (fixed order); publish in operand order
             for (int qb = 0; qb < q_n; qb += 128) {
                 const int w = min(128, q_n - qb);
-                if (n > 0) {
-                    // stage the [G][w] block of partials of this CTA's pairs
-                    if (((n_pairs | Q | w) & 3) == 0) {
-                        // 16-byte cp.async.cg pieces (no registers, every piece in flight at once); no divisions inside
-                        const int w4 = w >> 2;
-                        const int dcc = 128 / w4, dpc = 128 - dcc * w4;
-                        int cc = rt / w4, pc = rt - cc * w4;
-                        const float* src = f.part + q_lo + qb;
-                        while (cc < G) {
-                            cp_async16(sRed + cc * w + 4 * pc, src + (size_t)cc * n_pairs + 4 * pc, true);
-                            cc += dcc;
-                            pc += dpc;
-                            if (pc >= w4) {
-                                pc -= w4;
-                                ++cc;
-                            }
-                        }
-                        cp_async_commit();
-                        cp_async_wait<0>();
-                    } else {
-                        const int RP = 128 / w;
-                        const int r0 = rt / w, qc = rt - r0 * w;
-                        if (r0 < RP) {
-                            const float* src = f.part + (size_t)r0 * n_pairs + q_lo + qb + qc;
-                            float* dstp = sRed + r0 * w + qc;
-                            for (int cc0 = 0; cc0 < G; cc0 += RP * LB) {
-                                float v[LB];
-#pragma unroll
-                                for (int k = 0; k < LB; ++k)
-                                    if (cc0 + k * RP + r0 < G) v[k] = __ldcg(src + (size_t)(cc0 + k * RP) * n_pairs);
-#pragma unroll
-                                for (int k = 0; k < LB; ++k)
-                                    if (cc0 + k * RP + r0 < G) dstp[(cc0 + k * RP) * w] = v[k];
-                            }
-                        }
-                    }
-                    if (rt == 0) TB_TRACE(27);
-                    named_bar_sync(2, 128);
-                }
-                // sum over the CTAs: nsub threads per pair, each a fixed subset, combined in fixed order (deterministic)
+                // sum over the CTAs: nsub threads per pair, each a fixed subset of the CTAs, combined in fixed order
+                // (deterministic).  The partials are read straight from L2 into registers, every load of a thread in
+                // flight at once (staging them through shared memory first cost a second round trip and a barrier).
                 const bool hoisted = (qb == 0);
                 const int nsub = hoisted ? nsub0 : 128 / w;
                 const int sub = hoisted ? sub0 : rt / w, qi = hoisted ? qi0 : rt - (rt / w) * w;
                 if (n > 0) {
                     if (sub < nsub) {
+                        const float* p = f.part + (size_t)sub * n_pairs + q_lo + qb + qi;
+                        const size_t stp = (size_t)nsub * n_pairs;
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        const float* p = sRed + sub * w + qi;
-                        const int stp = nsub * w;
-                        int cc = sub;
-                        for (; cc + 3 * nsub < G; cc += 4 * nsub, p += 4 * stp) {
-                            s0 += p[0];
-                            s1 += p[stp];
-                            s2 += p[2 * stp];
-                            s3 += p[3 * stp];
+                        for (int cc = sub; cc < G; cc += 48 * nsub, p += 48 * stp) {
+                            float v[48];
+#pragma unroll
+                            for (int k = 0; k < 48; ++k) v[k] = (cc + k * nsub < G) ? __ldcg(p + (size_t)k * stp) : 0.f;
+#pragma unroll
+                            for (int k = 0; k < 48; k += 4) {
+                                s0 += v[k];
+                                s1 += v[k + 1];
+                                s2 += v[k + 2];
+                                s3 += v[k + 3];
+                            }
                         }
-                        for (; cc < G; cc += nsub, p += stp) s0 += p[0];
                         sPs[sub * w + qi] = (s0 + s1) + (s2 + s3);
                     }
+                    if (rt == 0) TB_TRACE(27);
                     named_bar_sync(2, 128);
                 }
                 if (rt < w) {
@@ -743,6 +726,7 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     a.smem_max = di.max_smem_optin;
     a.trace = nullptr;
     a.keepalive = 1;
+    a.relaxed = relaxed_polling() ? 1 : 0;
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     const char* trace_file = getenv("CVB_TRACE_FILE");
     const size_t trace_bytes = (size_t)(f.T + 1) * 64 * sizeof(long long);

@@ -81,6 +81,7 @@ struct GruTcEvalArgs {
     int B, T, H;
     int smem_max;
     int keepalive;
+    int relaxed;         // CVB_TC_POLL=relaxed: poll the arrival counters with relaxed loads + one acquire fence instead of ld.acquire
     int rotate;          // CVB_TC_ROTATE (default 1): per-cluster start stage of the K walk
     long long* trace;    // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE_EVAL), else null
 };
@@ -90,10 +91,6 @@ struct GruTcEvalArgs {
         if (a.trace && c == 0) a.trace[(size_t)t * 64 + (ev)] = clock64(); \
     } while (0)
 
-static __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target) {
-    while (ld_acquire_gpu(ctr) < target) {
-    }
-}
 static __device__ __forceinline__ void split8_f16(const float* x, uint4& hi, uint4& lo) {
     uint16_t h[8], l[8];
 #pragma unroll
@@ -210,9 +207,10 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
                 // inboxes completed, i.e. after this CTA's outgoing partial sums (staged in the ring) were delivered, and
                 // after they finished reading the inbox the next exchange will overwrite.
                 const bool polls = lane < ncs || lane == 31;
-                const unsigned v = polls ? ld_acquire_gpu(flag) : 0u;
+                const unsigned v = polls ? (a.relaxed ? ld_relaxed_gpu(flag) : ld_acquire_gpu(flag)) : 0u;
                 const unsigned ready = __ballot_sync(0xffffffffu, polls && v >= target);
                 if (!(ready >> 31)) continue;
+                if (a.relaxed) fence_acq_rel_gpu();
                 while (issued < L.nsub) {
                     int che = issued + rot;
                     if (che >= L.nsub) che -= L.nsub;
@@ -541,6 +539,7 @@ int gru_ar_fwd_tc_eval(GruFwdArgs& f, float* scratch, const float* cfb, cudaStre
     a.H = H;
     a.smem_max = di.max_smem_optin;
     a.keepalive = 1;
+    a.relaxed = relaxed_polling() ? 1 : 0;
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     a.rotate = 1;
     if (const char* e = getenv("CVB_TC_ROTATE")) a.rotate = atoi(e) != 0;
