@@ -43,10 +43,14 @@ constexpr uint32_t TF_COL_M1 = 2 * TF_NW;
 constexpr uint32_t TF_COL_Y = 288;    // D2: W_y y for the own units, 32 main + 32 correction columns
 constexpr uint32_t TF_COL_P = 352;    // D3: partial of y_t, 64 main + 64 correction columns
 constexpr uint32_t TF_COL_DUMMY = 480;
+// y_t is pulled by every CTA at the same moment: 128 readers of the same 160 lines queue up in the L2 slices (the pull took
+// 1360 cycles on the luckiest SM and 3570 on the unluckiest).  The reducers publish TF_YREP copies; CTA c reads copy c % TF_YREP.
+constexpr int TF_YREP = 8;
 
 struct TfLayout {
     int MB, nch, NS;
-    uint32_t half, stage_bytes, w_chunk_bytes, slot_bytes;
+    uint32_t half, stage_bytes, w_chunk_bytes, slot_bytes, ybuf_bytes;
+    int Q;   // pairs (b, o) per reducer CTA, a multiple of 8
     uint32_t off_ring, off_ybuf, off_w, off_b2, off_b3, off_a2, off_inbox, off_bias, off_bar, total;
 };
 
@@ -60,14 +64,17 @@ __host__ __device__ inline TfLayout tf_layout(int B, int H, int G, int out, int 
     L.slot_bytes = (uint32_t)L.MB * 8u * 96u;                   // [rows][24 floats]
     uint32_t inbox = (uint32_t)TF_S * L.slot_bytes;
     inbox = (inbox + 127u) & ~127u;
-    const uint32_t fixed = L.stage_bytes + (uint32_t)L.nch * L.w_chunk_bytes + 8192u + 4096u + 8192u + inbox + 640u + 256u;
+    L.Q = 8 * ((8 * B + G - 1) / G);                             // tf_pairs_per_reducer
+    const uint32_t red_bytes = (uint32_t)(G * L.Q) * 4u;         // a reducer's block of partials: staged where the y operand lands
+    L.ybuf_bytes = ((L.stage_bytes > red_bytes ? L.stage_bytes : red_bytes) + 1023u) & ~1023u;
+    const uint32_t fixed = L.ybuf_bytes + (uint32_t)L.nch * L.w_chunk_bytes + 8192u + 4096u + 8192u + inbox + 640u + 256u;
     int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
     L.NS = ns > 6 ? 6 : ns;
     const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
     L.off_ring = 0;                       // h chunks only: idle between a step's last h chunk and the next step's first, when it
                                           // doubles as the staging of the outgoing partial sums
     L.off_ybuf = ring;                    // y_{t-1} operand (hi | lo), its own buffer: it lands while the exchange is under way
-    L.off_w = L.off_ybuf + L.stage_bytes;
+    L.off_w = L.off_ybuf + L.ybuf_bytes;
     L.off_b2 = L.off_w + (uint32_t)L.nch * L.w_chunk_bytes;   // W_y rows of the own units: [hi 4 groups][lo 4 groups] x 1 KB
     L.off_b3 = L.off_b2 + 8192u;          // W_o columns of the own units: [hi 8 groups][lo 8 groups] x 256 B
     L.off_a2 = L.off_b3 + 4096u;          // o_t of the own units: [2 parts][16 row groups][2 kblk][8][8]
@@ -81,7 +88,9 @@ __host__ __device__ inline TfLayout tf_layout(int B, int H, int G, int out, int 
 struct GruTcArgs {
     GruFwdArgs f;
     uint16_t* hx;        // [2 slots][2 parts][H/64 chunks][MB][8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
-    uint16_t* yx;        // [2 slots][2 parts][MB][8 kblk][8 rows][8 k] fp16 of y_t, zero-initialised
+    uint16_t* yx;        // [TF_YREP replicas][2 slots][2 parts][MB][8 kblk][8 rows][8 k] fp16 of y_t, zero-initialised
+    float* part;         // [G reducers][G CTAs][Q] partial sums of y_t (part_walk)
+    int yrep;            // replicas of y_t actually published / read (1..TF_YREP, CVB_TC_YREP)
     unsigned* ctr;       // [0] = A, [32] = B (separate 128-B lines), zero-initialised
     int smem_max;
     int keepalive;
@@ -99,6 +108,11 @@ static __device__ __forceinline__ long long globaltimer_ns() {
     do {                                                                                                    \
         if (a.trace && t == 40) a.trace[(size_t)(T + 1) * 64 + (size_t)(slot) * 256 + c] = globaltimer_ns(); \
     } while (0)
+// per-CTA phase stamps (clock64 of the CTA's own SM: differences within a CTA are exact) of steps 40 and 41
+#define TF_PH(slot)                                                                                                          \
+    do {                                                                                                                     \
+        if (a.trace && (t == 40 || t == 41)) a.trace[(size_t)(T + 1) * 64 + 8 * 256 + (size_t)((t - 40) * 24 + (slot)) * 256 + c] = clock64(); \
+    } while (0)
 #define TF_TRACE(ev)                                                     \
     do {                                                                 \
         if (a.trace && c == 0) a.trace[(size_t)t * 64 + (ev)] = clock64(); \
@@ -113,17 +127,52 @@ static __device__ __forceinline__ void split8_f16(const float* x, uint4& hi, uin
     lo = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
                     (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
 }
-// drain columns [o_lo, o_hi) of D3 (main + correction halves) of this warp's 32 TMEM lanes into part[c][o][b]
-static __device__ __forceinline__ void drain_partial_y(uint32_t taddr_p, float* pd, int o_lo, int o_hi, int out, int B, bool row_ok) {
-    for (int o0 = o_lo; o0 < o_hi && o0 < out; o0 += 16) {
+// The partial sums of y_t.  Pairs are numbered q = b * 64 + o (the output axis padded to 64: D3's columns beyond out_dim
+// are exact zeros) and reducer CTA r owns the Q = 8 * ceil(8 B / G) pairs [r Q, (r + 1) Q), i.e. whole groups of 8
+// consecutive outputs of one row.  CTA c's partial of pair q lives at part[r = q / Q][c][q % Q]: everything reducer r sums
+// is ONE contiguous block of G * Q floats (a single bulk copy), a draining thread (fixed b, walking o) writes float4s, and
+// the reducer publishes a group as one 16-byte core-matrix row per plane.  (The first version -- pair order [o][b],
+// scalar stores addressed as base + index -- compiled to ~20 dependent instructions per store: 2400 cycles per step.)
+struct PartWalk {
+    unsigned long long addr;   // address of the thread's first float4
+    unsigned long long wrap;   // extra bytes when the slot index wraps into the next reducer
+    int i, Q;                  // slot of that float4 in the reducer's row
+};
+static __device__ __forceinline__ PartWalk part_walk(float* part, int c, int G, int Q, int b, int o_first) {
+    PartWalk w;
+    w.Q = Q;
+    const int q0 = b * 64 + o_first;
+    const int r0 = q0 / Q;
+    w.i = q0 - r0 * Q;
+    w.addr = reinterpret_cast<unsigned long long>(part + ((size_t)r0 * G + c) * Q + w.i);
+    w.wrap = ((unsigned long long)G * Q - Q) * 4ull;
+    asm volatile("" : "+l"(w.addr), "+r"(w.i));   // keep them in registers: no rematerialisation per store
+    return w;
+}
+static __device__ __forceinline__ void st_global_v4(unsigned long long addr, float x, float y, float z, float w) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// drain 32 columns (outputs [o_lo, o_lo + 32)) of D3 (main + correction halves) of this warp's 32 TMEM lanes into `part`
+static __device__ __forceinline__ void drain_partial_y(uint32_t taddr_p, const PartWalk& w, int o_lo, bool row_ok) {
+    unsigned long long addr = w.addr;
+    int i = w.i;
+#pragma unroll
+    for (int o0 = o_lo; o0 < o_lo + 32; o0 += 16) {
         float v[16], v2[16];
         tmem_ld_x16(taddr_p + o0, v);
         tmem_ld_x16(taddr_p + 64 + o0, v2);
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (o0 + q < out) pd[(size_t)(o0 + q) * B] = fmaf(v2[q], F16_LO_INV, v[q]);
+        for (int q = 0; q < 16; q += 4) {
+            if (row_ok)
+                st_global_v4(addr, fmaf(v2[q], F16_LO_INV, v[q]), fmaf(v2[q + 1], F16_LO_INV, v[q + 1]), fmaf(v2[q + 2], F16_LO_INV, v[q + 2]),
+                             fmaf(v2[q + 3], F16_LO_INV, v[q + 3]));
+            addr += 16;
+            i += 4;
+            if (i >= w.Q) {
+                i -= w.Q;
+                addr += w.wrap;
+            }
         }
     }
 }
@@ -160,6 +209,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     uint64_t* d1_full = full + 24;      // D1 (K-slice of W_hh h) complete
     uint64_t* y_full = full + 25;
     uint64_t* y_empty = full + 26;
+    uint64_t* red_full = full + 27;     // the reducers' block of partials has landed in sRed
     uint8_t* ybuf = smem + L.off_ybuf;
     uint64_t* inbox_full = accum_full + 1;
     uint64_t* a2_full = inbox_full + 1;
@@ -167,6 +217,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_full + 1);
     const size_t hx_part = (size_t)(H / TF_KC) * L.MB * 512;   // elements per part
     const size_t yx_part = (size_t)L.MB * 512;
+    const size_t yx_rep = 4 * yx_part;                         // one replica: [2 slots][2 parts]
     unsigned* ctrA = a.ctr;
     unsigned* ctrB = a.ctr + 32;
     const int n_pairs = B * out;
@@ -263,6 +314,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             mbar_init(inbox_full, 1);   // armed with expect_tx(S slots) every step; the peers' bulk copies complete_tx
             mbar_init(a2_full, 128);
             mbar_init(part_full, 1);
+            mbar_init(red_full, 1);
             mbar_fence_init();
         }
         fence_proxy_async_smem();
@@ -281,11 +333,12 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         uint32_t ph = 1;
         for (int t = 0; t < T; ++t) {
             const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
-            const uint16_t* srcy = a.yx + (size_t)(t & 1) * 2 * yx_part;
+            const uint16_t* srcy = a.yx + (size_t)(c % a.yrep) * yx_rep + (size_t)(t & 1) * 2 * yx_part;
             if (lane == 0) {
                 spin_until_ge(ctrA, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);   // the writers fenced generic -> async proxy before their release
                 TF_TRACE(14);
                 TF_SKEW(4);
+                TF_PH(11);
             }
             __syncwarp();
             for (int ch = 0; ch < L.nch; ++ch) {
@@ -307,6 +360,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 spin_until_ge(ctrB, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);
                 TF_TRACE(13);
                 TF_SKEW(5);
+                TF_PH(12);
                 mbar_wait(y_empty, ((uint32_t)t & 1) ^ 1);
                 mbar_expect_tx(y_full, 2 * L.half);
                 bulk_g2s(ybuf, srcy, L.half, y_full);
@@ -401,6 +455,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
         const uint32_t slot_f = L.slot_bytes / 4;
         float hreg[8];
+        const PartWalk pw = part_walk(a.part, c, G, L.Q, b, 32);   // this thread drains outputs [32, 64) of its row
         // prologue: publish h_in (slot 0) in operand order
         {
             const int t = 0;
@@ -422,7 +477,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             const size_t row = (size_t)t * B + (act ? b : 0);
             float4 gxv[6];
             float4 mk[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
-            if (act) {
+            {   // every lane loads (the rows beyond B re-read row 0 of the frame: `row`), so the gate math below is branch-free
                 const float* gp = f.gx + row * 3 * H + u0;
 #pragma unroll
                 for (int gi = 0; gi < 3; ++gi) {
@@ -435,9 +490,11 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 }
             }
             if (etid == 0) TF_TRACE(0);
+            if (etid == 0) TF_PH(0);
             if (etid == 0) mbar_expect_tx(inbox_full, (uint32_t)TF_S * L.slot_bytes);
             mbar_wait(d1_full, (uint32_t)t & 1);
             if (etid == 0) TF_TRACE(1);
+            if (etid == 0) TF_PH(1);
             tc_fence_after();
             // partial sums (main + correction) of the block's units -> the finalisers' inboxes
 #pragma unroll
@@ -474,10 +531,12 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 bulk_s2c(mapa(inbox_addr + (uint32_t)j * L.slot_bytes, (uint32_t)etid), stage + (size_t)etid * slot_f, L.slot_bytes,
                          mapa(inbox_bar_addr, (uint32_t)etid));
             if (etid == 0) TF_TRACE(2);
+            if (etid == 0) TF_PH(2);
             // W_y y_{t-1} of the own units: columns [r 8 | z 8 | n 8 | pad 8] (+ correction half at +32)
             float yr[8], yz[8], yn[8];
             mbar_wait(accum_full, (uint32_t)t & 1);
             if (etid == 0) TF_TRACE(4);
+            if (etid == 0) TF_PH(3);
             tc_fence_after();
             {
                 float c2[8];
@@ -500,13 +559,18 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             tc_fence_before();
             mbar_wait_cluster(inbox_full, (uint32_t)t & 1);
             if (etid == 0) TF_TRACE(3);
+            if (etid == 0) TF_PH(4);
+            // Straight-line code for every lane, active row or not (the rows beyond B hold garbage that is never stored): with
+            // the math of each unit inside an `if (act)` the compiler kept eight separate branch regions and the eight
+            // dependent chains LDS -> ex2 -> rcp -> ex2 -> rcp ran one after the other (2500 cycles per step; per-CTA phase stamps).
             float ar[8], az[8], an[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) ar[q] = az[q] = an[q] = 0.f;
-            if (act) {
+            {
+                const int bs = b < L.MB * 8 ? b : 0;   // rows beyond the staged row groups read row 0 (in bounds)
 #pragma unroll
                 for (int p = 0; p < TF_S; ++p) {   // fixed order: deterministic
-                    const float4* x = reinterpret_cast<const float4*>(inbox + (size_t)p * slot_f + b * 24);
+                    const float4* x = reinterpret_cast<const float4*>(inbox + (size_t)p * slot_f + bs * 24);
                     const float4 x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3], x4 = x[4], x5 = x[5];
                     ar[0] += x0.x; ar[1] += x0.y; ar[2] += x0.z; ar[3] += x0.w; ar[4] += x1.x; ar[5] += x1.y; ar[6] += x1.z; ar[7] += x1.w;
                     az[0] += x2.x; az[1] += x2.y; az[2] += x2.z; az[3] += x2.w; az[4] += x3.x; az[5] += x3.y; az[6] += x3.z; az[7] += x3.w;
@@ -520,21 +584,21 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 const float* gxz = reinterpret_cast<const float*>(&gxv[2]);
                 const float* gxn = reinterpret_cast<const float*>(&gxv[4]);
                 const float* mkf = reinterpret_cast<const float*>(&mk[0]);
+                float bh[24];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) *reinterpret_cast<float4*>(bh + 4 * q) = *reinterpret_cast<const float4*>(sBh + 4 * q);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    if (act) {
-                        rr[q] = sigmoid_fast(gxr[q] + yr[q] + ar[q] + sBh[q]);
-                        zz[q] = sigmoid_fast(gxz[q] + yz[q] + az[q] + sBh[8 + q]);
-                        gh[q] = an[q] + sBh[16 + q];
-                        nn[q] = tanh_fast(gxn[q] + yn[q] + rr[q] * gh[q]);
-                        hreg[q] = (1.0f - zz[q]) * nn[q] + zz[q] * hreg[q];
-                        ov[q] = hreg[q] * mkf[q];
-                    } else {
-                        rr[q] = zz[q] = nn[q] = gh[q] = ov[q] = 0.f;
-                    }
+                    rr[q] = sigmoid_fast(gxr[q] + yr[q] + ar[q] + bh[q]);
+                    zz[q] = sigmoid_fast(gxz[q] + yz[q] + az[q] + bh[8 + q]);
+                    gh[q] = an[q] + bh[16 + q];
+                    nn[q] = tanh_fast(gxn[q] + yn[q] + rr[q] * gh[q]);
+                    hreg[q] = (1.0f - zz[q]) * nn[q] + zz[q] * hreg[q];
+                    ov[q] = hreg[q] * mkf[q];
                 }
             }
             if (etid == 0) TF_TRACE(10);
+            if (etid == 0) TF_PH(5);
             uint4 oh, ol, hh, hl;
             split8_f16(ov, oh, ol);
             split8_f16(hreg, hh, hl);
@@ -556,16 +620,23 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             if (etid == 0) TF_TRACE(7);
             fence_proxy_async_global();   // own generic writes of h_t -> visible to the peers' bulk copies (async proxy)
             if (etid == 0) TF_TRACE(8);
+            if (etid == 0) TF_PH(6);
             if (out > 32) {   // second half of the partial accumulator (the aux warps drain [0, 32))
                 mbar_wait(part_full, (uint32_t)t & 1);
+                if (etid == 0) TF_PH(7);
                 tc_fence_after();
-                drain_partial_y(taddr + TF_COL_P, f.part + (size_t)c * n_pairs + b, 32, 64, out, B, act);
+                drain_partial_y(taddr + TF_COL_P, pw, 32, act);
                 tc_fence_before();
+                if (etid == 0) TF_PH(19);
+                fence_proxy_async_global();   // the reducers pull the partials with a bulk copy (async proxy)
             }
+            if (etid == 0) TF_PH(8);
             named_bar_sync(7, 256);    // every finaliser published; D3 is drained into `part`
+            if (etid == 0) TF_PH(9);
             if (etid == 0) TF_SKEW(0);
             if (etid == 0) red_release_gpu_add(ctrA, 1u);   // release is cumulative over the barrier: one gpu-scope fence per CTA
             if (etid == 0) TF_TRACE(9);
+            if (etid == 0) TF_PH(10);
             if (etid == 0) TF_SKEW(1);
             if (act) {   // off the critical path: outputs / saved activations that only later kernels read
                 float* hd = f.hs + (size_t)(t + 1) * B * H + (size_t)b * H + u0;
@@ -591,21 +662,25 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     } else if (warp >= 8) {
         // ================= aux: drain of D3, y reduction + publication ===================================
         const int rt = threadIdx.x - 256;
-        const int Q = (n_pairs + G - 1) / G;
+        const int Q = L.Q;
         const int q_lo = c * Q;
-        const int q_n = max(0, min(Q, n_pairs - q_lo));
+        const int q_n = max(0, min(Q, B * 64 - q_lo));   // whole groups of 8: Q and 64 are multiples of 8
         const uint32_t taddr = tmem + ((uint32_t)((warp - 8) * 32) << 16) + TF_COL_P;
-        constexpr int LB = 8;
-        // per-thread constants of the first (normally the only) block of pairs: no division / bias load inside the rounds
+        const PartWalk pw = part_walk(a.part, c, G, Q, rt, 0);     // this thread drains outputs [0, 32) of row rt
+        const uint32_t red_bytes = (uint32_t)(G * Q) * 4u;         // this reducer's block: [G CTAs][Q pairs]
+        const float* red_src = a.part + (size_t)c * G * Q;
+        const int yrep = a.yrep;
+        // per-thread constants of the first (normally the only) block of pairs
         const int w0 = min(128, q_n);
         const int nsub0 = w0 > 0 ? 128 / w0 : 1;
         const int sub0 = w0 > 0 ? rt / w0 : 0, qi0 = w0 > 0 ? rt - sub0 * w0 : 0;
-        int o0 = 0, bb0 = 0;
-        float bias0 = 0.f, y_deferred = 0.f;
-        if (rt < w0) {
-            o0 = (q_lo + rt) / B;
-            bb0 = (q_lo + rt) - o0 * B;
-            bias0 = f.bo[o0];
+        const int ng0 = w0 >> 3;
+        const int rep0 = ng0 > 0 ? rt / ng0 : 0, g0 = ng0 > 0 ? rt - rep0 * ng0 : 0;   // no division inside the rounds
+        float bias0[8];   // b_o of this thread's group in the first block (zero on the padding outputs)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int o = (q_lo + 8 * g0 + e) & 63;
+            bias0[e] = (o < out) ? __ldg(f.bo + o) : 0.f;
         }
         // round 0 publishes y_in; round r >= 1 reduces the partials of step r-1 into y_{r-1}
         for (int round = 0; round <= T; ++round) {
@@ -614,84 +689,113 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 // drain D3 of step round-1 (outputs [0, 32) of this CTA's partial)
                 mbar_wait(part_full, (uint32_t)(round - 1) & 1);
                 tc_fence_after();
-                drain_partial_y(taddr, f.part + (size_t)c * n_pairs + rt, 0, 32, out, B, rt < B);
+                drain_partial_y(taddr, pw, 0, rt < B);
                 tc_fence_before();
+                fence_proxy_async_global();   // generic stores -> the reducers' bulk copies (async proxy)
                 if (rt == 0) TF_TRACE(26);
                 named_bar_sync(7, 256);   // a full barrier, not an arrive: thread 0's release after it must cover these warps' stores to `part`
-                if (rt == 0) spin_until_ge(ctrA, (unsigned)G * (unsigned)(round + 1), a.relaxed != 0);
-                if (rt == 0) TF_TRACE(20);
-                named_bar_sync(2, 128);
+                if (rt == 0 && q_n > 0) {
+                    spin_until_ge(ctrA, (unsigned)G * (unsigned)(round + 1), a.relaxed != 0);
+                    TF_TRACE(20);
+                    TF_PH(13);
+                    // every CTA's partials of this reducer's pairs are one contiguous block: one bulk copy into sRed
+                    mbar_expect_tx(red_full, red_bytes);
+                    bulk_g2s(sRed, red_src, red_bytes, red_full);
+                }
+                if (q_n > 0) mbar_wait(red_full, (uint32_t)(round - 1) & 1);
+                if (rt == 0) TF_PH(14);
             }
             float* ydst = f.ys + (size_t)round * n_pairs;
             uint16_t* yx = a.yx + (size_t)(round & 1) * 2 * yx_part;
+            float ydef[8];
+            int ydef_b = -1, ydef_o = 0;   // the fp32 outputs of the last block are stored after the release (only later kernels read them)
             for (int qb = 0; qb < q_n; qb += 128) {
                 const int w = min(128, q_n - qb);
-                // sum over the CTAs: nsub threads per pair, each a fixed subset of the CTAs, combined in fixed order
-                // (deterministic).  The partials are read straight from L2 into registers, every load of a thread in
-                // flight at once (staging them through shared memory first cost a second round trip and a barrier).
+                // sum over the CTAs: nsub threads per pair, each a fixed subset of the CTAs (every nsub-th, four interleaved
+                // accumulators), combined in fixed order: deterministic
                 const bool hoisted = (qb == 0);
                 const int nsub = hoisted ? nsub0 : 128 / w;
                 const int sub = hoisted ? sub0 : rt / w, qi = hoisted ? qi0 : rt - (rt / w) * w;
                 if (round > 0) {
                     if (sub < nsub) {
-                        const float* p = f.part + (size_t)sub * n_pairs + q_lo + qb + qi;
-                        const size_t stp = (size_t)nsub * n_pairs;
+                        const float* p = sRed + (size_t)sub * Q + qb + qi;
+                        const int stp = nsub * Q;
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        for (int cc = sub; cc < G; cc += 48 * nsub, p += 48 * stp) {
-                            float v[48];
-#pragma unroll
-                            for (int k = 0; k < 48; ++k) v[k] = (cc + k * nsub < G) ? __ldcg(p + (size_t)k * stp) : 0.f;
-#pragma unroll
-                            for (int k = 0; k < 48; k += 4) {
-                                s0 += v[k];
-                                s1 += v[k + 1];
-                                s2 += v[k + 2];
-                                s3 += v[k + 3];
-                            }
+                        int cc = sub;
+                        for (; cc + 3 * nsub < G; cc += 4 * nsub, p += 4 * stp) {
+                            s0 += p[0];
+                            s1 += p[stp];
+                            s2 += p[2 * stp];
+                            s3 += p[3 * stp];
                         }
+                        if (cc < G) s0 += p[0];
+                        if (cc + nsub < G) s1 += p[stp];
+                        if (cc + 2 * nsub < G) s2 += p[2 * stp];
                         sPs[sub * w + qi] = (s0 + s1) + (s2 + s3);
                     }
                     if (rt == 0) TF_TRACE(27);
                     named_bar_sync(2, 128);
+                    if (rt == 0) TF_PH(16);
                 }
-                if (rt < w) {
-                    int o, bb;
-                    float bias;
-                    if (hoisted) {
-                        o = o0;
-                        bb = bb0;
-                        bias = bias0;
-                    } else {
-                        const int qq = q_lo + qb + rt;
-                        o = qq / B;   // pair order of `part` is [o][b]
-                        bb = qq - o * B;
-                        bias = f.bo[o];
-                    }
-                    float yv;
+                // publication: thread (group g of 8 consecutive outputs of one row, replica rep) -> one 16-byte core-matrix row per plane
+                const int ng = w >> 3;
+                const int rep = hoisted ? rep0 : rt / ng, g = hoisted ? g0 : rt - (rt / ng) * ng;
+                if (rep < yrep) {
+                    const int q0 = q_lo + qb + 8 * g;
+                    const int bb = q0 >> 6, o = q0 & 63;
+                    float yv[8];
                     if (round > 0) {
-                        float sacc = sPs[rt];
-                        for (int k = 1; k < nsub; ++k) sacc += sPs[k * w + rt];
-                        yv = sacc + bias;
-                        if (hoisted) y_deferred = yv;   // the fp32 output is stored after the release (only later kernels read it)
-                        else ydst[(size_t)bb * out + o] = yv;
+                        float bias[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) bias[e] = hoisted ? bias0[e] : __ldg(f.bo + min(o + e, out - 1));   // every load in flight at once
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) yv[e] = sPs[8 * g + e];
+                        for (int k = 1; k < nsub; ++k) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) yv[e] += sPs[k * w + 8 * g + e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) yv[e] = (o + e < out) ? yv[e] + bias[e] : 0.f;
                     } else {
-                        yv = f.ys[(size_t)bb * out + o];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) yv[e] = f.ys[(size_t)bb * out + min(o + e, out - 1)];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) yv[e] = (o + e < out) ? yv[e] : 0.f;
                     }
-                    uint16_t hi, lo;
-                    split_f16(yv, hi, lo);
-                    const size_t off = (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8 + (size_t)(o & 7);
-                    yx[off] = hi;
-                    yx[yx_part + off] = lo;
+                    uint4 hi, lo;
+                    split8_f16(yv, hi, lo);
+                    uint16_t* dst = yx + (size_t)rep * yx_rep + (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8;
+                    *reinterpret_cast<uint4*>(dst) = hi;
+                    *reinterpret_cast<uint4*>(dst + yx_part) = lo;
+                    if (round > 0 && rep == 0) {
+                        if (qb + 128 >= q_n) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) ydef[e] = yv[e];
+                            ydef_b = bb;
+                            ydef_o = o;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (o + e < out) ydst[(size_t)bb * out + o + e] = yv[e];
+                        }
+                    }
                 }
                 if (qb + 128 < q_n) named_bar_sync(2, 128);
             }
             if (rt == 0) TF_TRACE(21);
             if (rt == 0) TF_SKEW(2);
+            if (rt == 0) TF_PH(17);
             fence_proxy_async_global();
             named_bar_sync(2, 128);
+            if (rt == 0) TF_PH(18);
             if (rt == 0) red_release_gpu_add(ctrB, 1u);
             if (rt == 0) TF_SKEW(3);
-            if (round > 0 && rt < w0) ydst[(size_t)bb0 * out + o0] = y_deferred;
+            if (rt == 0) TF_PH(15);
+            if (ydef_b >= 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (ydef_o + e < out) ydst[(size_t)ydef_b * out + ydef_o + e] = ydef[e];
+            }
             if (rt == 0) TF_TRACE(22);
         }
     }
@@ -707,11 +811,18 @@ bool gru_tc_shape_ok(int B, int H, int out) {
     return H % (TF_KC * TF_S) == 0 && H >= TF_KC * TF_S && out >= 1 && out <= 64 && B >= 1 && B <= 128;
 }
 
+// floats of the partial-sum buffer part[G reducers][G CTAs][Q]
+static size_t tf_part_floats(int B, int H) {
+    const size_t G = (size_t)H / 8;
+    const size_t Q = 8 * (((size_t)8 * B + G - 1) / G);
+    return round_up_sz(G * G * Q, 64);
+}
+
 size_t gru_tc_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
     size_t hx = (size_t)2 * 2 * (H / TF_KC) * MB * 512 / 2;   // fp16 elements -> floats
-    size_t yx = (size_t)2 * 2 * MB * 512 / 2;
-    return round_up_sz(hx, 64) + round_up_sz(yx, 64) + 64;
+    size_t yx = (size_t)TF_YREP * 2 * 2 * MB * 512 / 2;
+    return round_up_sz(hx, 64) + round_up_sz(yx, 64) + 64 + tf_part_floats(B, H);
 }
 
 // are all G/4 clusters co-resident at this shape?  (cached per shape)
@@ -727,10 +838,7 @@ static bool fwd_runnable(int B, int H, int out, const DeviceInfo& di, TfLayout* 
     TfLayout L = tf_layout(B, H, G, out, di.max_smem_optin);
     if (ok < 0) {
         ok = 0;
-        const int Q = (B * out + G - 1) / G;
-        const uint32_t red_bytes = (uint32_t)(G * (Q < 128 ? Q : 128)) * 4u;
         if (L.NS >= 2 && (int)L.total <= di.max_smem_optin && (uint32_t)L.NS * L.stage_bytes >= (uint32_t)TF_S * L.slot_bytes &&
-            red_bytes <= L.stage_bytes &&
             cudaFuncSetAttribute(k_gru_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(G);
@@ -768,17 +876,20 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     GruTcArgs a;
     a.f = f;
     const size_t hx_f = round_up_sz((size_t)2 * 2 * (f.H / TF_KC) * L.MB * 512 / 2, 64);
-    const size_t yx_f = round_up_sz((size_t)2 * 2 * L.MB * 512 / 2, 64);
+    const size_t yx_f = round_up_sz((size_t)TF_YREP * 2 * 2 * L.MB * 512 / 2, 64);
     a.hx = reinterpret_cast<uint16_t*>(tc_scratch);
     a.yx = reinterpret_cast<uint16_t*>(tc_scratch + hx_f);
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + hx_f + yx_f);
+    a.part = tc_scratch + hx_f + yx_f + 64;
+    a.yrep = TF_YREP;
+    if (const char* e = getenv("CVB_TC_YREP")) a.yrep = max(1, min(TF_YREP, atoi(e)));
     a.smem_max = di.max_smem_optin;
     a.keepalive = 1;
     a.relaxed = relaxed_polling() ? 1 : 0;
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     a.trace = nullptr;
     const char* trace_file = getenv("CVB_TRACE_FILE_FWD");
-    const size_t trace_bytes = ((size_t)(f.T + 1) * 64 + 8 * 256) * sizeof(long long);
+    const size_t trace_bytes = ((size_t)(f.T + 1) * 64 + 8 * 256 + 48 * 256) * sizeof(long long);
     if (trace_file && trace_file[0]) {
         CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
         CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));

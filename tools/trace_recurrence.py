@@ -54,12 +54,39 @@ def run(tag):
     return path
 
 
+PH_FWD = [("fin  step top -> D1 (W_hh h) complete", 0, 0, 1, 0), ("fin  D1 drained, exchange copies issued", 1, 0, 2, 0),
+          ("fin  -> W_y y accumulator complete", 2, 0, 3, 0), ("fin  -> inbox complete", 3, 0, 4, 0), ("fin  partial sums + gates", 4, 0, 5, 0),
+          ("fin  splits, o staged, h published, proxy fence", 5, 0, 6, 0), ("fin  -> D3 (partial y) complete", 6, 0, 7, 0),
+          ("fin  drain of D3 -> part", 7, 0, 8, 0), ("fin  barrier with the aux warps", 8, 0, 9, 0), ("fin  red.release (counter A)", 9, 0, 10, 0),
+          ("     own release A -> aux sees all arrived", 10, 0, 13, 1), ("     own release A -> prod sees all arrived", 10, 0, 11, 1),
+          ("fin    drain: TMEM loads + stores", 7, 0, 19, 0), ("fin    drain: proxy fence", 19, 0, 8, 0),
+          ("aux  partials pulled (bulk copy)", 13, 1, 14, 1), ("aux  sums + barrier", 14, 1, 16, 1), ("aux  publication (sum of subsets, split, stores)", 16, 1, 17, 1),
+          ("aux  proxy fence + barrier", 17, 1, 18, 1), ("aux  red.release (counter B)", 18, 1, 15, 1),
+          ("     own release B -> prod sees all arrived", 15, 1, 12, 1), ("     prod saw B -> W_y y accumulator complete", 12, 1, 3, 1),
+          ("     whole step (fin step top to step top)", 0, 0, 0, 1)]
+
+
+def report_phases(ph, table):
+    """ph [2 steps][16 slots][256 CTAs] clock64 stamps; differences are taken inside one CTA (one SM clock)."""
+    print("  per-CTA phase durations at steps 40/41, distribution over the CTAs (cycles): min / median / p90 / max  [slowest CTAs]")
+    for name, s0, t0, s1, t1 in table:
+        a, b = ph[t0, s0, :128].astype(np.float64), ph[t1, s1, :128].astype(np.float64)
+        ok = (a > 0) & (b > 0)
+        if not ok.any():
+            continue
+        d = (b - a)[ok]
+        idx = np.nonzero(ok)[0][np.argsort(-d)[:4]]
+        print(f"    {name:52s} {d.min():7.0f} {np.median(d):7.0f} {np.percentile(d, 90):7.0f} {d.max():7.0f}   {list(idx)}")
+
+
 def report(path, names):
     raw = np.fromfile(path, dtype=np.int64)
-    n_rows = (raw.size - (8 * 256 if raw.size % 64 == 0 and (raw.size - 8 * 256) % 64 == 0 and "fwd" in path else 0)) // 64
+    n_rows = T + 1 if "eval" not in path else raw.size // 64
     tr = raw[:n_rows * 64].reshape(-1, 64)
+    if "fwd" in path and raw.size >= n_rows * 64 + 56 * 256:
+        report_phases(raw[n_rows * 64 + 8 * 256:n_rows * 64 + 56 * 256].reshape(2, 24, 256), PH_FWD)
     if "fwd" in path and raw.size > n_rows * 64:
-        sk = raw[n_rows * 64:].reshape(8, 256)[:, :128].astype(np.float64)
+        sk = raw[n_rows * 64:n_rows * 64 + 8 * 256].reshape(8, 256)[:, :128].astype(np.float64)
         sk_names = ["fin: before ctrA release", "fin: after ctrA release", "aux: y published", "aux: after ctrB release", "prod: ctrA seen (t=40)",
                  "prod: ctrB seen (t=40)"]
         ref = sk[0].min()
