@@ -45,11 +45,11 @@ constexpr uint32_t TF_COL_P = 352;    // D3: partial of y_t, 64 main + 64 correc
 constexpr uint32_t TF_COL_DUMMY = 480;
 // y_t is pulled by every CTA at the same moment: 128 readers of the same 160 lines queue up in the L2 slices (the pull took
 // 1360 cycles on the luckiest SM and 3570 on the unluckiest).  The reducers publish TF_YREP copies; CTA c reads copy c % TF_YREP.
-constexpr int TF_YREP = 8;
+constexpr int TF_YREP = 8;   // upper bound; gru_ar_fwd_tc publishes 2 unless CVB_TC_YREP says otherwise (1 vs 8 measured equal)
 
 struct TfLayout {
     int MB, nch, NS;
-    uint32_t half, stage_bytes, w_chunk_bytes, slot_bytes, ybuf_bytes;
+    uint32_t half, stage_bytes, w_chunk_bytes, slot_bytes, ybuf_bytes, bias_bytes;
     int Q;   // pairs (b, o) per reducer CTA, a multiple of 8
     uint32_t off_ring, off_ybuf, off_w, off_b2, off_b3, off_a2, off_inbox, off_bias, off_bar, total;
 };
@@ -67,7 +67,8 @@ __host__ __device__ inline TfLayout tf_layout(int B, int H, int G, int out, int 
     L.Q = 8 * ((8 * B + G - 1) / G);                             // tf_pairs_per_reducer
     const uint32_t red_bytes = (uint32_t)(G * L.Q) * 4u;         // a reducer's block of partials: staged where the y operand lands
     L.ybuf_bytes = ((L.stage_bytes > red_bytes ? L.stage_bytes : red_bytes) + 1023u) & ~1023u;
-    const uint32_t fixed = L.ybuf_bytes + (uint32_t)L.nch * L.w_chunk_bytes + 8192u + 4096u + 8192u + inbox + 640u + 256u;
+    L.bias_bytes = 128u + (uint32_t)(4 * L.Q) * 4u;              // [24] b_hh | [4 warp groups][Q] partial sums of the reducers
+    const uint32_t fixed = L.ybuf_bytes + (uint32_t)L.nch * L.w_chunk_bytes + 8192u + 4096u + 8192u + inbox + L.bias_bytes + 256u;
     int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
     L.NS = ns > 6 ? 6 : ns;
     const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
@@ -80,7 +81,7 @@ __host__ __device__ inline TfLayout tf_layout(int B, int H, int G, int out, int 
     L.off_a2 = L.off_b3 + 4096u;          // o_t of the own units: [2 parts][16 row groups][2 kblk][8][8]
     L.off_inbox = L.off_a2 + 8192u;
     L.off_bias = L.off_inbox + inbox;
-    L.off_bar = L.off_bias + 640u;   // [24] b_hh + [128] partial sums of the reducers
+    L.off_bar = L.off_bias + L.bias_bytes;
     L.total = L.off_bar + 256u;
     return L;
 }
@@ -91,6 +92,7 @@ struct GruTcArgs {
     uint16_t* yx;        // [TF_YREP replicas][2 slots][2 parts][MB][8 kblk][8 rows][8 k] fp16 of y_t, zero-initialised
     float* part;         // [G reducers][G CTAs][Q] partial sums of y_t (part_walk)
     int yrep;            // replicas of y_t actually published / read (1..TF_YREP, CVB_TC_YREP)
+    int ymc;             // CVB_TC_YMC=1: y_t pulled once per cluster and multicast (A/B; default: every CTA pulls its own copy)
     unsigned* ctr;       // [0] = A, [32] = B (separate 128-B lines), zero-initialised
     int smem_max;
     int keepalive;
@@ -126,31 +128,6 @@ static __device__ __forceinline__ void split8_f16(const float* x, uint4& hi, uin
                     (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
     lo = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
                     (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
-}
-// The partial sums of y_t.  Pairs are numbered q = b * 64 + o (the output axis padded to 64: D3's columns beyond out_dim
-// are exact zeros) and reducer CTA r owns the Q = 8 * ceil(8 B / G) pairs [r Q, (r + 1) Q), i.e. whole groups of 8
-// consecutive outputs of one row.  CTA c's partial of pair q lives at part[r = q / Q][c][q % Q]: everything reducer r sums
-// is ONE contiguous block of G * Q floats (a single bulk copy), a draining thread (fixed b, walking o) writes float4s, and
-// the reducer publishes a group as one 16-byte core-matrix row per plane.  (The first version -- pair order [o][b],
-// scalar stores addressed as base + index -- compiled to ~20 dependent instructions per store: 2400 cycles per step.)
-struct PartWalk {
-    unsigned long long addr;   // address of the thread's first float4
-    unsigned long long wrap;   // extra bytes when the slot index wraps into the next reducer
-    int i, Q;                  // slot of that float4 in the reducer's row
-};
-static __device__ __forceinline__ PartWalk part_walk(float* part, int c, int G, int Q, int b, int o_first) {
-    PartWalk w;
-    w.Q = Q;
-    const int q0 = b * 64 + o_first;
-    const int r0 = q0 / Q;
-    w.i = q0 - r0 * Q;
-    w.addr = reinterpret_cast<unsigned long long>(part + ((size_t)r0 * G + c) * Q + w.i);
-    w.wrap = ((unsigned long long)G * Q - Q) * 4ull;
-    asm volatile("" : "+l"(w.addr), "+r"(w.i));   // keep them in registers: no rematerialisation per store
-    return w;
-}
-static __device__ __forceinline__ void st_global_v4(unsigned long long addr, float x, float y, float z, float w) {
-    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 // drain 32 columns (outputs [o_lo, o_lo + 32)) of D3 (main + correction halves) of this warp's 32 TMEM lanes into `part`
 static __device__ __forceinline__ void drain_partial_y(uint32_t taddr_p, const PartWalk& w, int o_lo, bool row_ok) {
@@ -202,7 +179,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
     // inbox must NOT be reused: the peers' exchange copies land as soon as THEIR h chunks are consumed.)
     float* sRed = reinterpret_cast<float*>(smem + L.off_ybuf);
     float* sBh = reinterpret_cast<float*>(smem + L.off_bias);      // [3][8] b_hh of the own units
-    float* sPs = sBh + 32;                                         // [128] partial sums of the reducers
+    float* sPs = sBh + 32;                                         // [4 warp groups][Q] partial sums of the reducers
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* empty = full + 8;
     uint64_t* accum_full = empty + 8;   // D2 (W_y y) complete
@@ -333,7 +310,7 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         uint32_t ph = 1;
         for (int t = 0; t < T; ++t) {
             const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
-            const uint16_t* srcy = a.yx + (size_t)(c % a.yrep) * yx_rep + (size_t)(t & 1) * 2 * yx_part;
+            const uint16_t* srcy = a.yx + (size_t)((a.ymc ? c / TF_S : c) % a.yrep) * yx_rep + (size_t)(t & 1) * 2 * yx_part;
             if (lane == 0) {
                 spin_until_ge(ctrA, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);   // the writers fenced generic -> async proxy before their release
                 TF_TRACE(14);
@@ -357,14 +334,25 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 }
             }
             if (lane == 0) {
-                spin_until_ge(ctrB, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);
-                TF_TRACE(13);
-                TF_SKEW(5);
-                TF_PH(12);
+                // y_{t-1}: ONE CTA of the cluster pulls it and multicasts it into all four (every CTA reading the same lines at
+                // the same moment queued up in the L2 slices: the pull took 1500 cycles on the luckiest SM, 3500 on the
+                // unluckiest).  When counter B is complete every CTA's y buffer is free: its MMAs of the previous step
+                // retired before that CTA's arrival on A, its reducers' reads (sRed aliases it) before its arrival on B.
                 mbar_wait(y_empty, ((uint32_t)t & 1) ^ 1);
                 mbar_expect_tx(y_full, 2 * L.half);
-                bulk_g2s(ybuf, srcy, L.half, y_full);
-                bulk_g2s(ybuf + L.half, srcy + yx_part, L.half, y_full);
+                if (!a.ymc || j == 0) {
+                    spin_until_ge(ctrB, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);
+                    TF_TRACE(13);
+                    TF_SKEW(5);
+                    TF_PH(12);
+                    if (a.ymc) {
+                        bulk_g2s_multicast(ybuf, srcy, L.half, y_full, (uint16_t)((1u << TF_S) - 1u));
+                        bulk_g2s_multicast(ybuf + L.half, srcy + yx_part, L.half, y_full, (uint16_t)((1u << TF_S) - 1u));
+                    } else {
+                        bulk_g2s(ybuf, srcy, L.half, y_full);
+                        bulk_g2s(ybuf + L.half, srcy + yx_part, L.half, y_full);
+                    }
+                }
             }
             __syncwarp();
         }
@@ -670,18 +658,31 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
         const uint32_t red_bytes = (uint32_t)(G * Q) * 4u;         // this reducer's block: [G CTAs][Q pairs]
         const float* red_src = a.part + (size_t)c * G * Q;
         const int yrep = a.yrep;
-        // per-thread constants of the first (normally the only) block of pairs
-        const int w0 = min(128, q_n);
-        const int nsub0 = w0 > 0 ? 128 / w0 : 1;
-        const int sub0 = w0 > 0 ? rt / w0 : 0, qi0 = w0 > 0 ? rt - sub0 * w0 : 0;
-        const int ng0 = w0 >> 3;
-        const int rep0 = ng0 > 0 ? rt / ng0 : 0, g0 = ng0 > 0 ? rt - rep0 * ng0 : 0;   // no division inside the rounds
-        float bias0[8];   // b_o of this thread's group in the first block (zero on the padding outputs)
+        // Reduction geometry (all of it fixed before the rounds: no division inside them).  Stage 1: a thread sums ONE
+        // float4 column (4 consecutive pairs) over every nsub-th CTA; the columns fit one warp when there are <= 32 of
+        // them, and then the 32 / ncol subsets a warp holds are combined by shuffles in fixed order; each warp group
+        // writes its partial row to sPs.  Stage 2 (the publication threads) adds the rows in fixed order.
+        const int ncol = q_n >> 2;                                   // <= 64 (Q <= 256)
+        const int nwc = ncol > 32 ? 2 : 1;                           // warps side by side over the columns
+        const int ncw = ncol > 32 ? 32 : ncol;
+        const int spw = (nwc == 1 && ncw > 0) ? 32 / ncw : 1;        // subsets inside one warp
+        const int nwg = 4 / nwc;                                     // warp groups = rows of sPs
+        const int nsub = nwg * spw;
+        const int wq = warp - 8, lane_sl = ncw > 0 ? lane / ncw : 0;
+        const int col = (wq % nwc) * 32 + (ncw > 0 ? lane - lane_sl * ncw : 0);
+        const int sid = (wq / nwc) * spw + lane_sl;                  // this thread's subset of the CTAs: sid, sid + nsub, ...
+        const bool sum_act = ncol > 0 && lane_sl < spw && col < ncol;
+        float* sProw = sPs + (size_t)(wq / nwc) * Q;
+        // publication: thread (group g of 8 consecutive outputs of one row, replica rep0 + k * rep_step)
+        const int ng = q_n >> 3;
+        const int rep0 = ng > 0 ? rt / ng : 0, g = ng > 0 ? rt - rep0 * ng : 0;
+        const int rep_step = ng > 0 ? min(yrep, max(1, 128 / ng)) : 1;   // publication threads per group
+        const int pq0 = q_lo + 8 * g;
+        const int pbb = pq0 >> 6, po = pq0 & 63;                     // row and first output of the group
+        const bool pub_act = ng > 0 && rep0 < rep_step;
+        float bias[8];   // b_o of this thread's group (zero on the padding outputs)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int o = (q_lo + 8 * g0 + e) & 63;
-            bias0[e] = (o < out) ? __ldg(f.bo + o) : 0.f;
-        }
+        for (int e = 0; e < 8; ++e) bias[e] = (pub_act && po + e < out) ? __ldg(f.bo + po + e) : 0.f;
         // round 0 publishes y_in; round r >= 1 reduces the partials of step r-1 into y_{r-1}
         for (int round = 0; round <= T; ++round) {
             const int t = round;   // trace row
@@ -704,83 +705,66 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
                 }
                 if (q_n > 0) mbar_wait(red_full, (uint32_t)(round - 1) & 1);
                 if (rt == 0) TF_PH(14);
+                // stage 1
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                if (sum_act) {
+                    const float4* p = reinterpret_cast<const float4*>(sRed + (size_t)sid * Q + 4 * col);
+                    const int stp = nsub * (Q >> 2);
+                    int cc = sid;
+                    for (; cc + nsub < G; cc += 2 * nsub, p += 2 * stp) {
+                        const float4 x = p[0], y = p[stp];
+                        a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
+                        a1.x += y.x; a1.y += y.y; a1.z += y.z; a1.w += y.w;
+                    }
+                    if (cc < G) {
+                        const float4 x = p[0];
+                        a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
+                    }
+                    a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
+                }
+                for (int k = 1; k < spw; ++k) {   // the warp's other subsets of this column, in fixed order (warp-uniform trip count)
+                    const int src = (lane + k * ncw) & 31;
+                    const float vx = __shfl_sync(0xffffffffu, a0.x, src), vy = __shfl_sync(0xffffffffu, a0.y, src);
+                    const float vz = __shfl_sync(0xffffffffu, a0.z, src), vw = __shfl_sync(0xffffffffu, a0.w, src);
+                    if (lane_sl == 0) {
+                        a0.x += vx; a0.y += vy; a0.z += vz; a0.w += vw;
+                    }
+                }
+                if (sum_act && lane_sl == 0) *reinterpret_cast<float4*>(sProw + 4 * col) = a0;
+                if (rt == 0) TF_TRACE(27);
+                named_bar_sync(2, 128);
+                if (rt == 0) TF_PH(16);
             }
             float* ydst = f.ys + (size_t)round * n_pairs;
             uint16_t* yx = a.yx + (size_t)(round & 1) * 2 * yx_part;
-            float ydef[8];
-            int ydef_b = -1, ydef_o = 0;   // the fp32 outputs of the last block are stored after the release (only later kernels read them)
-            for (int qb = 0; qb < q_n; qb += 128) {
-                const int w = min(128, q_n - qb);
-                // sum over the CTAs: nsub threads per pair, each a fixed subset of the CTAs (every nsub-th, four interleaved
-                // accumulators), combined in fixed order: deterministic
-                const bool hoisted = (qb == 0);
-                const int nsub = hoisted ? nsub0 : 128 / w;
-                const int sub = hoisted ? sub0 : rt / w, qi = hoisted ? qi0 : rt - (rt / w) * w;
+            float yv[8];
+            if (pub_act) {
                 if (round > 0) {
-                    if (sub < nsub) {
-                        const float* p = sRed + (size_t)sub * Q + qb + qi;
-                        const int stp = nsub * Q;
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        int cc = sub;
-                        for (; cc + 3 * nsub < G; cc += 4 * nsub, p += 4 * stp) {
-                            s0 += p[0];
-                            s1 += p[stp];
-                            s2 += p[2 * stp];
-                            s3 += p[3 * stp];
+                    // stage 2: the warp groups' rows in fixed order
+#pragma unroll
+                    for (int e = 0; e < 8; e += 4) {
+                        float4 v = *reinterpret_cast<const float4*>(sPs + 8 * g + e);
+                        for (int k = 1; k < nwg; ++k) {
+                            const float4 x = *reinterpret_cast<const float4*>(sPs + (size_t)k * Q + 8 * g + e);
+                            v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
                         }
-                        if (cc < G) s0 += p[0];
-                        if (cc + nsub < G) s1 += p[stp];
-                        if (cc + 2 * nsub < G) s2 += p[2 * stp];
-                        sPs[sub * w + qi] = (s0 + s1) + (s2 + s3);
+                        yv[e] = v.x; yv[e + 1] = v.y; yv[e + 2] = v.z; yv[e + 3] = v.w;
                     }
-                    if (rt == 0) TF_TRACE(27);
-                    named_bar_sync(2, 128);
-                    if (rt == 0) TF_PH(16);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) yv[e] = (po + e < out) ? yv[e] + bias[e] : 0.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) yv[e] = f.ys[(size_t)pbb * out + min(po + e, out - 1)];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) yv[e] = (po + e < out) ? yv[e] : 0.f;
                 }
-                // publication: thread (group g of 8 consecutive outputs of one row, replica rep) -> one 16-byte core-matrix row per plane
-                const int ng = w >> 3;
-                const int rep = hoisted ? rep0 : rt / ng, g = hoisted ? g0 : rt - (rt / ng) * ng;
-                if (rep < yrep) {
-                    const int q0 = q_lo + qb + 8 * g;
-                    const int bb = q0 >> 6, o = q0 & 63;
-                    float yv[8];
-                    if (round > 0) {
-                        float bias[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) bias[e] = hoisted ? bias0[e] : __ldg(f.bo + min(o + e, out - 1));   // every load in flight at once
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) yv[e] = sPs[8 * g + e];
-                        for (int k = 1; k < nsub; ++k) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) yv[e] += sPs[k * w + 8 * g + e];
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) yv[e] = (o + e < out) ? yv[e] + bias[e] : 0.f;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) yv[e] = f.ys[(size_t)bb * out + min(o + e, out - 1)];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) yv[e] = (o + e < out) ? yv[e] : 0.f;
-                    }
-                    uint4 hi, lo;
-                    split8_f16(yv, hi, lo);
-                    uint16_t* dst = yx + (size_t)rep * yx_rep + (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8;
-                    *reinterpret_cast<uint4*>(dst) = hi;
-                    *reinterpret_cast<uint4*>(dst + yx_part) = lo;
-                    if (round > 0 && rep == 0) {
-                        if (qb + 128 >= q_n) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) ydef[e] = yv[e];
-                            ydef_b = bb;
-                            ydef_o = o;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (o + e < out) ydst[(size_t)bb * out + o + e] = yv[e];
-                        }
-                    }
+                uint4 hi, lo;
+                split8_f16(yv, hi, lo);
+                uint16_t* dst = yx + (size_t)(pbb >> 3) * 512 + (size_t)(po >> 3) * 64 + (size_t)(pbb & 7) * 8;
+                for (int rep = rep0; rep < yrep; rep += rep_step) {
+                    *reinterpret_cast<uint4*>(dst + (size_t)rep * yx_rep) = hi;
+                    *reinterpret_cast<uint4*>(dst + (size_t)rep * yx_rep + yx_part) = lo;
                 }
-                if (qb + 128 < q_n) named_bar_sync(2, 128);
             }
             if (rt == 0) TF_TRACE(21);
             if (rt == 0) TF_SKEW(2);
@@ -791,10 +775,10 @@ __global__ void __launch_bounds__(TF_NT, 1) k_gru_fwd_tc(GruTcArgs a) {
             if (rt == 0) red_release_gpu_add(ctrB, 1u);
             if (rt == 0) TF_SKEW(3);
             if (rt == 0) TF_PH(15);
-            if (ydef_b >= 0) {
+            if (round > 0 && pub_act && rep0 == 0) {   // the fp32 outputs: stored after the release (only later kernels read them)
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                    if (ydef_o + e < out) ydst[(size_t)ydef_b * out + ydef_o + e] = ydef[e];
+                    if (po + e < out) ydst[(size_t)pbb * out + po + e] = yv[e];
             }
             if (rt == 0) TF_TRACE(22);
         }
@@ -881,8 +865,10 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     a.yx = reinterpret_cast<uint16_t*>(tc_scratch + hx_f);
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + hx_f + yx_f);
     a.part = tc_scratch + hx_f + yx_f + 64;
-    a.yrep = TF_YREP;
+    a.yrep = 2;
     if (const char* e = getenv("CVB_TC_YREP")) a.yrep = max(1, min(TF_YREP, atoi(e)));
+    a.ymc = 0;   // measured: 18 440 -> 19 000 cycles per step with the multicast (at cluster size 4 a multicast saves no L2 traffic and adds a hop)
+    if (const char* e = getenv("CVB_TC_YMC")) a.ymc = atoi(e) != 0;
     a.smem_max = di.max_smem_optin;
     a.keepalive = 1;
     a.relaxed = relaxed_polling() ? 1 : 0;

@@ -40,6 +40,7 @@ constexpr uint32_t TB_COL_P = 256;     // D3 (partial of the y feedback): 2 x 64
 struct TbLayout {
     int MB, S, Ublk, nch, NS;
     uint32_t half, stage_bytes, w_part_bytes, slot_bytes;
+    int Q;   // pairs (b, o) per reducer CTA, a multiple of 8 (PartWalk, umma.cuh)
     uint32_t off_ring, off_w, off_inbox, off_stage, off_a2, off_b2, off_b3, off_aux, off_bar, total;
 };
 
@@ -54,9 +55,10 @@ __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int ou
     L.w_part_bytes = (uint32_t)L.nch * (uint32_t)S * 1024u;
     L.slot_bytes = (uint32_t)L.MB * 8u * 32u;
     const uint32_t inbox = (uint32_t)S * L.slot_bytes;
-    const int Q = (B * out + G - 1) / G;
-    const uint32_t aux = (((uint32_t)(G * (Q < 128 ? Q : 128)) * 4u) + 127u) & ~127u;   // staging of the partials being reduced
-    const uint32_t fixed = 2u * L.w_part_bytes + 2u * inbox + 16384u + 4096u + 8192u + aux + 768u;
+    L.Q = 8 * ((8 * B + G - 1) / G);
+    const uint32_t aux = (((uint32_t)(G * L.Q) * 4u) + 127u) & ~127u;   // a reducer's block of partials [G CTAs][Q pairs] (one bulk copy)
+    const uint32_t sps = (uint32_t)(4 * L.Q) * 4u;                      // [4 warp groups][Q] partial sums of the reducers
+    const uint32_t fixed = 2u * L.w_part_bytes + 2u * inbox + 16384u + 4096u + 8192u + aux + 256u + sps;
     int ns = ((int)smem_max - (int)fixed) / (int)L.stage_bytes;
     L.NS = ns > 6 ? 6 : ns;
     const uint32_t ring = (uint32_t)(L.NS > 0 ? L.NS : 0) * L.stage_bytes;
@@ -69,7 +71,7 @@ __host__ __device__ inline TbLayout tb_layout(int B, int H, int S, int G, int ou
     L.off_b3 = L.off_b2 + 4096u;        // [2 parts][8 n blocks][4 kblk][8][8] bf16: W_y rows of the own units
     L.off_aux = L.off_b3 + 8192u;
     L.off_bar = L.off_aux + aux;
-    L.total = L.off_bar + 256u + 512u;   // mbarriers + tmem slot | [128] partial sums of the reducers
+    L.total = L.off_bar + 256u + sps;    // mbarriers + tmem slot | partial sums of the reducers
     return L;
 }
 
@@ -77,6 +79,7 @@ struct GruTcBwdArgs {
     GruBwdArgs f;
     uint16_t* gxh;    // [2 slots][2 parts][3H/64 chunks][MB][8 kblk][8 rows][8 k] bf16 (UMMA order) of dgh_t
     uint16_t* dyx;    // [2 slots][2 parts][MB][8 kblk][8 rows][8 k] bf16 (UMMA order) of dy_t, zero-initialised
+    float* part;      // [G reducers][G CTAs][Q] partial sums of the y feedback (PartWalk)
     unsigned* ctr;    // [0] = A, [32] = B (separate 128-B lines), zero-initialised
     int S;
     int smem_max;
@@ -103,17 +106,26 @@ static __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& 
     lo = pack_bf16x8(l);
 }
 
-// drain columns [o_lo, o_hi) of D3 (hi + correction halves) of this warp's 32 TMEM lanes into part[c][o][b]
-static __device__ __forceinline__ void drain_partial(uint32_t taddr_p, float* pd, int o_lo, int o_hi, int out, int B, bool row_ok) {
-    for (int o0 = o_lo; o0 < o_hi && o0 < out; o0 += 16) {
+// drain 32 columns (outputs [o_lo, o_lo + 32)) of D3 (hi + correction halves) of this warp's 32 TMEM lanes into `part`
+// (layout and walk: PartWalk, umma.cuh)
+static __device__ __forceinline__ void drain_partial(uint32_t taddr_p, const PartWalk& w, int o_lo, bool row_ok) {
+    unsigned long long addr = w.addr;
+    int i = w.i;
+#pragma unroll
+    for (int o0 = o_lo; o0 < o_lo + 32; o0 += 16) {
         float v[16], v2[16];
         tmem_ld_x16(taddr_p + o0, v);
         tmem_ld_x16(taddr_p + 64 + o0, v2);
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (o0 + q < out) pd[(size_t)(o0 + q) * B] = v[q] + v2[q];
+        for (int q = 0; q < 16; q += 4) {
+            if (row_ok) st_global_v4(addr, v[q] + v2[q], v[q + 1] + v2[q + 1], v[q + 2] + v2[q + 2], v[q + 3] + v2[q + 3]);
+            addr += 16;
+            i += 4;
+            if (i >= w.Q) {
+                i -= w.Q;
+                addr += w.wrap;
+            }
         }
     }
 }
@@ -144,7 +156,8 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
     uint64_t* inbox_full = accum_full + 1;
     uint64_t* a2_full = inbox_full + 1;
     uint64_t* part_full = a2_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_full + 1);
+    uint64_t* red_full = part_full + 1;   // the reducers' block of partials has landed in sRed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_full + 1);
     const size_t gx_part = (size_t)(K3 / TB_KC) * L.MB * 512;   // elements per part
     const size_t dy_part = (size_t)L.MB * 512;
     unsigned* ctrA = a.ctr;
@@ -223,6 +236,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             mbar_init(inbox_full, 1);   // armed with expect_tx(S slots) every step; the peers' bulk copies complete_tx
             mbar_init(a2_full, 128);    // every finaliser thread has staged its dgi row
             mbar_init(part_full, 1);
+            mbar_init(red_full, 1);
             mbar_fence_init();
         }
         fence_proxy_async_smem();
@@ -344,6 +358,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
         float carry[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) carry[q] = act ? f.dhc[(size_t)b * H + u0 + q] : 0.f;
+        const PartWalk pw = part_walk(a.part, c, G, L.Q, b, 32);   // this thread drains outputs [32, 64) of its row
         float bsum = 0.f;   // lane i: sum over (t, rows of this warp) of value i of [dar 8 | daz 8 | dan 8 | dan*r 8]
         const bool want_db = f.dbih != nullptr || f.dbhh != nullptr;
         for (int n = 0; n <= T; ++n) {
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             const size_t row = (size_t)(t < 0 ? 0 : t) * B + (act ? b : 0);
             float4 pr[2], pz[2], pn[2], pg[2], ph[2];
             float4 pm[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
-            if (t >= 0 && act) {
+            if (t >= 0) {   // every lane loads (the rows beyond B re-read row 0 of the frame: `row`), so the gate math below is branch-free
                 const size_t so = row * H + u0;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -407,10 +422,11 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             if (n > 0) {
                 mbar_wait_cluster(inbox_full, (uint32_t)(n - 1) & 1);
                 if (etid == 0) TB_TRACE(3);
-                if (act) {
+                {
+                    const int bs = b < L.MB * 8 ? b : 0;   // rows beyond the staged row groups read row 0 (in bounds)
                     for (int p = 0; p < S; ++p) {
-                        const float4 x0 = *reinterpret_cast<const float4*>(inbox + (size_t)p * (L.slot_bytes / 4) + b * 8);
-                        const float4 x1 = *reinterpret_cast<const float4*>(inbox + (size_t)p * (L.slot_bytes / 4) + b * 8 + 4);
+                        const float4 x0 = *reinterpret_cast<const float4*>(inbox + (size_t)p * (L.slot_bytes / 4) + bs * 8);
+                        const float4 x1 = *reinterpret_cast<const float4*>(inbox + (size_t)p * (L.slot_bytes / 4) + bs * 8 + 4);
                         acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
                         acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
                     }
@@ -433,21 +449,17 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                 const float* h_ = reinterpret_cast<const float*>(ph);
                 const float* m_ = reinterpret_cast<const float*>(pm);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (act) {
-                        const float dh = carry[q] + acc[q] + qv[q] * m_[q];
-                        const float r = r_[q], z = z_[q], nn = n_[q];
-                        const float dn = dh * (1.0f - z);
-                        const float dz = dh * (h_[q] - nn);
-                        carry[q] = dh * z;
-                        const float dan = dn * (1.0f - nn * nn);
-                        dgr[q] = dan * g_[q] * r * (1.0f - r);
-                        dgz[q] = dz * z * (1.0f - z);
-                        dgn[q] = dan;
-                        dgnr[q] = dan * r;
-                    } else {
-                        dgr[q] = dgz[q] = dgn[q] = dgnr[q] = 0.f;
-                    }
+                for (int q = 0; q < 8; ++q) {   // straight-line for every lane (see gru_tc.cu: per-unit branch regions serialise the chains)
+                    const float dh = carry[q] + acc[q] + qv[q] * m_[q];
+                    const float r = r_[q], z = z_[q], nn = n_[q];
+                    const float dn = dh * (1.0f - z);
+                    const float dz = dh * (h_[q] - nn);
+                    carry[q] = dh * z;
+                    const float dan = dn * (1.0f - nn * nn);
+                    dgr[q] = act ? dan * g_[q] * r * (1.0f - r) : 0.f;   // zeros on the rows beyond B: the bias sums below add every lane
+                    dgz[q] = act ? dz * z * (1.0f - z) : 0.f;
+                    dgn[q] = act ? dan : 0.f;
+                    dgnr[q] = act ? dan * r : 0.f;
                 }
             }
             uint4 hr, lr, hz, lz, hn, ln, hnr, lnr;
@@ -485,8 +497,9 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             if (out > 32) {   // second half of the partial accumulator (the aux warps drain [0, 32))
                 mbar_wait(part_full, (uint32_t)n & 1);
                 tc_fence_after();
-                drain_partial(taddr + TB_COL_P, f.part + (size_t)c * n_pairs + b, 32, 64, out, B, act);
+                drain_partial(taddr + TB_COL_P, pw, 32, act);
                 tc_fence_before();
+                fence_proxy_async_global();   // the reducers pull the partials with a bulk copy (async proxy)
             }
             named_bar_sync(7, 256);    // every finaliser published; the aux warps have drained D3 into `part`
             if (etid == 0) red_release_gpu_add(ctrA, 1u);   // release is cumulative over the barrier: one gpu-scope fence per CTA
@@ -534,107 +547,118 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
     } else if (warp >= 8) {
         // ================= aux: dy reduction + publication, drain of the partial accumulator ============
         const int rt = threadIdx.x - 256;
-        const int Q = (n_pairs + G - 1) / G;
+        const int Q = L.Q;
         const int q_lo = c * Q;
-        const int q_n = max(0, min(Q, n_pairs - q_lo));
+        const int q_n = max(0, min(Q, B * 64 - q_lo));   // whole groups of 8 pairs q = b * 64 + o (PartWalk, umma.cuh)
         const uint32_t taddr = tmem + ((uint32_t)((warp - 8) * 32) << 16) + TB_COL_P;
-        constexpr int LB = 8;   // independent loads in flight per thread
-        // per-thread constants of the first (normally the only) block of pairs: no division inside the steps
-        const int w0 = min(128, q_n);
-        const int nsub0 = w0 > 0 ? 128 / w0 : 1;
-        const int sub0 = w0 > 0 ? rt / w0 : 0, qi0 = w0 > 0 ? rt - sub0 * w0 : 0;
-        int o0 = 0, bb0 = 0;
-        if (rt < w0) {
-            o0 = (q_lo + rt) / B;
-            bb0 = (q_lo + rt) - o0 * B;
-        }
-        float* sPs = reinterpret_cast<float*>(smem + L.off_bar + 256);   // [128] partial sums (behind the mbarriers)
+        const PartWalk pw = part_walk(a.part, c, G, Q, rt, 0);     // this thread drains outputs [0, 32) of row rt
+        const uint32_t red_bytes = (uint32_t)(G * Q) * 4u;         // this reducer's block: [G CTAs][Q pairs]
+        const float* red_src = a.part + (size_t)c * G * Q;
+        float* sPs = reinterpret_cast<float*>(smem + L.off_bar + 256);   // [4 warp groups][Q] partial sums (behind the mbarriers)
+        // Reduction geometry, fixed before the steps (no division inside them; same scheme as gru_tc.cu).  Stage 1: a thread
+        // sums ONE float4 column (4 consecutive pairs) over every nsub-th CTA; the subsets a warp holds are combined by
+        // shuffles in fixed order; each warp group writes its partial row to sPs.  Stage 2 adds the rows in fixed order.
+        const int ncol = q_n >> 2;
+        const int nwc = ncol > 32 ? 2 : 1;
+        const int ncw = ncol > 32 ? 32 : ncol;
+        const int spw = (nwc == 1 && ncw > 0) ? 32 / ncw : 1;
+        const int nwg = 4 / nwc;
+        const int nsub = nwg * spw;
+        const int wq = warp - 8, lane_sl = ncw > 0 ? lane / ncw : 0;
+        const int col = (wq % nwc) * 32 + (ncw > 0 ? lane - lane_sl * ncw : 0);
+        const int sid = (wq / nwc) * spw + lane_sl;
+        const bool sum_act = ncol > 0 && lane_sl < spw && col < ncol;
+        float* sProw = sPs + (size_t)(wq / nwc) * Q;
+        // publication: thread g < ng owns the group of 8 consecutive outputs [po, po + 8) of row pbb
+        const int ng = q_n >> 3;
+        const int pq0 = q_lo + 8 * rt;
+        const int pbb = pq0 >> 6, po = pq0 & 63;
+        const bool pub_act = rt < ng;
         for (int n = 0; n <= T; ++n) {
             const int t = T - 1 - n;
             float* dyt = f.dy_tot + (size_t)(t + 1) * n_pairs;
-            // the head's dY of this thread's pair: fetched before the wait, only this thread ever modifies it
-            float dy_base = (rt < w0) ? __ldcg(dyt + (size_t)bb0 * out + o0) : 0.f;
-            float dy_deferred = 0.f;
+            // the head's dY of this thread's group: fetched before the wait, only this thread ever modifies it
+            float dyv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dyv[e] = pub_act ? __ldcg(dyt + (size_t)pbb * out + min(po + e, out - 1)) : 0.f;
             uint16_t* dyx = a.dyx + (size_t)(n & 1) * 2 * dy_part;
             if (n > 0) {
-                if (rt == 0) spin_until_ge(ctrA, (unsigned)G * (unsigned)n, a.relaxed != 0);
-                if (rt == 0) TB_TRACE(20);
+                if (rt == 0 && q_n > 0) {
+                    spin_until_ge(ctrA, (unsigned)G * (unsigned)n, a.relaxed != 0);
+                    TB_TRACE(20);
+                    // every CTA's partials of this reducer's pairs are one contiguous block: one bulk copy into sRed
+                    mbar_expect_tx(red_full, red_bytes);
+                    bulk_g2s(sRed, red_src, red_bytes, red_full);
+                }
+                if (q_n > 0) mbar_wait(red_full, (uint32_t)(n - 1) & 1);
+                if (rt == 0) TB_TRACE(27);
+                // stage 1
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                if (sum_act) {
+                    const float4* p = reinterpret_cast<const float4*>(sRed + (size_t)sid * Q + 4 * col);
+                    const int stp = nsub * (Q >> 2);
+                    int cc = sid;
+                    for (; cc + nsub < G; cc += 2 * nsub, p += 2 * stp) {
+                        const float4 x = p[0], y = p[stp];
+                        a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
+                        a1.x += y.x; a1.y += y.y; a1.z += y.z; a1.w += y.w;
+                    }
+                    if (cc < G) {
+                        const float4 x = p[0];
+                        a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
+                    }
+                    a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
+                }
+                for (int k = 1; k < spw; ++k) {   // the warp's other subsets of this column, in fixed order (warp-uniform trip count)
+                    const int src = (lane + k * ncw) & 31;
+                    const float vx = __shfl_sync(0xffffffffu, a0.x, src), vy = __shfl_sync(0xffffffffu, a0.y, src);
+                    const float vz = __shfl_sync(0xffffffffu, a0.z, src), vw = __shfl_sync(0xffffffffu, a0.w, src);
+                    if (lane_sl == 0) {
+                        a0.x += vx; a0.y += vy; a0.z += vz; a0.w += vw;
+                    }
+                }
+                if (sum_act && lane_sl == 0) *reinterpret_cast<float4*>(sProw + 4 * col) = a0;
                 named_bar_sync(2, 128);
-            }
-            // dy_tot[t+1] += sum over the CTAs of the partials of step t+1 (fixed order); publish in operand order
-            for (int qb = 0; qb < q_n; qb += 128) {
-                const int w = min(128, q_n - qb);
-                // sum over the CTAs: nsub threads per pair, each a fixed subset of the CTAs, combined in fixed order
-                // (deterministic).  The partials are read straight from L2 into registers, every load of a thread in
-                // flight at once (staging them through shared memory first cost a second round trip and a barrier).
-                const bool hoisted = (qb == 0);
-                const int nsub = hoisted ? nsub0 : 128 / w;
-                const int sub = hoisted ? sub0 : rt / w, qi = hoisted ? qi0 : rt - (rt / w) * w;
-                if (n > 0) {
-                    if (sub < nsub) {
-                        const float* p = f.part + (size_t)sub * n_pairs + q_lo + qb + qi;
-                        const size_t stp = (size_t)nsub * n_pairs;
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        for (int cc = sub; cc < G; cc += 48 * nsub, p += 48 * stp) {
-                            float v[48];
+                if (pub_act) {   // stage 2: the warp groups' rows in fixed order, added to the head's dY
 #pragma unroll
-                            for (int k = 0; k < 48; ++k) v[k] = (cc + k * nsub < G) ? __ldcg(p + (size_t)k * stp) : 0.f;
-#pragma unroll
-                            for (int k = 0; k < 48; k += 4) {
-                                s0 += v[k];
-                                s1 += v[k + 1];
-                                s2 += v[k + 2];
-                                s3 += v[k + 3];
-                            }
+                    for (int e = 0; e < 8; e += 4) {
+                        float4 v = *reinterpret_cast<const float4*>(sPs + 8 * rt + e);
+                        for (int k = 1; k < nwg; ++k) {
+                            const float4 x = *reinterpret_cast<const float4*>(sPs + (size_t)k * Q + 8 * rt + e);
+                            v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
                         }
-                        sPs[sub * w + qi] = (s0 + s1) + (s2 + s3);
-                    }
-                    if (rt == 0) TB_TRACE(27);
-                    named_bar_sync(2, 128);
-                }
-                if (rt < w) {
-                    int o, bb;
-                    float dyv;
-                    if (hoisted) {
-                        o = o0;
-                        bb = bb0;
-                        dyv = dy_base;
-                    } else {
-                        const int qq = q_lo + qb + rt;
-                        o = qq / B;   // pair order of `part` is [o][b]
-                        bb = qq - o * B;
-                        dyv = __ldcg(dyt + (size_t)bb * out + o);
-                    }
-                    if (n > 0) {
-                        float sacc = sPs[rt];
-                        for (int k = 1; k < nsub; ++k) sacc += sPs[k * w + rt];
-                        dyv += sacc;
-                        if (hoisted) dy_deferred = dyv;   // the fp32 total is stored after the release (only later kernels read it)
-                        else dyt[(size_t)bb * out + o] = dyv;
-                    }
-                    if (t >= 0) {
-                        uint16_t hi, lo;
-                        split_bf16(dyv, hi, lo);
-                        const size_t off = (size_t)(bb >> 3) * 512 + (size_t)(o >> 3) * 64 + (size_t)(bb & 7) * 8 + (size_t)(o & 7);
-                        dyx[off] = hi;
-                        dyx[dy_part + off] = lo;
+                        dyv[e] += v.x; dyv[e + 1] += v.y; dyv[e + 2] += v.z; dyv[e + 3] += v.w;
                     }
                 }
-                if (qb + 128 < q_n) named_bar_sync(2, 128);
+            }
+            if (pub_act && t >= 0) {   // dy_t in operand order: one 16-byte core-matrix row per plane
+                float pv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pv[e] = (po + e < out) ? dyv[e] : 0.f;
+                uint4 hi, lo;
+                split8(pv, hi, lo);
+                uint16_t* dst = dyx + (size_t)(pbb >> 3) * 512 + (size_t)(po >> 3) * 64 + (size_t)(pbb & 7) * 8;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + dy_part) = lo;
             }
             if (rt == 0) TB_TRACE(21);
             fence_proxy_async_global();
             named_bar_sync(2, 128);
             if (rt == 0) red_release_gpu_add(ctrB, 1u);
             if (rt == 0) TB_TRACE(22);
-            if (n > 0 && rt < w0) dyt[(size_t)bb0 * out + o0] = dy_deferred;
+            if (n > 0 && pub_act) {   // the fp32 total: stored after the release (only later kernels read it)
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (po + e < out) dyt[(size_t)pbb * out + po + e] = dyv[e];
+            }
             if (t < 0) break;
-            // drain D3 (partial of the y feedback of step t, this CTA's units) into part[c][o][b]
+            // drain D3 (partial of the y feedback of step t, this CTA's units) into `part`
             mbar_wait(part_full, (uint32_t)n & 1);
             if (rt == 0) TB_TRACE(25);
             tc_fence_after();
-            drain_partial(taddr, f.part + (size_t)c * n_pairs + rt, 0, 32, out, B, rt < B);   // the finaliser warps take [32, 64)
+            drain_partial(taddr, pw, 0, rt < B);   // the finaliser warps take [32, 64)
             tc_fence_before();
+            fence_proxy_async_global();   // generic stores -> the reducers' bulk copies (async proxy)
             if (rt == 0) TB_TRACE(26);
             named_bar_sync(7, 256);   // a full barrier, not an arrive: thread 0's release after it must cover these warps' stores to `part`
         }
@@ -650,11 +674,18 @@ bool gru_tc_bwd_shape_ok(int B, int H, int out) {
     return H % 64 == 0 && H >= 64 && out >= 1 && out <= 64 && B >= 1 && B <= 128 && (3 * H / TB_KC) % 4 == 0 && H % 32 == 0;
 }
 
+// floats of the partial-sum buffer part[G reducers][G CTAs][Q] (G = CTAs of the launch: H / 8)
+static size_t tb_part_floats(int B, int H) {
+    const size_t G = (size_t)H / 8;
+    const size_t Q = 8 * (((size_t)8 * B + G - 1) / G);
+    return round_up_sz(G * G * Q, 64);
+}
+
 size_t gru_tc_bwd_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
     size_t gxh = (size_t)2 * 2 * (3 * H / TB_KC) * MB * 512 / 2;   // bf16 elements -> floats
     size_t dyx = (size_t)2 * 2 * MB * 512 / 2;
-    return round_up_sz(gxh, 64) + round_up_sz(dyx, 64) + 64;
+    return round_up_sz(gxh, 64) + round_up_sz(dyx, 64) + 64 + tb_part_floats(B, H);
 }
 
 // picks the cluster size (8 preferred) whose clusters are all co-resident; 0 = not runnable
@@ -722,6 +753,7 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     a.gxh = reinterpret_cast<uint16_t*>(tc_scratch);
     a.dyx = reinterpret_cast<uint16_t*>(tc_scratch + gxh_f);
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + gxh_f + dyx_f);
+    a.part = tc_scratch + gxh_f + dyx_f + 64;
     a.S = S;
     a.smem_max = di.max_smem_optin;
     a.trace = nullptr;

@@ -57,6 +57,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// the same copy delivered to the same shared-memory offset of every CTA of the cluster named in cta_mask; each
+// destination's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / bulk copy)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -259,6 +268,33 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     }
+}
+
+// ---- partial sums of the y feedback of the training recurrence kernels (gru_tc.cu, gru_tc_bwd.cu) ----------------
+// Pairs are numbered q = b * 64 + o (the output axis padded to 64: D3's columns beyond out_dim
+// are exact zeros) and reducer CTA r owns the Q = 8 * ceil(8 B / G) pairs [r Q, (r + 1) Q), i.e. whole groups of 8
+// consecutive outputs of one row.  CTA c's partial of pair q lives at part[r = q / Q][c][q % Q]: everything reducer r sums
+// is ONE contiguous block of G * Q floats (a single bulk copy), a draining thread (fixed b, walking o) writes float4s, and
+// the reducer publishes a group as one 16-byte core-matrix row per plane.  (The first version -- pair order [o][b],
+// scalar stores addressed as base + index -- compiled to ~20 dependent instructions per store: 2400 cycles per step.)
+struct PartWalk {
+    unsigned long long addr;   // address of the thread's first float4
+    unsigned long long wrap;   // extra bytes when the slot index wraps into the next reducer
+    int i, Q;                  // slot of that float4 in the reducer's row
+};
+static __device__ __forceinline__ PartWalk part_walk(float* part, int c, int G, int Q, int b, int o_first) {
+    PartWalk w;
+    w.Q = Q;
+    const int q0 = b * 64 + o_first;
+    const int r0 = q0 / Q;
+    w.i = q0 - r0 * Q;
+    w.addr = reinterpret_cast<unsigned long long>(part + ((size_t)r0 * G + c) * Q + w.i);
+    w.wrap = ((unsigned long long)G * Q - Q) * 4ull;
+    asm volatile("" : "+l"(w.addr), "+r"(w.i));   // keep them in registers: no rematerialisation per store
+    return w;
+}
+static __device__ __forceinline__ void st_global_v4(unsigned long long addr, float x, float y, float z, float w) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
 }  // namespace umma
