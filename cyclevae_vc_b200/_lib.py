@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcyclevae_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -56,6 +56,8 @@ PROTOTYPES = {
     "cvb_gru_rnn_backward": (_i, [_netp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _gradp, _vp]),
     "cvb_frontend_fwd": (_i, [_netp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cvb_frontend_bwd_ws_floats": (_sz, [_netp, _i, _i]),
+    "cvb_frontend_bwd": (_i, [_netp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _gradp, _vp]),
     "cvb_reparam_concat_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "cvb_reparam_concat_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cvb_concat2_fwd": (_i, [_i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),

@@ -785,4 +785,12 @@ int cvb_frontend_fwd(const cvb_net* net, int B, int T, const float* x_bm, const 
                      float* xc_tm, void* stream) {
     return cvb::frontend_fwd(net, B, T, x_bm, mask_conv_tm, fe_ws, xc_tm, (cudaStream_t)stream);
 }
+
+size_t cvb_frontend_bwd_ws_floats(const cvb_net* net, int B, int T) { return cvb::frontend_bwd_scratch_floats(net, B, T); }
+
+int cvb_frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const float* mask_conv_tm, const float* fe_ws,
+                     const float* dxc_tm, float* scratch, float* dx_bm, const cvb_net_grads* grads, void* stream) {
+    CVB_REQUIRE(net && x_bm && fe_ws && dxc_tm && scratch, "cvb_frontend_bwd: NULL argument");
+    return cvb::frontend_bwd(net, B, T, x_bm, mask_conv_tm, fe_ws, dxc_tm, scratch, dx_bm, grads, (cudaStream_t)stream);
+}
 }

@@ -116,11 +116,11 @@ def cyc_forward(enc: gv.GRU_RNN, dec: gv.GRU_RNN, *, x, cv, src_code, trg_code, 
         return None if eps is None else eps[i][k]
 
     for i in range(n_cyc):
-        enc_in = x if i == 0 else torch.cat((x[:, :, :stdim], out["trj_src_trg_src"][i - 1]), 2)
+        enc_in = x if i == 0 else gv.concat_features(x[:, :, :stdim], out["trj_src_trg_src"][i - 1])
         lat_src = run(enc, enc_in, "pp_src", i, 0, clamp_vae=True, lat_dim=lat_dim)
         trj_src_src = run(dec, gv.reparam_concat(lat_src, src_code, e(i, 0), lat_dim), "src_src", i, 1)
         trj_src_trg = run(dec, gv.reparam_concat(lat_src, trg_code, e(i, 1), lat_dim), "src_trg", i, 2)
-        lat_src_trg = run(enc, torch.cat((cv, trj_src_trg), 2), "pp_src_trg", i, 3, clamp_vae=True, lat_dim=lat_dim)
+        lat_src_trg = run(enc, gv.concat_features(cv, trj_src_trg), "pp_src_trg", i, 3, clamp_vae=True, lat_dim=lat_dim)
         trj_src_trg_src = run(dec, gv.reparam_concat(lat_src_trg, src_code, e(i, 2), lat_dim), "src_trg_src", i, 4)
         for k, v in zip(OUT_KEYS, (lat_src, trj_src_src, trj_src_trg, lat_src_trg, trj_src_trg_src)):
             out[k].append(v)

@@ -31,7 +31,7 @@ from . import _lib
 from ._lib import CvbNet, CvbNetGrads, check, lib, ptr
 
 __all__ = ["initialize", "TwoSidedDilConv1d", "GRU_RNN", "TWFSEloss", "sampling_vae_batch", "sampling_vae", "loss_vae",
-           "reparam_concat", "kl_per_utt", "mcd_l1_per_utt", "draw_dropout_masks", "LOG_VAR_FLOOR", "DeviceRng", "device_rng"]
+           "reparam_concat", "concat_features", "kl_per_utt", "mcd_l1_per_utt", "draw_dropout_masks", "LOG_VAR_FLOOR", "DeviceRng", "device_rng"]
 
 LOG_VAR_FLOOR = -13.815510557964274104107948728106  # gru_vae.py:412
 MAX_ROWS_PER_LAUNCH = 128   # batch rows of one persistent recurrence launch (= the M of a tcgen05 MMA)
@@ -129,9 +129,72 @@ class TwoSidedDilConv1d(nn.Module):
             self.conv += [nn.Conv1d(cin, cin * self.kernel_size, self.kernel_size, stride=1, dilation=self.kernel_size ** i,
                                     padding=self.padding if i == 0 else 0)]
 
+    def _net_struct(self, params) -> CvbNet:
+        """The front-end half of a cvb_net (no scale_in; the GRU fields are not read by cvb_frontend_fwd/bwd)."""
+        net = CvbNet()
+        net.in_dim, net.out_dim, net.hidden = self.in_dim, 1, 1
+        net.kernel_size, net.n_conv = self.kernel_size, self.layers
+        net.has_scale_in = net.has_scale_out = 0
+        for i in range(self.layers):
+            net.conv_w[i], net.conv_b[i] = ptr(params[2 * i]), ptr(params[2 * i + 1])
+        return net
+
     def forward(self, x):
-        raise NotImplementedError("TwoSidedDilConv1d is evaluated inside GRU_RNN.forward's fused front-end "
-                                  "(cvb_frontend_fwd); it has no stand-alone eager path")
+        """x [B, in, T] -> [B, in*k^layers, T] (gru_vae.py:53-66), stand-alone: the same front-end kernels GRU_RNN.forward
+        runs (cvb_frontend_fwd / cvb_frontend_bwd), differentiable w.r.t. x and the conv parameters."""
+        if self.layers > 4:
+            raise NotImplementedError("cyclevae_vc_b200: at most 4 conv layers (dilation_size)")
+        if not x.is_cuda:
+            raise RuntimeError("cyclevae_vc_b200 runs on CUDA only (no CPU fallback)")
+        params = []
+        for c in self.conv:
+            params += [c.weight, c.bias]
+        with torch.cuda.device(x.device):
+            return _ConvFn.apply(self, _f32c(x), *params)
+
+
+class _ConvFn(torch.autograd.Function):
+    """TwoSidedDilConv1d.forward through the C ABI: x [B,C,T] -> [B,C*k^L,T]."""
+
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        B, Cin, T = x.shape
+        dev = x.device
+        params = tuple(_f32c(p) for p in params)
+        net = mod._net_struct(params)
+        netp = C.byref(net)
+        x_bm = x.transpose(1, 2).contiguous()                     # [B,T,C]: the library's batch-major layout
+        fe_ws = torch.empty(lib.cvb_frontend_ws_floats(netp, B, T), dtype=torch.float32, device=dev)
+        Cout = Cin * mod.kernel_size ** mod.layers
+        xc_tm = torch.empty(T, B, Cout, dtype=torch.float32, device=dev)
+        check(lib.cvb_frontend_fwd(netp, B, T, ptr(x_bm), None, ptr(fe_ws), ptr(xc_tm), _stream()), "cvb_frontend_fwd")
+        ctx.mod, ctx.dims = mod, (B, T, Cin, Cout)
+        ctx.save_for_backward(x_bm, fe_ws, *params)
+        return xc_tm.permute(1, 2, 0).contiguous()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        mod = ctx.mod
+        B, T, Cin, Cout = ctx.dims
+        x_bm, fe_ws, *params = ctx.saved_tensors
+        dev = x_bm.device
+        net = mod._net_struct(params)
+        netp = C.byref(net)
+        dxc_tm = _f32c(d_out).permute(2, 0, 1).contiguous()       # [T,B,Cout]
+        need = ctx.needs_input_grad                               # (mod, x, *params)
+        dx_bm = torch.empty(B, T, Cin, dtype=torch.float32, device=dev) if need[1] else None
+        grads = CvbNetGrads()
+        gts = []
+        for i, p in enumerate(params):
+            g = torch.empty_like(p) if need[2 + i] else None
+            gts.append(g)
+            if g is not None:
+                (grads.conv_w if i % 2 == 0 else grads.conv_b)[i // 2] = ptr(g)
+        grads.accumulate = 0
+        scratch = torch.empty(lib.cvb_frontend_bwd_ws_floats(netp, B, T), dtype=torch.float32, device=dev)
+        check(lib.cvb_frontend_bwd(netp, B, T, ptr(x_bm), None, ptr(fe_ws), ptr(dxc_tm), ptr(scratch), ptr(dx_bm), C.byref(grads),
+                                   _stream()), "cvb_frontend_bwd")
+        return (None, None if dx_bm is None else dx_bm.transpose(1, 2), *gts)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -419,6 +482,51 @@ class _ReparamConcatFn(torch.autograd.Function):
         check(lib.cvb_reparam_concat_bwd(B, T, ctx.lat_dim, ctx.n_code, ptr(lat), ptr(eps), ptr(_f32c(d_out)), ptr(d_lat),
                                          _stream()), "cvb_reparam_concat_bwd")
         return d_lat, None, None, None
+
+
+def _row_stride(t: torch.Tensor):
+    """Leading dimension of `t` seen as [rows, C] when it is a last-dim slice of a contiguous tensor, else None."""
+    if t.stride(-1) != 1:
+        return None
+    ld = t.stride(-2) if t.dim() >= 2 else t.shape[-1]
+    exp = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != exp:
+            return None
+        exp *= t.shape[d]
+    return ld if ld >= t.shape[-1] else None
+
+
+class _Concat2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        if a.dtype != torch.float32 or b.dtype != torch.float32:
+            raise TypeError("cyclevae_vc_b200 computes in float32")
+        lda, ldb = _row_stride(a), _row_stride(b)
+        if lda is None:
+            a, lda = a.contiguous(), a.shape[-1]
+        if ldb is None:
+            b, ldb = b.contiguous(), b.shape[-1]
+        rows, ca, cb = a.numel() // a.shape[-1], a.shape[-1], b.shape[-1]
+        out = torch.empty(*a.shape[:-1], ca + cb, dtype=torch.float32, device=a.device)
+        check(lib.cvb_concat2_fwd(rows, ca, a.data_ptr(), lda, cb, b.data_ptr(), ldb, ptr(out), _stream()), "cvb_concat2_fwd")
+        ctx.ca = ca
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        return d_out[..., :ctx.ca], d_out[..., ctx.ca:]   # the split backward: two views of the incoming gradient
+
+
+def concat_features(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """torch.cat((a, b), 2) of the encoder-input call sites (train_*.py:1304: cat((cv, trj_src_trg), 2); :1307:
+    cat((x[:, :, :stdim], rec), 2)) as one library kernel (cvb_concat2_fwd)."""
+    if a.shape[:-1] != b.shape[:-1]:
+        raise ValueError(f"concat_features: leading shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+    if not (a.is_cuda and b.is_cuda):
+        raise RuntimeError("cyclevae_vc_b200 runs on CUDA only (no CPU fallback)")
+    with torch.cuda.device(a.device):
+        return _Concat2Fn.apply(a, b)
 
 
 def reparam_concat(param, code=None, eps=None, lat_dim=None):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 11
+#define CVB_ABI_VERSION 12
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -130,6 +130,14 @@ int cvb_gru_rnn_backward(const cvb_net* net, int B, int T, const float* x_bm,
 /* scale_in + TwoSidedDilConv1d (+mask) -> xc_tm [T,B,in*k^n]   (gru_vae.py:336,53-66,355) */
 int cvb_frontend_fwd(const cvb_net* net, int B, int T, const float* x_bm, const float* mask_conv_tm,
                      float* fe_ws, float* xc_tm, void* stream);
+
+/* backward of cvb_frontend_fwd (TwoSidedDilConv1d.forward stand-alone, gru_vae.py:53-66, and the front-end half of
+ * GRU_RNN's BPTT): dxc_tm [T,B,in*k^n] = gradient of the masked conv output -> dx_bm [B,T,in] (may be NULL) and the conv /
+ * scale_in gradients named in `grads` (NULL members are skipped; grads may be NULL).  x_bm / mask_conv_tm / fe_ws as
+ * given to / left by cvb_frontend_fwd; scratch: cvb_frontend_bwd_ws_floats(net, B, T) floats. */
+size_t cvb_frontend_bwd_ws_floats(const cvb_net* net, int B, int T);
+int cvb_frontend_bwd(const cvb_net* net, int B, int T, const float* x_bm, const float* mask_conv_tm, const float* fe_ws,
+                     const float* dxc_tm, float* scratch, float* dx_bm, const cvb_net_grads* grads, void* stream);
 
 /* ---- sampling_vae_batch + torch.cat((code, z), 2) fused (gru_vae.py:85-98; train_*.py:1302) ---
  * lat_bm [B,T,2*lat] = [mu | log-var]; eps_bm [B,T,lat] or NULL (then N(0,1) is drawn in-kernel

@@ -1117,3 +1117,55 @@ def test_device_mcd_and_dtw_metrics(cvb):
     _, p2, s2 = cycle.dtw_org_to_trg(torch.tensor(a).cuda(), torch.tensor(b).cuda())
     _, rp2, _, rsteps2, _ = dto.dtw_org_to_trg(a, b)
     assert (p2.cpu().numpy() == rp2).all() and int(s2[1]) == rsteps2
+
+
+@pytest.mark.parametrize("in_dim,B,T", [(7, 3, 11), (54, 80, 80)])
+def test_two_sided_dil_conv_stand_alone(cvb, in_dim, B, T):
+    """TwoSidedDilConv1d.forward on its own (gru_vae.py:53-66: x [B,C,T] -> [B,9C,T]) and its gradients against the same
+    stack of torch Conv1d layers evaluated in float64 on the CPU; the small shape runs the per-tap products, the bench shape
+    the composed / tap-fused tensor-core products."""
+    torch.manual_seed(3)
+    conv = cvb.TwoSidedDilConv1d(in_dim=in_dim, kernel_size=3, layers=2)
+    conv.apply(cvb.initialize)
+    for c in conv.conv:
+        torch.nn.init.normal_(c.bias, std=0.1)
+    ref = [torch.nn.Conv1d(c.in_channels, c.out_channels, 3, dilation=c.dilation, padding=c.padding).double() for c in conv.conv]
+    for r, c in zip(ref, conv.conv):
+        r.weight.data.copy_(c.weight.data.double())
+        r.bias.data.copy_(c.bias.data.double())
+    conv = conv.cuda()
+    x = torch.randn(B, in_dim, T)
+    w = torch.randn(B, in_dim * 9, T)
+    xr = x.double().requires_grad_(True)
+    yr = ref[1](ref[0](xr))
+    (yr * w.double()).sum().backward()
+    xd = x.cuda().requires_grad_(True)
+    yd = conv(xd)
+    assert yd.shape == (B, in_dim * 9, T)
+    (yd * w.cuda()).sum().backward()
+    scale = max(1.0, float(yr.abs().max()))
+    assert _maxabs(yd.double(), yr.detach()) < TOL * scale
+    assert _maxabs(xd.grad.double(), xr.grad) < TOL * max(1.0, float(xr.grad.abs().max()))
+    for r, c in zip(ref, conv.conv):
+        assert _maxabs(c.weight.grad.double(), r.weight.grad) < 2e-4 * max(1.0, float(r.weight.grad.abs().max()))
+        assert _maxabs(c.bias.grad.double(), r.bias.grad) < 2e-4 * max(1.0, float(r.bias.grad.abs().max()))
+
+
+def test_concat_features_matches_torch_cat(cvb):
+    """The encoder-input concatenations of the trainer (train_*.py:1304,1307) through cvb_concat2_fwd: a strided slice as the
+    first part (x[:, :, :stdim]), values and the split gradient bit-exact against torch.cat."""
+    from cyclevae_vc_b200 import gru_vae as gv
+    torch.manual_seed(5)
+    x = torch.randn(6, 13, 54, device="cuda")
+    rec = torch.randn(6, 13, 50, device="cuda", requires_grad=True)
+    a = x[:, :, :4]
+    out = gv.concat_features(a, rec)
+    ref = torch.cat((a, rec.detach()), 2)
+    assert torch.equal(out.detach(), ref)
+    g = torch.randn_like(out)
+    out.backward(g)
+    assert torch.equal(rec.grad, g[:, :, 4:])
+    cv = torch.randn(6, 13, 4, device="cuda", requires_grad=True)
+    out2 = gv.concat_features(cv, rec.detach())
+    out2.backward(g)
+    assert torch.equal(out2.detach(), torch.cat((cv.detach(), rec.detach()), 2)) and torch.equal(cv.grad, g[:, :, :4])

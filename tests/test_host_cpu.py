@@ -96,6 +96,8 @@ def test_no_cpu_fallback_and_unused_kwargs_raise(pkg):
     for kw in (dict(softmax=True), dict(res=True), dict(noise=0.1), dict(relu_vae=True), dict(clamp_vae_laplace=True)):
         with pytest.raises(NotImplementedError):
             m(x, y, **kw)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        pkg.TwoSidedDilConv1d(in_dim=5)(torch.zeros(2, 5, 7))    # stand-alone conv: same rule, no eager path
     with pytest.raises(NotImplementedError):
         pkg.GRU_RNN(hidden_layers=2)
     with pytest.raises(NotImplementedError):
