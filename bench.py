@@ -332,8 +332,10 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device: cyclevae_vc_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)        # plumbing: barriers, max-over-ranks of the timings, id exchange
+        comm = cycle.NativeComm(rank, world)                  # the data-path collective: the library's own cvb_allreduce_sum
     decode = args.workload == "decode"
     B, T = args.batch_utt, (DEC_T if decode else TCHUNK)
     enc, dec, y0d1 = synth.build_models(HIDDEN, LAT, args.n_spk, NMCEP, STDIM, seed=1, device=dev)
@@ -361,7 +363,7 @@ def run_native(args):
         opt = cycle.FlatAdam(cycle.trainable_parameters(enc, dec), lr=1e-4)
         # the fused step driver: forward + losses + BPTT replayed as one CUDA graph, all-reduce, Adam
         cs = cycle.CycleStep(enc, dec, opt, B=B, T=T, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, n_spk=args.n_spk, y0_enc=y0e, y0_dec=y0d,
-                             graph=not args.no_graph)
+                             graph=not args.no_graph, comm=comm)
 
         def step(x, cv, sc, tc):
             return cs.step(x, cv, sc, tc)
@@ -418,7 +420,7 @@ def run_native(args):
         # buffers) is run kernel by kernel for a few extra steps with CUDA events around every recurrence launch and
         # front-end chain on the launching stream.  Outside the timed region above; only feeds the roofline objects.
         eager = cycle.CycleStep(enc, dec, opt, B=B, T=T, n_cyc=NCYC, lat_dim=LAT, stdim=STDIM, n_spk=args.n_spk, y0_enc=y0e, y0_dec=y0d,
-                                graph=False)
+                                graph=False, comm=comm)
         for d, h in zip((eager.x, eager.cv, eager.sc, eager.tc), host):
             d.copy_(h)
         eager.step(eager.x, eager.cv, eager.sc, eager.tc)
@@ -512,6 +514,8 @@ def run_native(args):
         cfg = config_of(args, world)
         cfg["l2"] = "per-step working set (saved gate activations / gx, > 1 GB at the default batch) exceeds the 126 MB L2; no flush needed"
         cfg["last_result"] = last
+        if world > 1 and not decode:
+            cfg["collective"] = f"one cvb_allreduce_sum per step (ncclAllReduce SUM fp32 over the flat gradient buffer, {opt.n * 4 / 1e6:.1f} MB)"
         if full_ms is not None:
             cfg["full_stage6"] = {"composition": "2 ENC + 3 DEC (decode_*.py:303-323)", "ms_per_step": full_ms,
                                   "frames_per_s": B * T * world / (full_ms * 1e-3)}
@@ -559,6 +563,7 @@ def run_native(args):
                                              + " on the host CPU"}
         print(json.dumps(res))
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

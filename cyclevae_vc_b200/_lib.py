@@ -60,6 +60,10 @@ PROTOTYPES = {
     "cvb_frontend_bwd": (_i, [_netp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _gradp, _vp]),
     "cvb_reparam_concat_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "cvb_reparam_concat_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cvb_comm_unique_id": (_i, [_vp]),
+    "cvb_comm_init": (_i, [C.POINTER(_vp), _vp, _i, _i]),
+    "cvb_allreduce_sum": (_i, [_vp, _vp, _sz, _vp]),
+    "cvb_comm_destroy": (_i, [_vp]),
     "cvb_concat2_fwd": (_i, [_i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "cvb_kl_fwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "cvb_kl_bwd": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

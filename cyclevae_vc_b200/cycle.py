@@ -207,10 +207,47 @@ class FlatAdam:
                                     grad_scale, torch.cuda.current_stream().cuda_stream), "cvb_adam_step")
 
 
-def allreduce_grads(flat_grad: torch.Tensor) -> None:
+class NativeComm:
+    """The library's own NCCL communicator (cvb_comm_init / cvb_allreduce_sum of the C ABI): one per rank, created on the
+    current CUDA device.  The 128-byte NCCL id is made by rank 0 and handed to the other ranks by the caller's side
+    channel -- here torch.distributed's object broadcast when a process group is up (the plumbing; the collective on
+    the data path is the library's)."""
+
+    def __init__(self, rank: int, world: int, unique_id: Optional[bytes] = None):
+        import ctypes as C
+        if unique_id is None:
+            import torch.distributed as dist
+            box = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                check(lib.cvb_comm_unique_id(buf), "cvb_comm_unique_id")
+                box[0] = buf.raw
+            dist.broadcast_object_list(box, src=0)
+            unique_id = box[0]
+        self.rank, self.world = rank, world
+        self._h = C.c_void_p()
+        check(lib.cvb_comm_init(C.byref(self._h), C.c_char_p(unique_id), rank, world), "cvb_comm_init")
+
+    def allreduce_sum(self, flat: torch.Tensor) -> None:
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
+        with torch.cuda.device(flat.device):
+            check(lib.cvb_allreduce_sum(self._h, flat.data_ptr(), flat.numel(), torch.cuda.current_stream().cuda_stream), "cvb_allreduce_sum")
+
+    def close(self) -> None:
+        if self._h:
+            check(lib.cvb_comm_destroy(self._h), "cvb_comm_destroy")
+            self._h = None
+
+
+def allreduce_grads(flat_grad: torch.Tensor, comm: Optional[NativeComm] = None) -> None:
     """The only collective of the data-parallel path: SUM (not mean -- the reference sums the
     per-utterance losses, train_*.py:1403,1408, so summed shard gradients equal the gradient of one
-    process holding every shard's utterances)."""
+    process holding every shard's utterances).  comm: the library's own communicator (cvb_allreduce_sum);
+    None: torch.distributed's NCCL process group when one is initialised."""
+    if comm is not None:
+        if comm.world > 1:
+            comm.allreduce_sum(flat_grad)
+        return
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
@@ -228,9 +265,10 @@ class CycleStep:
     flens: int32 [B] frames of each utterance that count in the losses (flen_acc; 0 = utterance not selected)."""
 
     def __init__(self, enc: gv.GRU_RNN, dec: gv.GRU_RNN, opt: FlatAdam, *, B: int, T: int, n_cyc: int, lat_dim: int, stdim: int,
-                 n_spk: int, y0_enc: torch.Tensor, y0_dec: torch.Tensor, graph: bool = True, kl_cv_quirk: bool = True):
+                 n_spk: int, y0_enc: torch.Tensor, y0_dec: torch.Tensor, graph: bool = True, kl_cv_quirk: bool = True,
+                 comm: Optional[NativeComm] = None):
         dev = opt.flat.device
-        self.enc, self.dec, self.opt = enc, dec, opt
+        self.enc, self.dec, self.opt, self.comm = enc, dec, opt, comm
         self.n_cyc, self.lat_dim, self.stdim, self.kl_cv_quirk = n_cyc, lat_dim, stdim, kl_cv_quirk
         self.x = torch.zeros(B, T, enc.in_dim, device=dev)
         self.cv = torch.zeros(B, T, stdim, device=dev)
@@ -282,7 +320,7 @@ class CycleStep:
             self.graph.replay()
         else:
             self._body()
-        allreduce_grads(self.opt.grad)
+        allreduce_grads(self.opt.grad, self.comm)
         self.opt.step(dev_state=self.rng.state)
         check(lib.cvb_state_advance(self.rng.state.data_ptr(), 0, 1, torch.cuda.current_stream().cuda_stream), "cvb_state_advance")
         return self.loss

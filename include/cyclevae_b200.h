@@ -154,6 +154,17 @@ int cvb_reparam_concat_bwd(int B, int T, int lat, int n_code, const float* lat_b
 int cvb_concat2_fwd(int rows, int ca, const float* a, int lda, int cb, const float* b, int ldb,
                     float* out, void* stream);
 
+/* ---- the data-parallel collective: utterance shards, one all-reduce of the flat gradient buffer ----
+ * NCCL is bound at run time (dlopen of libnccl.so.2).  One communicator per rank = per GPU = per process (or per host
+ * thread that has made its device current).  Rank 0 calls cvb_comm_unique_id and hands the 128 bytes to the other ranks
+ * by any side channel; every rank then calls cvb_comm_init on its own device.  cvb_allreduce_sum adds `flat` over the
+ * ranks IN PLACE on `stream` -- SUM, not mean: the reference sums per-utterance losses (train_*.py:1403,1408), so summed
+ * shard gradients equal the gradient of one process holding every shard's utterances. */
+int cvb_comm_unique_id(void* id128);
+int cvb_comm_init(void** comm, const void* id128, int rank, int world);
+int cvb_allreduce_sum(void* comm, float* flat, size_t n_floats, void* stream);
+int cvb_comm_destroy(void* comm);
+
 /* ---- losses -----------------------------------------------------------------------------------
  * loss_vae (gru_vae.py:117-123) per utterance: kl[j] = mean_{t<flen[j]} 0.5*sum_d(e^s+mu^2-s-1).
  * lat_bm [B,T,2*lat]; flens int32 [B] (device); utterances with flen<=0 give 0. */

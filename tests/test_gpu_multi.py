@@ -63,14 +63,18 @@ def _worker(rank, world, port, out_q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", device_id=dev)
     res = {}
+    comm = cycle.NativeComm(rank, world)                 # the library's own communicator (cvb_comm_init through the C ABI)
     for chunk in (0, 1):
         lo, hi = cycle.shard_utterances(4, rank, world)
         g, selected = _grads_for(range(lo, hi), chunk, dev)
-        cycle.allreduce_grads(g)                         # the only collective: SUM
+        g_lib = g.clone()
+        cycle.allreduce_grads(g)                         # the only collective: SUM (torch.distributed's NCCL group)
+        cycle.allreduce_grads(g_lib, comm)               # the same through cvb_allreduce_sum
         torch.cuda.synchronize()
         if rank == 0:
             full, _ = _grads_for(range(4), chunk, dev)
-            res[chunk] = (float((g - full).abs().max()), float(full.abs().max()), list(selected))
+            res[chunk] = (float((g - full).abs().max()), float(full.abs().max()), list(selected), float((g_lib - g).abs().max()))
+    comm.close()
     if rank == 0:
         out_q.put(res)
     dist.barrier()
@@ -93,5 +97,6 @@ def test_two_gpu_summed_shard_gradients_equal_single_gpu_gradient():
         assert p.exitcode == 0
     assert res[0][2] == [0, 1, 2, 3] and res[1][2] == [0, 1]        # second chunk: rank 1 has no utterance left (zero gradient, still reduces)
     for chunk in (0, 1):
-        err, scale, _ = res[chunk]
+        err, scale, _, lib_vs_torch = res[chunk]
         assert err <= 2e-4 * max(1.0, scale), (chunk, err, scale)
+        assert lib_vs_torch <= 1e-6 * max(1.0, scale), (chunk, lib_vs_torch)   # two-rank sums: the same additions either way
