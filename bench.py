@@ -84,6 +84,50 @@ def folded_flops_per_frame():
     return 2 * 4 * HIDDEN * HIDDEN        # [r' | z' | hn | in'] rows of the folded inference recurrence (gru_tc_eval.cu)
 
 
+def streaming_rooflines(enc, dec, opt, B, T, n_spk, dev, peak_hbm):
+    """Achieved HBM GB/s of the path's streaming kernels (bytes = inputs + outputs once), each timed
+    alone with CUDA events after an L2 flush (a 256 MB write), median of 9 launches, at the step's own sizes."""
+    import torch
+    from cyclevae_vc_b200 import gru_vae as gv
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    lat = torch.randn(B, T, 2 * LAT, device=dev)
+    code = torch.zeros(B, T, n_spk, device=dev)
+    trj = torch.randn(B, T, NMCEP, device=dev)
+    x = torch.randn(B, T, STDIM + NMCEP, device=dev)
+    flens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    conv_dim, frames = 9 * (STDIM + NMCEP), B * T
+    cases = [
+        ("k_adam (cvb_adam_step: Adam over the flat parameter buffer)", lambda: opt.step(), opt.n * 28.0,
+         "read p, g, m, v + write p, m, v = 28 B per parameter"),
+        ("k_dropout_mask (conv + GRU-output masks of one encoder pass)", lambda: gv.draw_dropout_masks(B, T, conv_dim, HIDDEN, 0.5, dev),
+         frames * (conv_dim + HIDDEN) * 4.0, "4 B per mask element written"),
+        ("k_reparam_concat_fwd (sampling_vae_batch + speaker-code concat, noise drawn in-kernel)",
+         lambda: gv.reparam_concat(lat, code, None, LAT), frames * (2 * LAT + n_spk + (n_spk + LAT) + LAT) * 4.0,
+         "read [mu|log-var] + code, write [code|z] + the stored noise"),
+        ("k_kl_fwd (loss_vae per utterance)", lambda: gv.kl_per_utt(lat, flens, LAT), frames * 2 * LAT * 4.0, "256 B per frame read"),
+        ("k_mcd_fwd (TWFSEloss L1 per utterance)", lambda: gv.mcd_l1_per_utt(trj, x, flens, 0, STDIM), frames * 2 * NMCEP * 4.0,
+         "400 B per frame read"),
+    ]
+    out = []
+    with torch.no_grad():
+        for name, fn, nbytes, what in cases:
+            fn()
+            ts = []
+            for _ in range(9):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = statistics.median(ts)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out.append({"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                        "ms": ms, "algorithmic_bytes": nbytes, "bytes_rule": what})
+    return out
+
+
 def frontend_bytes_per_frame(in_dim):
     return 4 * in_dim + 4 * 9 * in_dim    # read x, write xc (SURVEY.md §8d: 2160 B ENC, 1360 B DEC)
 
@@ -546,6 +590,8 @@ def run_native(args):
         }
         if roof_fe:
             res["roofline_frontend"] = roof_fe
+        if not decode:
+            res["roofline_streaming"] = streaming_rooflines(enc, dec, opt, B, T, args.n_spk, dev, peak_hbm)
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             if decode:
