@@ -53,6 +53,11 @@ bool gru_tc_supported(int B, int H, int out, const DeviceInfo& di);
 size_t gru_tc_scratch_floats(int B, int H);
 int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s);
 
+// one-exchange-per-step variant of the training forward kernel (cluster partials of y summed by every consumer), gru_tc2.cu
+bool gru_tc2_supported(int B, int H, int out, const DeviceInfo& di);
+size_t gru_tc2_scratch_floats(int B, int H);
+int gru_ar_fwd_tc2(GruFwdArgs& a, float* tc_scratch, cudaStream_t s);
+
 // inference-only forward with the y feedback folded into the recurrent matrix (one exchange per step), gru_tc_eval.cu
 bool gru_tc_eval_shape_ok(int B, int H);                    // host-only shape test (any out_dim)
 bool gru_tc_eval_supported(int B, int H, int out, const DeviceInfo& di);

@@ -806,7 +806,15 @@ size_t gru_tc_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
     size_t hx = (size_t)2 * 2 * (H / TF_KC) * MB * 512 / 2;   // fp16 elements -> floats
     size_t yx = (size_t)TF_YREP * 2 * 2 * MB * 512 / 2;
-    return round_up_sz(hx, 64) + round_up_sz(yx, 64) + 64 + tf_part_floats(B, H);
+    const size_t two_hop = round_up_sz(hx, 64) + round_up_sz(yx, 64) + 64 + tf_part_floats(B, H);
+    const size_t one_hop = gru_tc2_scratch_floats(B, H);
+    return two_hop > one_hop ? two_hop : one_hop;
+}
+
+// CVB_TC_FEEDBACK=grid keeps the two-exchange kernel of this file (A/B); default: the one-exchange kernel of gru_tc2.cu
+static bool want_one_hop() {
+    const char* e = getenv("CVB_TC_FEEDBACK");
+    return !(e && e[0] == 'g');
 }
 
 // are all G/4 clusters co-resident at this shape?  (cached per shape)
@@ -855,6 +863,7 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     if (f.T <= 0 || f.B <= 0) return 0;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
+    if (want_one_hop() && gru_tc2_supported(f.B, f.H, f.out, di)) return gru_ar_fwd_tc2(f, tc_scratch, s);
     TfLayout L;
     CVB_REQUIRE(fwd_runnable(f.B, f.H, f.out, di, &L), "gru_ar_fwd_tc: unsupported shape B=%d H=%d out=%d", f.B, f.H, f.out);
     GruTcArgs a;
