@@ -57,6 +57,10 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s);
 bool gru_tc2_supported(int B, int H, int out, const DeviceInfo& di);
 size_t gru_tc2_scratch_floats(int B, int H);
 int gru_ar_fwd_tc2(GruFwdArgs& a, float* tc_scratch, cudaStream_t s);
+bool gru_tc2_bwd_supported(int B, int H, int out, const DeviceInfo& di);
+size_t gru_tc2_bwd_scratch_floats(int B, int H);
+int gru_ar_bwd_tc2(GruBwdArgs& a, float* tc_scratch, cudaStream_t s);
+bool gru_tc_one_hop();   // CVB_TC_FEEDBACK=grid keeps the two-exchange training kernels (A/B); default: the one-exchange kernels
 
 // inference-only forward with the y feedback folded into the recurrent matrix (one exchange per step), gru_tc_eval.cu
 bool gru_tc_eval_shape_ok(int B, int H);                    // host-only shape test (any out_dim)

@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
         const uint32_t inbox_bar_addr = smem_u32(inbox_full);
         const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
         const uint32_t slot_f = L.slot_bytes / 4;
+        const bool wact = (warp - 4) * 32 < L.MB * 8;   // this warp holds rows of the staged row groups
         float hreg[8];
         {   // prologue: publish h_in (slot 0) in operand order; y_in needs no partials
 #pragma unroll
@@ -442,6 +443,9 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
             mbar_wait(d1_full, (uint32_t)t & 1);
             if (etid == 0) T2_TRACE(1);
             tc_fence_after();
+            // a warp whose 32 rows are all beyond B skips the drain: the 288 columns of D1 are TMEM-read-bandwidth bound
+            // (147 KB at 64 B/clk for four warps)
+            if (wact) {
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
 #pragma unroll
@@ -469,6 +473,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                         }
                     }
                 }
+            }
             }
             fence_proxy_async_smem();
             named_bar_sync(3, 128);

@@ -685,7 +685,9 @@ size_t gru_tc_bwd_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
     size_t gxh = (size_t)2 * 2 * (3 * H / TB_KC) * MB * 512 / 2;   // bf16 elements -> floats
     size_t dyx = (size_t)2 * 2 * MB * 512 / 2;
-    return round_up_sz(gxh, 64) + round_up_sz(dyx, 64) + 64 + tb_part_floats(B, H);
+    const size_t two_hop = round_up_sz(gxh, 64) + round_up_sz(dyx, 64) + 64 + tb_part_floats(B, H);
+    const size_t one_hop = gru_tc2_bwd_scratch_floats(B, H);
+    return two_hop > one_hop ? two_hop : one_hop;
 }
 
 // picks the cluster size (8 preferred) whose clusters are all co-resident; 0 = not runnable
@@ -743,6 +745,10 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     if (f.T <= 0 || f.B <= 0) return 0;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
+    {
+        const char* e8 = getenv("CVB_TC_CLUSTER8");
+        if (gru_tc_one_hop() && !(e8 && e8[0] == '1') && gru_tc2_bwd_supported(f.B, f.H, f.out, di)) return gru_ar_bwd_tc2(f, tc_scratch, s);
+    }
     TbLayout L;
     const int S = pick_cluster(f.B, f.H, f.out, di, &L);
     CVB_REQUIRE(S != 0, "gru_ar_bwd_tc: unsupported shape B=%d H=%d out=%d", f.B, f.H, f.out);
