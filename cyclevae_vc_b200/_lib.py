@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcyclevae_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -52,6 +52,7 @@ PROTOTYPES = {
     "cvb_scratch_floats": (_sz, [_netp, _i, _i, _i]),
     "cvb_recurrence_max_rows": (_i, [_netp, _i]),
     "cvb_last_recurrence_path": (_i, [_i]),
+    "cvb_last_recurrence_hops": (_i, [_i]),
     "cvb_gru_rnn_forward": (_i, [_netp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvb_gru_rnn_backward": (_i, [_netp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _gradp, _vp]),

@@ -190,6 +190,10 @@ size_t cvb_scratch_floats(const cvb_net* net, int B, int T, int training) {
 // which recurrence kernel the last forward / backward call of this process launched (tests: no silent fallback)
 static int g_last_path[2] = {-1, -1};
 int cvb_last_recurrence_path(int backward) { return g_last_path[backward ? 1 : 0]; }
+int cvb_last_recurrence_hops(int backward) {
+    const int p = g_last_path[backward ? 1 : 0];
+    return p == CVB_PATH_TC_FOLDED ? 1 : p == CVB_PATH_TC ? g_tc_hops[backward ? 1 : 0] : 0;
+}
 
 int cvb_recurrence_max_rows(const cvb_net* net, int mode) {
     // largest batch-row count (multiple of 8, <= 128) one launch of the tensor-core recurrence kernels holds at this

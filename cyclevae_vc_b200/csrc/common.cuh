@@ -167,6 +167,17 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Arrival counters in CTR_BANKS banks (one 128-byte line each).  128 CTAs adding to ONE address serialise in the L2 atomic
+// unit (~27 cycles per same-address atomic, B300_MICROARCH.md "L2-atom multi-CTA"): the last arrival of a round would be
+// performed > 3 000 cycles after the first.  CTA c arrives on bank c % CTR_BANKS; a polling warp watches every bank, one
+// per lane (the warp barrier behind the polls makes every lane's acquire cumulative for all of them).
+constexpr int CTR_BANKS = 8;
+__device__ __forceinline__ void banked_arrive(unsigned* base, int c) { red_release_gpu_add(base + 32 * (c & (CTR_BANKS - 1)), 1u); }
+__device__ __forceinline__ void banked_wait_warp(const unsigned* base, unsigned per_bank_target, int lane, bool relaxed) {
+    if (lane < CTR_BANKS) spin_until_ge(base + 32 * lane, per_bank_target, relaxed);
+    __syncwarp();
+}
+
 // Grid-wide barrier for a co-resident (cooperatively launched) grid.  `ctr` is zero at kernel
 // start; `target` is this thread's running count of expected arrivals (starts at 0).
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target, unsigned n_cta) {

@@ -60,6 +60,7 @@ int gru_ar_fwd_tc2(GruFwdArgs& a, float* tc_scratch, cudaStream_t s);
 bool gru_tc2_bwd_supported(int B, int H, int out, const DeviceInfo& di);
 size_t gru_tc2_bwd_scratch_floats(int B, int H);
 int gru_ar_bwd_tc2(GruBwdArgs& a, float* tc_scratch, cudaStream_t s);
+extern int g_tc_hops[2];   // grid-wide exchanges per step of the last tensor-core launch: [0] forward, [1] backward
 bool gru_tc_one_hop();   // CVB_TC_FEEDBACK=grid keeps the two-exchange training kernels (A/B); default: the one-exchange kernels
 
 // inference-only forward with the y feedback folded into the recurrent matrix (one exchange per step), gru_tc_eval.cu

@@ -812,6 +812,7 @@ size_t gru_tc_scratch_floats(int B, int H) {
 }
 
 // CVB_TC_FEEDBACK=grid keeps the two-exchange kernel of this file (A/B); default: the one-exchange kernel of gru_tc2.cu
+int g_tc_hops[2] = {0, 0};
 bool gru_tc_one_hop() {
     const char* e = getenv("CVB_TC_FEEDBACK");
     return !(e && e[0] == 'g');
@@ -863,7 +864,11 @@ int gru_ar_fwd_tc(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     if (f.T <= 0 || f.B <= 0) return 0;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
-    if (gru_tc_one_hop() && gru_tc2_supported(f.B, f.H, f.out, di)) return gru_ar_fwd_tc2(f, tc_scratch, s);
+    if (gru_tc_one_hop() && gru_tc2_supported(f.B, f.H, f.out, di)) {
+        g_tc_hops[0] = 1;
+        return gru_ar_fwd_tc2(f, tc_scratch, s);
+    }
+    g_tc_hops[0] = 2;
     TfLayout L;
     CVB_REQUIRE(fwd_runnable(f.B, f.H, f.out, di, &L), "gru_ar_fwd_tc: unsupported shape B=%d H=%d out=%d", f.B, f.H, f.out);
     GruTcArgs a;

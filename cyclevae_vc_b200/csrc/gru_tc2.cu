@@ -92,10 +92,11 @@ struct GruTc2Args {
     GruFwdArgs f;
     uint16_t* hx;        // [2 slots][2 parts][H/64 chunks][MB][8 kblk][8 rows][8 k] fp16 (UMMA order) of h_t
     unsigned long long* yacc;   // [2 slots][64 outputs][MB*8 rows] running fixed-point totals of y_t, zero-initialised
-    unsigned* ctr;       // [0] = H, [32] = Y (separate 128-B lines), zero-initialised
+    unsigned* ctr;       // CTR_BANKS lines of counter H, then CTR_BANKS lines of counter Y (common.cuh), zero-initialised
     int smem_max;
     int keepalive;
     int relaxed;
+    int dbg;            // CVB_TC_DBG bits (experiments): 1 = skip the fixed-point adds (wrong results), 2 = no L2 prefetch of the next frames
     long long* trace;    // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE_FWD), else null
 };
 
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 22);
     const size_t hx_part = (size_t)(H / T2_KC) * L.MB * 512;   // elements per part
     unsigned* ctrH = a.ctr;
-    unsigned* ctrY = a.ctr + 32;
+    unsigned* ctrY = a.ctr + 32 * CTR_BANKS;
+    const unsigned per_bank = (unsigned)(G / CTR_BANKS);
     const int n_pairs = B * out;
     const int half1 = (L.nch + 1) / 2;   // first chunk of the K-slice that accumulates into main1
     const bool two_main = half1 < L.nch;
@@ -276,11 +278,8 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
         uint32_t ph = 1;
         for (int t = 0; t < T; ++t) {
             const uint16_t* src = a.hx + (size_t)(t & 1) * 2 * hx_part + (size_t)(j * L.nch) * L.MB * 512;
-            if (lane == 0) {
-                spin_until_ge(ctrH, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);   // the writers fenced generic -> async proxy before their release
-                T2_TRACE(14);
-            }
-            __syncwarp();
+            banked_wait_warp(ctrH, per_bank * (unsigned)(t + 1), lane, a.relaxed != 0);   // the writers fenced generic -> async proxy before their release
+            if (lane == 0) T2_TRACE(14);
             for (int ch = 0; ch < L.nch; ++ch) {
                 if (lane == 0) {
                     mbar_wait(&empty[s], ph);
@@ -319,7 +318,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                 ok = __shfl_sync(0xffffffffu, ok, 0);
                 if (ok) break;
                 if (!block) return false;
-                if (a.keepalive) mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dA0, dB2, idesc_dummy, false);
+                if (a.keepalive) mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dW0, dB2, idesc_dummy, false);
             }
             if (lane == 0) T2_TRACE(12);
             tc_fence_after();
@@ -340,10 +339,9 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                     uint32_t ok = (lane == 0) ? (mbar_test_wait(&full[s], ph) ? 1u : 0u) : 0u;
                     ok = __shfl_sync(0xffffffffu, ok, 0);
                     if (ok) break;
-                    if (!y_done)
-                        y_done = try_y(t, false);
-                    else if (a.keepalive)
-                        mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dA0, dB2, idesc_dummy, false);
+                    if (!y_done) y_done = try_y(t, false);
+                    if (a.keepalive && !(a.dbg & 32))
+                        mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dW0, dB2, idesc_dummy, false);
                 }
                 if (lane == 0 && ch < 8) T2_TRACE(40 + ch);
                 tc_fence_after();
@@ -382,7 +380,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                 uint32_t ok = (lane == 0) ? (mbar_test_wait(a2_full, (uint32_t)t & 1) ? 1u : 0u) : 0u;
                 ok = __shfl_sync(0xffffffffu, ok, 0);
                 if (ok) break;
-                if (a.keepalive) mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dA0, dB2, idesc_dummy, false);
+                if (a.keepalive) mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dW0, dB2, idesc_dummy, false);
             }
             if (lane == 0) T2_TRACE(13);
             tc_fence_after();
@@ -417,26 +415,31 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
             fence_proxy_async_all();
             named_bar_sync(1, 128);
             if (etid == 0) {
-                red_release_gpu_add(ctrH, 1u);
-                red_release_gpu_add(ctrY, 1u);
+                banked_arrive(ctrH, c);
+                banked_arrive(ctrY, c);
             }
         }
+        // Gate inputs of the step: every lane loads (the rows beyond B re-read row 0 of the frame), so the gate math is branch-free.
+        // Their frames were pulled into L2 two steps earlier by warp 8 (bulk prefetch in the window in which no CTA pulls h chunks;
+        // see gru_tc2_bwd.cu for what HBM misses at the step top cost).
+        float4 gxv[6];
+        float4 mk[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
+        auto fetch_inputs = [&](int tt) {
+            const size_t rw = (size_t)tt * B + (act ? b : 0);
+            const float* gp = f.gx + rw * 3 * H + u0;
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) {
+                gxv[2 * gi] = ldg_nc_v4_pinned(gp + (size_t)gi * H);
+                gxv[2 * gi + 1] = ldg_nc_v4_pinned(gp + (size_t)gi * H + 4);
+            }
+            if (f.mask) {
+                mk[0] = ldg_nc_v4_pinned(f.mask + rw * H + u0);
+                mk[1] = ldg_nc_v4_pinned(f.mask + rw * H + u0 + 4);
+            }
+        };
         for (int t = 0; t < T; ++t) {
             const size_t row = (size_t)t * B + (act ? b : 0);
-            float4 gxv[6];
-            float4 mk[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
-            {   // every lane loads (the rows beyond B re-read row 0 of the frame), so the gate math below is branch-free
-                const float* gp = f.gx + row * 3 * H + u0;
-#pragma unroll
-                for (int gi = 0; gi < 3; ++gi) {
-                    gxv[2 * gi] = ldg_nc_v4_pinned(gp + (size_t)gi * H);
-                    gxv[2 * gi + 1] = ldg_nc_v4_pinned(gp + (size_t)gi * H + 4);
-                }
-                if (f.mask) {
-                    mk[0] = ldg_nc_v4_pinned(f.mask + row * H + u0);
-                    mk[1] = ldg_nc_v4_pinned(f.mask + row * H + u0 + 4);
-                }
-            }
+            fetch_inputs(t);
             if (etid == 0) T2_TRACE(0);
             if (etid == 0) mbar_expect_tx(inbox_full, (uint32_t)T2_S * L.slot_bytes);
             // ---- exchange of the K-slice partial sums ------------------------------------------------------
@@ -581,13 +584,13 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                     unsigned long long* d = a.yacc + (size_t)(t & 1) * yslot + (size_t)(T2_OQ * j) * RP + b;
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
-                        if (T2_OQ * j + q < out) red_add_u64(d + (size_t)q * RP, (unsigned long long)__float2ll_rn(fmaf(v2[q], F16_LO_INV, v[q]) * T2_FX));
+                        if (T2_OQ * j + q < out && !(a.dbg & 1)) red_add_u64(d + (size_t)q * RP, (unsigned long long)__float2ll_rn(fmaf(v2[q], F16_LO_INV, v[q]) * T2_FX));
                 }
             }
             tc_fence_before();
             if (etid == 0) T2_TRACE(26);
             named_bar_sync(7, 128);    // every finaliser has added its rows of the partial
-            if (etid == 0) red_release_gpu_add(ctrY, 1u);   // release is cumulative over the barrier: one gpu-scope fence per CTA
+            if (etid == 0) banked_arrive(ctrY, c);   // release is cumulative over the barrier: one gpu-scope fence per CTA
             if (etid == 0) T2_TRACE(9);
             if (act) {   // outputs / saved activations that only later kernels read: after both releases (a gpu-scope fence waits for
                          // every store the SM has in flight: issued before the release of counter H they cost it 1 000 cycles)
@@ -627,9 +630,9 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
         for (int t = 0; t <= T; ++t) {
             // step T is the epilogue: y_{T-1} is read once more for the fp32 output (cluster 0 only)
             if (t == T && ci != 0) break;
-            if (rt == 0) {
-                spin_until_ge(ctrY, (unsigned)G * (unsigned)(t + 1), a.relaxed != 0);
-                T2_TRACE(20);
+            if (warp == 8) {
+                banked_wait_warp(ctrY, per_bank * (unsigned)(t + 1), lane, a.relaxed != 0);
+                if (lane == 0) T2_TRACE(20);
             }
             named_bar_sync(5, 128);
             float yv[16];
@@ -680,8 +683,14 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
             }
             if (warp == 8) {   // counter H: the finalisers arrive (without waiting) once h_t is published and fenced
                 named_bar_sync(6, 160);
-                if (lane == 0) red_release_gpu_add(ctrH, 1u);   // release is cumulative over the barrier
+                if (lane == 0) banked_arrive(ctrH, c);   // release is cumulative over the barrier
                 if (lane == 0) T2_TRACE(22);
+                // gate inputs of frame t+2 -> L2: this CTA's 1/G of the gx frame and of the mask frame
+                if (t + 2 < T && lane < 2 && !(a.dbg & 2)) {
+                    const size_t frame = (size_t)B * H * (lane == 0 ? 3 : 1), slice = frame / (size_t)G;   // a multiple of 16 bytes
+                    const float* base = lane == 0 ? f.gx : f.mask;
+                    if (base) bulk_prefetch_l2(base + (size_t)(t + 2) * frame + (size_t)c * slice, (uint32_t)(slice * sizeof(float)));
+                }
             }
             if (y_act && t > 0 && ci == 0) {   // the fp32 output y_{t-1} (slot t of ys): one cluster stores it, after the release
                 float* yd = f.ys + (size_t)t * n_pairs + (size_t)rt * out + yo;
@@ -708,7 +717,7 @@ size_t gru_tc2_scratch_floats(int B, int H) {
     const size_t MB = (B + 7) / 8;
     const size_t hx = (size_t)2 * 2 * (H / T2_KC) * MB * 512 / 2;   // fp16 elements -> floats
     const size_t yacc = (size_t)2 * 64 * MB * 8 * 2;   // u64 -> floats
-    return round_up_sz(hx, 64) + 64 + round_up_sz(yacc, 64);
+    return round_up_sz(hx, 64) + 1024 + round_up_sz(yacc, 64);
 }
 
 // are all G/4 clusters co-resident at this shape?  (cached per shape)
@@ -764,10 +773,12 @@ int gru_ar_fwd_tc2(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
     const size_t hx_f = round_up_sz((size_t)2 * 2 * (f.H / T2_KC) * L.MB * 512 / 2, 64);
     a.hx = reinterpret_cast<uint16_t*>(tc_scratch);
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + hx_f);
-    a.yacc = reinterpret_cast<unsigned long long*>(tc_scratch + hx_f + 64);
+    a.yacc = reinterpret_cast<unsigned long long*>(tc_scratch + hx_f + 1024);
     a.smem_max = di.max_smem_optin;
     a.keepalive = 1;
     a.relaxed = relaxed_polling() ? 1 : 0;
+    a.dbg = 0;
+    if (const char* e = getenv("CVB_TC_DBG")) a.dbg = atoi(e);
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     a.trace = nullptr;
     const char* trace_file = getenv("CVB_TRACE_FILE_FWD");
@@ -776,7 +787,7 @@ int gru_ar_fwd_tc2(GruFwdArgs& f, float* tc_scratch, cudaStream_t s) {
         CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
         CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));
     }
-    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, (64 + (size_t)2 * 64 * L.MB * 8 * 2) * sizeof(float), s));   // both counters + the totals
+    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, (1024 + (size_t)2 * 64 * L.MB * 8 * 2) * sizeof(float), s));   // the counter banks + the totals
     CVB_CHECK(cudaFuncSetAttribute(k_gru_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(f.H / 8);

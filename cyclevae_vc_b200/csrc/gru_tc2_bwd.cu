@@ -76,10 +76,11 @@ struct GruTc2BwdArgs {
     GruBwdArgs f;
     uint16_t* gxh;    // [2 slots][2 parts][3H/64 chunks][MB][8 kblk][8 rows][8 k] bf16 (UMMA order) of dgh_t
     unsigned long long* yacc;   // [2 slots][64 outputs][MB*8 rows] running fixed-point totals of the feedback, zero-initialised
-    unsigned* ctr;    // [0] = H, [32] = Y, [64] = set-up arrivals, [65] = max |incoming gradient| (float bits); zero-initialised
+    unsigned* ctr;    // CTR_BANKS lines of counter H, CTR_BANKS lines of counter Y (common.cuh), then set-up arrivals and max |incoming gradient| (float bits); zero-initialised
     int smem_max;
     int keepalive;
     int relaxed;
+    int dbg;            // CVB_TC_DBG bits (experiments): 1 = skip the fixed-point adds (wrong results), 2 = no L2 prefetch of the next frames
     long long* trace;   // optional [T+1][64] clock64 stamps of CTA 0 (CVB_TRACE_FILE), else null
 };
 
@@ -154,9 +155,10 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
     float* s_max = reinterpret_cast<float*>(full + 23);            // [12] per-warp maxima of the set-up scan
     const size_t gx_part = (size_t)(K3 / U2_KC) * L.MB * 512;   // elements per part
     unsigned* ctrH = a.ctr;
-    unsigned* ctrY = a.ctr + 32;
-    unsigned* ctrS = a.ctr + 64;
-    unsigned* gmax = a.ctr + 65;
+    unsigned* ctrY = a.ctr + 32 * CTR_BANKS;
+    unsigned* ctrS = a.ctr + 64 * CTR_BANKS;
+    unsigned* gmax = ctrS + 1;
+    const unsigned per_bank = (unsigned)(G / CTR_BANKS);
     const int n_pairs = B * out;
     const size_t RP = (size_t)L.MB * 8;
     const size_t yslot = (size_t)64 * RP;
@@ -275,11 +277,8 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
         uint32_t ph = 1;   // parity to wait on the empty barrier of stage s (first pass: free)
         for (int n = 1; n <= T; ++n) {
             const uint16_t* src = a.gxh + (size_t)((n - 1) & 1) * 2 * gx_part + (size_t)(j * L.nch) * L.MB * 512;
-            if (lane == 0) {
-                spin_until_ge(ctrH, (unsigned)G * (unsigned)n, a.relaxed != 0);
-                U2_TRACE(14);
-            }
-            __syncwarp();
+            banked_wait_warp(ctrH, per_bank * (unsigned)n, lane, a.relaxed != 0);
+            if (lane == 0) U2_TRACE(14);
             for (int ch = 0; ch < L.nch; ++ch) {
                 if (lane == 0) {
                     mbar_wait(&empty[s], ph);
@@ -317,7 +316,7 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
                 ok = __shfl_sync(0xffffffffu, ok, 0);
                 if (ok) break;
                 if (!block) return false;
-                if (a.keepalive) mma_bf16_ss_elect(tmem + U2_COL_DUMMY, dA0, dB2, idesc2, false);
+                if (a.keepalive) mma_bf16_ss_elect(tmem + U2_COL_DUMMY, dW0, dB2, idesc2, false);
             }
             if (lane == 0) U2_TRACE(12);
             tc_fence_after();
@@ -339,10 +338,9 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
                         uint32_t ok = (lane == 0) ? (mbar_test_wait(&full[s], ph) ? 1u : 0u) : 0u;
                         ok = __shfl_sync(0xffffffffu, ok, 0);
                         if (ok) break;
-                        if (!y_done)
-                            y_done = try_y(n, false);
-                        else if (a.keepalive)
-                            mma_bf16_ss_elect(tmem + U2_COL_DUMMY, dA0, dB2, idesc2, false);
+                        if (!y_done) y_done = try_y(n, false);
+                        if (a.keepalive && !(a.dbg & 32))
+                            mma_bf16_ss_elect(tmem + U2_COL_DUMMY, dW0, dB2, idesc2, false);
                     }
                     if (lane == 0 && ch < 8) U2_TRACE(40 + ch);
                     tc_fence_after();
@@ -369,7 +367,7 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
                     uint32_t ok = (lane == 0) ? (mbar_test_wait(a2_full, (uint32_t)n & 1) ? 1u : 0u) : 0u;
                     ok = __shfl_sync(0xffffffffu, ok, 0);
                     if (ok) break;
-                    if (a.keepalive) mma_bf16_ss_elect(tmem + U2_COL_DUMMY, dA0, dB2, idesc2, false);
+                    if (a.keepalive) mma_bf16_ss_elect(tmem + U2_COL_DUMMY, dW0, dB2, idesc2, false);
                 }
                 if (lane == 0) U2_TRACE(13);
                 tc_fence_after();
@@ -396,23 +394,28 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
         float bsum = 0.f;   // lane i: sum over (t, rows of this warp) of value i of [dar 8 | daz 8 | dan 8 | dan*r 8]
         const bool want_db = f.dbih != nullptr || f.dbhh != nullptr;
         float fx = 0.f;     // fixed-point scale of the totals, known once every CTA has finished its set-up scan
+        // Saved activations of the step: every lane loads (the rows beyond B re-read row 0 of the frame), so the gate math is
+        // branch-free.  Their frames were pulled into L2 two steps earlier by warp 8 (bulk prefetch, in the window in which no
+        // CTA pulls dgh chunks): as HBM misses, issued by all CTAs while the chunks of the step are being pulled from L2, these
+        // loads cost the chunk chain 2 400 cycles per step (measured by skipping them).
+        float4 pr[2], pz[2], pn[2], pg[2], ph[2];
+        float4 pm[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
+        auto fetch_saved = [&](int tt) {
+            const size_t so = ((size_t)tt * B + (act ? b : 0)) * H + u0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                pr[q] = ldg_nc_v4_pinned(f.sv_r + so + 4 * q);
+                pz[q] = ldg_nc_v4_pinned(f.sv_z + so + 4 * q);
+                pn[q] = ldg_nc_v4_pinned(f.sv_n + so + 4 * q);
+                pg[q] = ldg_nc_v4_pinned(f.sv_ghn + so + 4 * q);
+                ph[q] = ldg_nc_v4_pinned(f.hs + so + 4 * q);   // hs slot t = h_{t-1}
+                if (f.mask) pm[q] = ldg_nc_v4_pinned(f.mask + so + 4 * q);
+            }
+        };
         for (int n = 0; n <= T; ++n) {
             const int t = T - 1 - n;
             const size_t row = (size_t)(t < 0 ? 0 : t) * B + (act ? b : 0);
-            float4 pr[2], pz[2], pn[2], pg[2], ph[2];
-            float4 pm[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
-            if (t >= 0) {   // every lane loads (the rows beyond B re-read row 0 of the frame: `row`), so the gate math below is branch-free
-                const size_t so = row * H + u0;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    pr[q] = ldg_nc_v4_pinned(f.sv_r + so + 4 * q);
-                    pz[q] = ldg_nc_v4_pinned(f.sv_z + so + 4 * q);
-                    pn[q] = ldg_nc_v4_pinned(f.sv_n + so + 4 * q);
-                    pg[q] = ldg_nc_v4_pinned(f.sv_ghn + so + 4 * q);
-                    ph[q] = ldg_nc_v4_pinned(f.hs + so + 4 * q);   // hs slot t = h_{t-1}
-                    if (f.mask) pm[q] = ldg_nc_v4_pinned(f.mask + so + 4 * q);
-                }
-            }
+            if (t >= 0) fetch_saved(t);
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (etid == 0) U2_TRACE(0);
             if (n > 0) {
@@ -562,13 +565,13 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
                     unsigned long long* d = a.yacc + (size_t)(n & 1) * yslot + (size_t)(U2_OQ * j) * RP + b;
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
-                        if (U2_OQ * j + q < out) u2_red_add(d + (size_t)q * RP, (unsigned long long)__float2ll_rn((v[q] + v2[q]) * fx));
+                        if (U2_OQ * j + q < out && !(a.dbg & 1)) u2_red_add(d + (size_t)q * RP, (unsigned long long)__float2ll_rn((v[q] + v2[q]) * fx));
                 }
             }
             tc_fence_before();
             if (etid == 0) U2_TRACE(26);
             named_bar_sync(7, 128);    // every finaliser has added its rows of the partial
-            if (etid == 0) red_release_gpu_add(ctrY, 1u);   // release is cumulative over the barrier: one gpu-scope fence per CTA
+            if (etid == 0) banked_arrive(ctrY, c);   // release is cumulative over the barrier: one gpu-scope fence per CTA
             if (etid == 0) U2_TRACE(9);
             if (act) {   // after both releases: only the products after the kernel read these
                 float* gi = f.dgi + row * K3 + u0;
@@ -633,10 +636,10 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) dyv[e] = (need_dy && yo + e < out) ? __ldcg(dyt + (size_t)rt * out + yo + e) : 0.f;
             if (n > 0) {
-                if (rt == 0) {
-                    spin_until_ge(ctrY, (unsigned)G * (unsigned)n, a.relaxed != 0);
-                    if (n == 1) spin_until_ge(ctrS, (unsigned)G, false);
-                    U2_TRACE(20);
+                if (warp == 8) {
+                    banked_wait_warp(ctrY, per_bank * (unsigned)n, lane, a.relaxed != 0);
+                    if (n == 1 && lane == 0) spin_until_ge(ctrS, (unsigned)G, false);
+                    if (lane == 0) U2_TRACE(20);
                 }
                 named_bar_sync(5, 128);
                 if (n == 1) {
@@ -689,8 +692,15 @@ __global__ void __launch_bounds__(U2_NT, 1) k_gru_bwd_tc2(GruTc2BwdArgs a) {
                 }
                 if (warp == 8) {   // counter H: the finalisers arrive (without waiting) once dgh_t is published and fenced
                     named_bar_sync(6, 160);
-                    if (lane == 0) red_release_gpu_add(ctrH, 1u);   // release is cumulative over the barrier
+                    if (lane == 0) banked_arrive(ctrH, c);   // release is cumulative over the barrier
                     if (lane == 0) U2_TRACE(22);
+                    // the saved activations of frame t-2 -> L2: this CTA's 1/G of each frame (every CTA reads 32 bytes of every row),
+                    // issued now: counter H is not complete yet, so no CTA pulls dgh chunks
+                    if (t >= 2 && lane < 6 && !(a.dbg & 2)) {
+                        const float* base = lane == 0 ? f.sv_r : lane == 1 ? f.sv_z : lane == 2 ? f.sv_n : lane == 3 ? f.sv_ghn : lane == 4 ? f.hs : f.mask;
+                        const size_t frame = (size_t)B * H, slice = frame / (size_t)G;   // B * 8 floats: a multiple of 16 bytes
+                        if (base) bulk_prefetch_l2(base + (size_t)(t - 2) * frame + (size_t)c * slice, (uint32_t)(slice * sizeof(float)));
+                    }
                 }
             }
             if (t < 0) {
@@ -719,7 +729,7 @@ size_t gru_tc2_bwd_scratch_floats(int B, int H) {
     const size_t MB = (B + 7) / 8;
     const size_t gxh = (size_t)2 * 2 * (3 * H / U2_KC) * MB * 512 / 2;   // bf16 elements -> floats
     const size_t yacc = (size_t)2 * 64 * MB * 8 * 2;                    // u64 -> floats
-    return round_up_sz(gxh, 64) + 128 + round_up_sz(yacc, 64);
+    return round_up_sz(gxh, 64) + 1024 + round_up_sz(yacc, 64);
 }
 
 static bool u2_runnable(int B, int H, int out, const DeviceInfo& di, U2Layout* Lout) {
@@ -775,11 +785,13 @@ int gru_ar_bwd_tc2(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     const size_t yacc_f = (size_t)2 * 64 * L.MB * 8 * 2;
     a.gxh = reinterpret_cast<uint16_t*>(tc_scratch);
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + gxh_f);
-    a.yacc = reinterpret_cast<unsigned long long*>(tc_scratch + gxh_f + 128);
+    a.yacc = reinterpret_cast<unsigned long long*>(tc_scratch + gxh_f + 1024);
     a.smem_max = di.max_smem_optin;
     a.trace = nullptr;
     a.keepalive = 1;
     a.relaxed = relaxed_polling() ? 1 : 0;
+    a.dbg = 0;
+    if (const char* e = getenv("CVB_TC_DBG")) a.dbg = atoi(e);
     if (const char* e = getenv("CVB_TC_KEEPALIVE")) a.keepalive = atoi(e) != 0;
     const char* trace_file = getenv("CVB_TRACE_FILE");
     const size_t trace_bytes = (size_t)(f.T + 1) * 64 * sizeof(long long);
@@ -787,7 +799,7 @@ int gru_ar_bwd_tc2(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
         CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
         CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));
     }
-    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, (128 + yacc_f) * sizeof(float), s));   // counters, maximum and the totals
+    CVB_CHECK(cudaMemsetAsync(a.ctr, 0, (1024 + yacc_f) * sizeof(float), s));   // counter banks, maximum and the totals
     CVB_CHECK(cudaFuncSetAttribute(k_gru_bwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(f.H / 8);

@@ -746,8 +746,18 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
     {
+        // One-hop variant (gru_tc2_bwd.cu): faster up to ~32 rows (B = 8: 16.0k -> 14.8k cycles per step), slower beyond ~48: its
+        // dgh pulls (245 KB per CTA and step at B = 80, the same lines read by all 32 clusters) run while other CTAs are still
+        // in their tails and take twice as long as in the quiet window this kernel's single barrier gives them (21.9k vs
+        // 20.3k cycles at B = 80).  CVB_TC_FEEDBACK=cluster / grid forces one or the other.
         const char* e8 = getenv("CVB_TC_CLUSTER8");
-        if (gru_tc_one_hop() && !(e8 && e8[0] == '1') && gru_tc2_bwd_supported(f.B, f.H, f.out, di)) return gru_ar_bwd_tc2(f, tc_scratch, s);
+        const char* fb = getenv("CVB_TC_FEEDBACK");
+        const bool want2 = fb ? fb[0] == 'c' : f.B <= 32;
+        if (want2 && !(e8 && e8[0] == '1') && gru_tc2_bwd_supported(f.B, f.H, f.out, di)) {
+            g_tc_hops[1] = 1;
+            return gru_ar_bwd_tc2(f, tc_scratch, s);
+        }
+        g_tc_hops[1] = 2;
     }
     TbLayout L;
     const int S = pick_cluster(f.B, f.H, f.out, di, &L);

@@ -66,6 +66,10 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* g
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
         : "memory");
 }
+// contiguous range of global memory -> L2 (no destination: a hint, nothing to wait for); bytes a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / bulk copy)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CVB_ABI_VERSION 12
+#define CVB_ABI_VERSION 13
 
 /* Shape + parameter pointers of one GRU_RNN instance (gru_vae.py:282-320).  Parameter pointers
  * are the data_ptr()s of the module's own nn.Parameters (same names as the reference's
@@ -101,9 +101,12 @@ int cvb_recurrence_max_rows(const cvb_net* net, int mode);
  * process launched; -1 before the first call.  For tests and monitoring: a shape that silently leaves the tensor-core
  * path shows up here. */
 #define CVB_PATH_FP32 0      /* fp32-FMA persistent kernels (gru_ar.cu) */
-#define CVB_PATH_TC 1        /* tcgen05 kernels, two exchanges per step (gru_tc.cu / gru_tc_bwd.cu) */
+#define CVB_PATH_TC 1        /* tcgen05 training kernels (gru_tc.cu / gru_tc_bwd.cu: two grid-wide exchanges per step; gru_tc2.cu / gru_tc2_bwd.cu: one) */
 #define CVB_PATH_TC_FOLDED 2 /* tcgen05 inference kernel, feedback folded, one exchange per step (gru_tc_eval.cu) */
 int cvb_last_recurrence_path(int backward);
+/* Grid-wide exchanges per recurrent step of the tensor-core kernel that call launched: 1 (gru_tc2.cu, gru_tc2_bwd.cu,
+ * gru_tc_eval.cu), 2 (gru_tc.cu, gru_tc_bwd.cu); 0 for the fp32-FMA kernels or before the first call. */
+int cvb_last_recurrence_hops(int backward);
 
 /* ---- GRU_RNN.forward (gru_vae.py:322-455; kwargs do / clamp_vae / lat_dim / h_in) ------------
  * x_bm [B,T,in]; y_in [B,out] (the reference's [B,1,out]); h_in [B,H] or NULL (= zeros);

@@ -446,12 +446,15 @@ def test_full_size_properties(cvb):
     assert torch.isfinite(od).all()
 
 
+@pytest.mark.parametrize("feedback", ["default", "grid", "cluster"])
 @pytest.mark.parametrize("net,B", [("enc", 80), ("dec", 80), ("dec", 5), ("enc", 128)])
-def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B):
+def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B, feedback):
     """The tcgen05 recurrence kernels (forward: fp16 hi/lo split; BPTT: bf16 hi/lo split over thread-block
     clusters) against the fp32-FMA persistent kernels (CVB_RECURRENCE=exact, themselves checked against the
     oracle above) at the BASELINE.json chunk size hu1024 x T=80, dropout masks, carried h_in / y_in,
-    gradients w.r.t. inputs, carried state and every parameter."""
+    gradients w.r.t. inputs, carried state and every parameter.  Both generations of the training kernels are checked
+    at every shape: two grid-wide exchanges per step (CVB_TC_FEEDBACK=grid: gru_tc.cu / gru_tc_bwd.cu) and one
+    (cluster: gru_tc2.cu / gru_tc2_bwd.cu, fixed-point totals of the y feedback); the default picks per shape."""
     lat, stdim, T = 32, 4, 80
     mean, std = orc.synth_stats(50)
     if net == "enc":
@@ -480,6 +483,8 @@ def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B):
         else:
             os.environ.pop("CVB_RECURRENCE", None)
             os.environ.pop("CVB_GEMM", None)
+            if feedback != "default":
+                os.environ["CVB_TC_FEEDBACK"] = feedback
         try:
             xs, ys, hs = (t.clone().requires_grad_(True) for t in (x, y0, h0))
             for p in m.parameters():
@@ -493,10 +498,16 @@ def test_tensor_core_recurrence_vs_exact_kernels(cvb, net, B):
             from cyclevae_vc_b200._lib import lib
             want = 0 if mode else 1
             assert lib.cvb_last_recurrence_path(0) == want and lib.cvb_last_recurrence_path(1) == want
+            hops = (lib.cvb_last_recurrence_hops(0), lib.cvb_last_recurrence_hops(1))
+            if mode:
+                assert hops == (0, 0)
+            else:   # default: the one-exchange forward kernel at every shape, the one-exchange BPTT kernel up to 32 rows
+                assert hops == {"grid": (2, 2), "cluster": (1, 1), "default": (1, 1 if B <= 32 else 2)}[feedback], hops
             return (o.detach(), yl.detach(), hl.detach()), (xs.grad, ys.grad, hs.grad), grads
         finally:
             os.environ.pop("CVB_RECURRENCE", None)
             os.environ.pop("CVB_GEMM", None)
+            os.environ.pop("CVB_TC_FEEDBACK", None)
 
     out_e, gin_e, gp_e = run("exact")
     out_t, gin_t, gp_t = run(None)
@@ -737,21 +748,75 @@ def test_persistent_kernels_are_deterministic(cvb):
     mg = (torch.rand(B, T, 1024, device="cuda") >= 0.5).float() * 2
     w = torch.randn(B, T, 64, device="cuda")
     enc.train()
-    first = None
-    for _ in range(3):
-        xs, hs = x.clone().requires_grad_(True), h0.clone().requires_grad_(True)
-        for p in enc.parameters():
-            p.grad = None
-        enc.inject_dropout_masks(mc, mg)
-        o, yl, hl = enc(xs, y0, h_in=hs, do=True, clamp_vae=True, lat_dim=32)
-        ((o * w).sum() + hl.sum()).backward()
-        got = [o.detach().clone(), hl.detach().clone(), xs.grad.clone(), hs.grad.clone()] + \
-              [p.grad.clone() for p in enc.parameters() if p.grad is not None]
-        if first is None:
-            first = got
+    # both generations of the training kernels; the one-exchange kernels sum the y feedback with integer (fixed-point)
+    # atomics, whose result does not depend on the arrival order
+    for feedback in ("grid", "cluster"):
+        os.environ["CVB_TC_FEEDBACK"] = feedback
+        try:
+            first = None
+            for _ in range(3):
+                xs, hs = x.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+                for p in enc.parameters():
+                    p.grad = None
+                enc.inject_dropout_masks(mc, mg)
+                o, yl, hl = enc(xs, y0, h_in=hs, do=True, clamp_vae=True, lat_dim=32)
+                ((o * w).sum() + hl.sum()).backward()
+                got = [o.detach().clone(), hl.detach().clone(), xs.grad.clone(), hs.grad.clone()] + \
+                      [p.grad.clone() for p in enc.parameters() if p.grad is not None]
+                if first is None:
+                    first = got
+                else:
+                    assert all(torch.equal(a, b) for a, b in zip(got, first)), feedback
+            assert lib.cvb_last_recurrence_path(0) == 1 and lib.cvb_last_recurrence_path(1) == 1
+            assert lib.cvb_last_recurrence_hops(0) == lib.cvb_last_recurrence_hops(1) == (2 if feedback == "grid" else 1)
+        finally:
+            os.environ.pop("CVB_TC_FEEDBACK", None)
+
+
+@pytest.mark.parametrize("gscale", [1e-9, 1.0, 1e7])
+def test_one_exchange_bptt_any_gradient_scale(cvb, gscale):
+    """The one-exchange BPTT kernel adds the cluster partials of the y feedback as 64-bit fixed-point numbers whose scale is
+    chosen per launch from max |dY|, |dh_last|: gradients of a loss scaled by 1e-9 or 1e7 must come out as accurate
+    (relative to their own size) as at scale 1 -- against the all-fp32 path run on the same scaled loss."""
+    lat, T, B = 32, 40, 8
+    mean, std = orc.synth_stats(50)
+    spec = orc.encoder_spec(54, lat, 1024)
+    P = orc.init_params(spec, 203, gain=1.5, bias_std=0.02, mean=mean, scale=std)
+    m = _module(cvb, spec, P).train()
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(B, T, spec.in_dim, generator=g).cuda()
+    y0 = (0.3 * torch.randn(B, 1, spec.out_dim, generator=g)).cuda()
+    mc = ((torch.rand(B, T, spec.conv_dim, generator=g) >= 0.5).float() * 2).cuda()
+    mg = ((torch.rand(B, T, 1024, generator=g) >= 0.5).float() * 2).cuda()
+    w_o = (gscale * torch.randn(B, T, spec.out_dim, generator=g)).cuda()
+    from cyclevae_vc_b200._lib import lib
+
+    def run(exact):
+        if exact:
+            os.environ["CVB_RECURRENCE"] = "exact"
+            os.environ["CVB_GEMM"] = "cublas"
         else:
-            assert all(torch.equal(a, b) for a, b in zip(got, first))
-    assert lib.cvb_last_recurrence_path(0) == 1 and lib.cvb_last_recurrence_path(1) == 1
+            os.environ["CVB_TC_FEEDBACK"] = "cluster"
+        try:
+            xs = x.clone().requires_grad_(True)
+            for p in m.parameters():
+                p.grad = None
+            m.inject_dropout_masks(mc, mg)
+            o, yl, hl = m(xs, y0, do=True, clamp_vae=True, lat_dim=lat)
+            (o * w_o).sum().backward()
+            torch.cuda.synchronize()
+            assert lib.cvb_last_recurrence_hops(1) == (0 if exact else 1)
+            return xs.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        finally:
+            for k in ("CVB_RECURRENCE", "CVB_GEMM", "CVB_TC_FEEDBACK"):
+                os.environ.pop(k, None)
+
+    gx_e, gp_e = run(True)
+    gx_t, gp_t = run(False)
+    assert torch.isfinite(gx_t).all() and float(gx_e.abs().max()) > 0
+    assert _maxabs(gx_t, gx_e) < 1e-4 * float(gx_e.abs().max())
+    for k in gp_e:
+        assert _maxabs(gp_t[k], gp_e[k]) < 1e-4 * max(1e-3 * gscale, float(gp_e[k].abs().max())), k
 
 
 @pytest.mark.parametrize("cluster8", ["0", "1"])

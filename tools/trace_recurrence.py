@@ -37,6 +37,17 @@ NAMES_FWD.update({40 + i: f"mma: chunk {i} full" for i in range(8)})
 NAMES_FWD.update({48 + i: f"mma: chunk {i} issued+committed" for i in range(8)})
 
 
+# event names of the one-exchange kernels (gru_tc2.cu, gru_tc2_bwd.cu): same slots, other roles
+NAMES_ONE = {0: "fin: step start", 1: "fin: D1 complete seen", 2: "fin: exchange copies issued", 3: "fin: inbox complete", 4: "fin: W_y y / q accumulator seen",
+             10: "fin: gates done", 7: "fin: h / dgh published, counter-H barrier arrived", 6: "fin: o / dgi staged, swap copies issued",
+             25: "fin: partial (D3) complete seen", 26: "fin: partial added to the fixed-point totals", 9: "fin: counter Y released",
+             14: "prod: counter H complete seen", 20: "aux: counter Y complete seen", 27: "aux: totals read", 21: "aux: own quarter staged, swap copies issued",
+             22: "aux (w8): counter H released", 12: "mma: y / dy operand complete, chain issued", 13: "mma: o / dgi operand complete"}
+NAMES_ONE.update({32 + i: f"prod: chunk {i} slot free, issuing" for i in range(8)})
+NAMES_ONE.update({40 + i: f"mma: chunk {i} full" for i in range(8)})
+NAMES_ONE.update({48 + i: f"mma: chunk {i} issued+committed" for i in range(8)})
+
+
 def run(tag):
     enc = cvb.GRU_RNN(in_dim=54, out_dim=64, hidden_units=1024, do_prob=0.5, scale_out_flag=False).cuda().train()
     enc.apply(cvb.initialize)
@@ -141,5 +152,6 @@ if __name__ == "__main__":
         report(run_eval(), NAMES_EVAL)
         sys.exit(0)
     p = run("bwd")
-    report(p.replace("trace_bwd", "trace_fwd"), NAMES_FWD)
-    report(p, NAMES_BWD)
+    from cyclevae_vc_b200._lib import lib
+    report(p.replace("trace_bwd", "trace_fwd"), NAMES_ONE if lib.cvb_last_recurrence_hops(0) == 1 else NAMES_FWD)
+    report(p, NAMES_ONE if lib.cvb_last_recurrence_hops(1) == 1 else NAMES_BWD)
