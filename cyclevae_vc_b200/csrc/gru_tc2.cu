@@ -167,8 +167,6 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
     const bool two_main = half1 < L.nch;
     const size_t RP = (size_t)L.MB * 8;                         // padded rows of the y accumulators
     const size_t yslot = (size_t)64 * RP;                       // elements of one slot
-    const uint32_t ypiece = 2u * L.kstr;                        // bytes of a CTA's contribution to the y operand (2 k blocks)
-    const uint32_t opiece = L.kstr;                             // ... to the o operand (1 k block)
 
     if (a.trace && c == 0 && threadIdx.x == 0) a.trace[60] = clock64();
     // ---- one-time setup: weights -> fp16 hi/lo in UMMA K-major core-matrix order -----------------
@@ -321,6 +319,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                 if (a.keepalive) mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dW0, dB2, idesc_dummy, false);
             }
             if (lane == 0) T2_TRACE(12);
+            fence_proxy_async_smem();   // the peers' rows arrived as st.async stores (counted on the barrier): order them before the MMAs' reads
             tc_fence_after();
 #pragma unroll
             for (int k16 = 0; k16 < T2_KC / 16; ++k16) {
@@ -383,6 +382,7 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                 if (a.keepalive) mma_bf16_ss_elect(tmem + T2_COL_DUMMY, dW0, dB2, idesc_dummy, false);
             }
             if (lane == 0) T2_TRACE(13);
+            fence_proxy_async_smem();
             tc_fence_after();
 #pragma unroll
             for (int k16 = 0; k16 < 2; ++k16) {
@@ -556,20 +556,23 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
             named_bar_arrive(6, 160);     // warp 8 releases counter H
             if (etid == 0) T2_TRACE(7);
             t2_split8(ov, oh, ol);
-            if (act) {   // o_t of the own units: k block j of the cluster's o operand
-                uint8_t* a2 = sA2 + (uint32_t)j * L.kstr + (uint32_t)(b >> 3) * 128u + (uint32_t)(b & 7) * 16u;
-                *reinterpret_cast<uint4*>(a2) = oh;
-                *reinterpret_cast<uint4*>(a2 + L.pstr) = ol;
+            if (act) {   // o_t of the own units: k block j of the cluster's o operand, here and in the three peers (st.async: every
+                         // thread sends its row as soon as it has it; the bytes are counted on the receivers' barriers)
+                const uint32_t off = (uint32_t)j * L.kstr + (uint32_t)(b >> 3) * 128u + (uint32_t)(b & 7) * 16u;
+                *reinterpret_cast<uint4*>(sA2 + off) = oh;
+                *reinterpret_cast<uint4*>(sA2 + off + L.pstr) = ol;
+                const uint32_t a2_addr = smem_u32(sA2) + off, bar_addr = smem_u32(a2_full);
+#pragma unroll
+                for (int pp = 1; pp < T2_S; ++pp) {
+                    const uint32_t p = (uint32_t)((j + pp) & (T2_S - 1));
+                    const uint32_t rb = mapa(bar_addr, p);
+                    st_async_v4(mapa(a2_addr, p), oh, rb);
+                    st_async_v4(mapa(a2_addr + L.pstr, p), ol, rb);
+                }
             }
-            fence_proxy_async_smem();
+            fence_proxy_async_smem();   // the own rows (generic stores) -> the tensor core
             named_bar_sync(3, 128);
-            if (etid < T2_S - 1) {
-                const uint32_t p = (uint32_t)((j + 1 + etid) & (T2_S - 1));
-                const uint32_t off = smem_u32(sA2) + (uint32_t)j * L.kstr;
-                bulk_s2c(mapa(off, p), sA2 + (size_t)j * L.kstr, opiece, mapa(smem_u32(a2_full), p));
-            } else if (etid == T2_S - 1) {
-                mbar_expect_tx(a2_full, (uint32_t)(T2_S - 1) * opiece);
-            }
+            if (etid == 0) mbar_expect_tx(a2_full, (uint32_t)(T2_S - 1) * (uint32_t)B * 32u);   // 32 bytes per row and peer
             if (etid == 0) T2_TRACE(6);
             // cluster partial of the own quarter -> fixed-point totals of slot t & 1 (lane == row: coalesced 8-byte adds)
             mbar_wait(part_full, (uint32_t)t & 1);
@@ -661,24 +664,30 @@ __global__ void __launch_bounds__(T2_NT, 1) k_gru_fwd_tc2(GruTc2Args a) {
                 }
                 break;
             }
-            if (y_act) {   // two core-matrix rows: this CTA's two k blocks of the y operand
-                uint4 hi, lo;
-                uint8_t* d = ybuf + (uint32_t)(2 * j) * L.kstr + (uint32_t)(rt >> 3) * 128u + (uint32_t)(rt & 7) * 16u;
-                t2_split8(yv, hi, lo);
-                *reinterpret_cast<uint4*>(d) = hi;
-                *reinterpret_cast<uint4*>(d + L.pstr) = lo;
-                t2_split8(yv + 8, hi, lo);
-                *reinterpret_cast<uint4*>(d + L.kstr) = hi;
-                *reinterpret_cast<uint4*>(d + L.kstr + L.pstr) = lo;
+            if (y_act) {   // two core-matrix rows per plane: this CTA's two k blocks of the y operand, here and in the three peers
+                uint4 hi0, lo0, hi1, lo1;
+                const uint32_t off = (uint32_t)(2 * j) * L.kstr + (uint32_t)(rt >> 3) * 128u + (uint32_t)(rt & 7) * 16u;
+                t2_split8(yv, hi0, lo0);
+                t2_split8(yv + 8, hi1, lo1);
+                *reinterpret_cast<uint4*>(ybuf + off) = hi0;
+                *reinterpret_cast<uint4*>(ybuf + off + L.pstr) = lo0;
+                *reinterpret_cast<uint4*>(ybuf + off + L.kstr) = hi1;
+                *reinterpret_cast<uint4*>(ybuf + off + L.kstr + L.pstr) = lo1;
+                const uint32_t y_addr = smem_u32(ybuf) + off, bar_addr = smem_u32(y_full);
+#pragma unroll
+                for (int pp = 1; pp < T2_S; ++pp) {
+                    const uint32_t p = (uint32_t)((j + pp) & (T2_S - 1));
+                    const uint32_t rb = mapa(bar_addr, p);
+                    st_async_v4(mapa(y_addr, p), hi0, rb);
+                    st_async_v4(mapa(y_addr + L.pstr, p), lo0, rb);
+                    st_async_v4(mapa(y_addr + L.kstr, p), hi1, rb);
+                    st_async_v4(mapa(y_addr + L.kstr + L.pstr, p), lo1, rb);
+                }
             }
-            fence_proxy_async_smem();
+            fence_proxy_async_smem();   // the own rows (generic stores) -> the tensor core
             named_bar_sync(5, 128);
-            if (rt < T2_S - 1) {
-                const uint32_t p = (uint32_t)((j + 1 + rt) & (T2_S - 1));
-                const uint32_t off = smem_u32(ybuf) + (uint32_t)(2 * j) * L.kstr;
-                bulk_s2c(mapa(off, p), ybuf + (size_t)(2 * j) * L.kstr, ypiece, mapa(smem_u32(y_full), p));
-            } else if (rt == T2_S - 1) {
-                mbar_expect_tx(y_full, (uint32_t)(T2_S - 1) * ypiece);
+            if (rt == 0) {
+                mbar_expect_tx(y_full, (uint32_t)(T2_S - 1) * (uint32_t)B * 64u);   // 64 bytes per row and peer
                 T2_TRACE(21);
             }
             if (warp == 8) {   // counter H: the finalisers arrive (without waiting) once h_t is published and fenced

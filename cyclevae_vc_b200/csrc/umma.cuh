@@ -258,6 +258,14 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster_addr, const void* 
                  "r"(smem_u32(smem_src)), "r"(bytes), "r"(cluster_bar_addr)
                  : "memory");
 }
+// 16 bytes from registers straight into the shared memory of a CTA of the cluster; the bytes are counted on an mbarrier of
+// the destination CTA (complete_tx).  dst and bar are shared::cluster addresses (mapa).  No local staging, no proxy fence and
+// no CTA barrier on the sender's side: every thread sends its own rows as soon as it has them.
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, uint4 v, uint32_t cluster_bar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst_cluster_addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar_addr)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
