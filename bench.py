@@ -123,8 +123,12 @@ def streaming_rooflines(enc, dec, opt, B, T, n_spk, dev, peak_hbm):
                 ts.append(e0.elapsed_time(e1))
             ms = statistics.median(ts)
             gbs = nbytes / (ms * 1e-3) / 1e9
-            out.append({"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
-                        "ms": ms, "algorithmic_bytes": nbytes, "bytes_rule": what})
+            e = {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                 "ms": ms, "algorithmic_bytes": nbytes, "bytes_rule": what}
+            if nbytes / (peak_hbm * 1e9) * 1e3 < 0.002:   # a full-bandwidth pass would take less than 2 us: launch latency, not bandwidth
+                e["note"] = (f"{nbytes / 1e6:.1f} MB at this batch: {nbytes / (peak_hbm * 1e9) * 1e6:.2f} us at the HBM peak -- the launch is "
+                             "latency-bound at this size, not bandwidth-bound")
+            out.append(e)
     return out
 
 
@@ -543,14 +547,35 @@ def run_native(args):
             # launches alternate encoder (out 64) / decoder (out 50) passes: 4 enc + 6 dec per step
             fl = rows * T * (4 * recurrence_flops_per_frame(2 * LAT, bwd) + 6 * recurrence_flops_per_frame(NMCEP, bwd)) / 10.0
             note = ("split-precision tcgen05 recurrence (fp16/bf16 hi+lo operands, fp32 TMEM accumulation); `achieved` counts ALGORITHMIC "
-                    "fp32-equivalent FLOPs (issued 16-bit MMA FLOPs are 3x) against the dense bf16 peak; the kernel is bound by the "
-                    "grid-wide exchanges of every recurrent step (us_per_recurrent_step), not by the tensor pipe")
+                    "fp32-equivalent FLOPs (issued 16-bit MMA FLOPs are 3x) against the dense bf16 peak; not tensor-bound: a recurrent step is "
+                    "0.54 GFLOP (0.4 us at the peak) behind a grid-wide exchange -- the forward kernel (gru_tc2.cu) is bound by its one hop + "
+                    "the chain totals -> operand swap -> gates -> partial swap -> release, the BPTT kernel at B >= 48 by the L2 -> SM broadcast "
+                    "of dgh (245 KB per CTA and step, the same lines wanted by 32 clusters) plus one hop (DESIGN.md section 4)")
         achieved = fl / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        # which generation of the training kernels ran (gru_tc2*.cu: one grid-wide exchange per step, gru_tc*.cu: two), and both
+        # directions side by side
+        hops = {"k_gru_fwd": lib.cvb_last_recurrence_hops(0), "k_gru_bwd": lib.cvb_last_recurrence_hops(1)}
+
+        def kname(k):
+            return k + ("_tc_eval" if decode else "_tc2" if hops[k] == 1 else "_tc")
+
+        both = []
+        for k, (t_ms, n_k) in rec.items():
+            if not n_k:
+                continue
+            a_ms = t_ms / n_k
+            if decode:
+                f_k = rows * T * folded_flops_per_frame()
+            else:
+                f_k = rows * T * (4 * recurrence_flops_per_frame(2 * LAT, k == "k_gru_bwd") + 6 * recurrence_flops_per_frame(NMCEP, k == "k_gru_bwd")) / 10.0
+            both.append({"kernel": kname(k), "grid_wide_exchanges_per_step": hops[k], "avg_launch_ms": a_ms, "us_per_recurrent_step": a_ms * 1e3 / T,
+                         "achieved": f_k / (a_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "frac": f_k / (a_ms * 1e-3) / 1e12 / peak_tf,
+                         "share_of_step": t_ms / prof_steps / ms})
         traffic, traffic_src = None, None
         try:
             for line in open(os.path.join(ROOT, "profiles", "r02_ncu_summary.csv")):
                 c = line.strip().split(",")
-                if c[0] == dom + ("_tc_eval" if decode else "_tc") and int(c[1]) == B:
+                if c[0] == kname(dom) and int(c[1]) == B:
                     traffic = (float(c[2]) + float(c[3])) * 1e6
                     traffic_src = "profiles/r02_ncu_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
         except Exception:
@@ -582,11 +607,12 @@ def run_native(args):
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": dom + ("_tc_eval" if decode else "_tc"), "achieved": achieved, "peak": peak_tf,
+            "roofline": {"bound": "tensor", "kernel": kname(dom), "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "avg_launch_ms": avg_ms, "launches_timed": n_l, "algorithmic_flops_per_launch": fl, "peak_source": peak_src,
                          "share_of_step": {k: v[0] / prof_steps / ms for k, v in prof.items()},
                          "us_per_recurrent_step": avg_ms * 1e3 / T, "rows_per_launch": rows, "note": note},
+            "roofline_recurrence": both,
         }
         if roof_fe:
             res["roofline_frontend"] = roof_fe
