@@ -696,7 +696,8 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
         CVB_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
     }
-    const int grid = tiles < di.n_sm ? tiles : di.n_sm;
+    int grid = tiles < di.n_sm ? tiles : di.n_sm;
+    if (const char* e = getenv("CVB_GEMM_MAX_CTAS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tools/overlap_probe.py
     prof_begin(s, CVB_PROF_GEMM);
     k_gemm_tc<<<grid, GT_THREADS, smem, s>>>(g);
     CVB_LAUNCH_CHECK();
