@@ -429,6 +429,12 @@ __global__ void __launch_bounds__(TE_NT, 1) k_gru_fwd_tc_eval(GruTcEvalArgs a) {
             if (etid == 0) red_release_gpu_add(a.ctr + c / TE_S, 1u);
             if (++wslot == 3) wslot = 0;
             if (etid == 0) TE_TRACE(9);
+            // gate inputs of frame t+2 -> L2 (this CTA's 1/G of the frame; every CTA reads 96 bytes of every row): as HBM misses
+            // issued by all CTAs at the step top they slow the h pulls of that moment (gru_tc2_bwd.cu)
+            if (etid == 32 && t + 2 < T) {
+                const size_t frame = (size_t)B * 3 * H, slice = frame / (size_t)G;   // 24 B floats: a multiple of 16 bytes
+                bulk_prefetch_l2(a.gx + (size_t)(t + 2) * frame + (size_t)c * slice, (uint32_t)(slice * sizeof(float)));
+            }
             if (act) {   // off the critical path: the state trajectory (the y product after the launch reads it)
                 float* hd = a.hs + (size_t)(t + 1) * B * H + (size_t)b * H + u0;
                 *reinterpret_cast<float4*>(hd) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
