@@ -43,6 +43,8 @@ constexpr int GT_STAGE_BYTES = 2 * GT_BLOCK_BYTES;        // A block, B block
 constexpr int GT_NS = 3;
 constexpr int GT_KD = 2;   // chunks (of 64) accumulated inside the tensor core before the slice is added in fp32 registers
 constexpr int GT_THREADS = 256;
+constexpr int GT_EPI_LD = 68;   // floats per staged output row (64 + 4 pad: the float4 writes of 8 lanes = 8 rows hit distinct banks)
+constexpr int GT_EPI_BYTES = 4 * 32 * GT_EPI_LD * 4;   // staging of the 4 epilogue warps
 constexpr int GT_MAXP = 6;                                // products per launch
 constexpr int GT_MAXO = 2 * GT_MAXP;                      // operands per split launch
 
@@ -258,7 +260,7 @@ struct GtWalk {
 
 __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant__ GemmTcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_NS * GT_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_NS * GT_STAGE_BYTES + GT_EPI_BYTES);
     uint64_t* empty = full + GT_NS;
     uint64_t* tmem_full = empty + GT_NS;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;   // [2]
@@ -359,7 +361,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             const GtProblem& P = g.p[w.prob];
             // both cross products sit in the second 128 columns; fp16 lo planes are stored scaled by 2^11 (umma.cuh)
             const float lo_inv = P.f16 ? F16_LO_INV : 1.0f;
-            const bool vec_ok = (P.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
             const int n_slices = (w.kc1 - w.kc0 + GT_KD - 1) / GT_KD;
             const int row = w.mt * GT_BM + (warp - 4) * 32 + lane;
             const int n0 = w.nt * GT_BN;
@@ -386,49 +387,93 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                     acc_ph ^= 1;
                 }
             }
-            if (P.S > 1) {   // raw partial sums of this split; alpha / bias / accumulate are applied by the reduction
-                if (row < P.M) {
-                    float* prow = P.part + ((size_t)w.sp * P.M + row) * P.N + n0;
-#pragma unroll
-                    for (int c0 = 0; c0 < GT_BN; ++c0)
-                        if (n0 + c0 < P.N) prow[c0] = sum[c0];
-                }
-                continue;
-            }
-            size_t orow = (size_t)row;
-            bool row_ok = row < P.M;
-            if (P.map_Tp) {   // padded-grid row (b, t) -> time-major row t * B + b; rows of the padding are dropped
+            // ---- store phase.  During the drain a lane owns one ROW of the tile; storing from there would make every
+            // instruction of a warp touch 32 different lines and would chain the bias / mask / old-value loads behind the
+            // stores (measured: 25 000 cycles per tile, 90 % of the epilogue warps' time on the short-K forward products).
+            // The warp transposes its 32 x 128 block through a padded shared-memory staging area in two halves of 64
+            // columns, so that 16 lanes cover 256 contiguous bytes of one output row; the loads of 8 rows are in flight
+            // together.  Split-K partial sums take the same path (raw: no alpha / bias / mask / accumulate).
+            const bool raw = P.S > 1;
+            int my_orow = row < P.M ? row : -1;
+            if (!raw && P.map_Tp && my_orow >= 0) {   // padded-grid row (b, t) -> time-major row t * B + b; padding rows are dropped
                 const int bb = row / P.map_Tp, tt = row - bb * P.map_Tp;
-                row_ok = row_ok && tt < P.map_T;
-                orow = (size_t)tt * P.map_B + bb;
+                my_orow = tt < P.map_T ? tt * P.map_B + bb : -1;
             }
-            if (row_ok) {
-                float* crow = P.C + orow * P.ldc + n0;
-                const float* mrow = P.mask ? P.mask + orow * P.ldc + n0 : nullptr;
+            float* const obase = raw ? P.part + (size_t)w.sp * P.M * P.N : P.C;
+            const int ldo = raw ? P.N : P.ldc;
+            const float alpha = raw ? 1.f : P.alpha;
+            const float* const bias = raw ? nullptr : P.bias;
+            const float* const mask = raw ? nullptr : P.mask;
+            const bool acc1 = !raw && P.beta1;
+            const bool vec_ok = (ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0) &&
+                                (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+            float* const stg = reinterpret_cast<float*>(smem + GT_NS * GT_STAGE_BYTES) + (warp - 4) * (32 * GT_EPI_LD);
+            const int rsub = lane >> 4, c4 = (lane & 15) * 4;
 #pragma unroll
-                for (int c0 = 0; c0 < GT_BN; c0 += 4) {
-                    if (n0 + c0 < P.N) {
-                        float o[4];
+            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            o[q] = P.alpha * sum[c0 + q];
-                            if (P.bias && n0 + c0 + q < P.N) o[q] += P.bias[n0 + c0 + q];
-                            if (mrow && n0 + c0 + q < P.N) o[q] *= mrow[c0 + q];
-                        }
-                        if (vec_ok && n0 + c0 + 4 <= P.N) {
-                            float4 wv = make_float4(o[0], o[1], o[2], o[3]);
-                            if (P.beta1) {
-                                const float4 old = *reinterpret_cast<const float4*>(crow + c0);
-                                wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
+                for (int j = 0; j < 16; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * GT_EPI_LD + 4 * j) =
+                        make_float4(sum[64 * half + 4 * j], sum[64 * half + 4 * j + 1], sum[64 * half + 4 * j + 2], sum[64 * half + 4 * j + 3]);
+                __syncwarp();
+                const int col = n0 + 64 * half + c4;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (bias) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (col + q < P.N) bv[q] = __ldg(bias + col + q);
+                }
+                const bool full4 = vec_ok && col + 4 <= P.N;
+#pragma unroll
+                for (int it0 = 0; it0 < 16; it0 += 4) {
+                    int orr[4];
+                    float4 v[4], mk[4], ov[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 2 * (it0 + j) + rsub;
+                        orr[j] = __shfl_sync(0xffffffffu, my_orow, r);
+                        v[j] = *reinterpret_cast<const float4*>(stg + r * GT_EPI_LD + c4);
+                        mk[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        ov[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (full4) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (orr[j] >= 0) {
+                                const size_t off = (size_t)orr[j] * ldo + col;
+                                if (mask) mk[j] = __ldg(reinterpret_cast<const float4*>(mask + off));
+                                if (acc1) ov[j] = *reinterpret_cast<const float4*>(obase + off);
                             }
-                            *reinterpret_cast<float4*>(crow + c0) = wv;
-                        } else {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (n0 + c0 + q < P.N) crow[c0 + q] = P.beta1 ? crow[c0 + q] + o[q] : o[q];
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            if (orr[j] >= 0) {
+                                float4 o;
+                                o.x = (alpha * v[j].x + bv[0]) * mk[j].x + ov[j].x;
+                                o.y = (alpha * v[j].y + bv[1]) * mk[j].y + ov[j].y;
+                                o.z = (alpha * v[j].z + bv[2]) * mk[j].z + ov[j].z;
+                                o.w = (alpha * v[j].w + bv[3]) * mk[j].w + ov[j].w;
+                                *reinterpret_cast<float4*>(obase + (size_t)orr[j] * ldo + col) = o;
+                            }
+                    } else if (col < P.N) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (orr[j] >= 0) {
+                                const size_t off = (size_t)orr[j] * ldo + col;
+                                const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                                float mm[4] = {1.f, 1.f, 1.f, 1.f}, oo[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (col + q < P.N) {
+                                        if (mask) mm[q] = __ldg(mask + off + q);
+                                        if (acc1) oo[q] = obase[off + q];
+                                    }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (col + q < P.N) obase[off + q] = (alpha * vv[q] + bv[q]) * mm[q] + oo[q];
+                            }
                     }
                 }
+                __syncwarp();
             }
         }
     }
@@ -690,7 +735,7 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
         g.p[i].At = ops[which[i][0]].img;
         g.p[i].Bt = ops[which[i][1]].img;
     }
-    const int smem = GT_NS * GT_STAGE_BYTES + 256;
+    const int smem = GT_NS * GT_STAGE_BYTES + GT_EPI_BYTES + 256;
     static bool attr_set[64] = {};   // function attributes are per device
     if (!attr_set[dev]) {
         CVB_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -123,6 +123,7 @@ class TwoSidedDilConv1d(nn.Module):
         self.layers = layers
         self.rec_field = self.kernel_size ** self.layers
         self.padding = int((self.rec_field - 1) / 2)
+        self._param_stamp = None
         self.conv = nn.ModuleList()
         for i in range(self.layers):
             cin = self.in_dim * (self.kernel_size ** i)
@@ -149,6 +150,11 @@ class TwoSidedDilConv1d(nn.Module):
         params = []
         for c in self.conv:
             params += [c.weight, c.bias]
+        # same contract as GRU_RNN._dispatch: the library caches the composed conv weights by address
+        stamp = tuple((p.data_ptr(), p._version) for p in params)
+        if stamp != self._param_stamp:
+            self._param_stamp = stamp
+            lib.cvb_weights_changed()
         with torch.cuda.device(x.device):
             return _ConvFn.apply(self, _f32c(x), *params)
 
