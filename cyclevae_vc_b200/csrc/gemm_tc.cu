@@ -221,7 +221,9 @@ struct GtProblem {
     float alpha;
     int M, N, ldc, MT, NT, KC;
     int beta1, f16;
-    int tile_end;      // running tile count up to and including this product
+    int cm, cn;        // the launch's cluster of cm x cn CTAs covers cm row tiles x cn column tiles of this product
+    int MTc, NTc;      // cluster tiles: ceil(MT / cm), ceil(NT / cn)
+    int tile_end;      // running CLUSTER-tile count up to and including this product
     int map_Tp, map_T, map_B;   // output row map (GemmDesc), 0 = identity
     const float* mask;
     // split-K (few tiles, deep K): split s sums chunks [s * kc_split, ...) into part[s][M][N]; k_splitk_reduce finishes
@@ -231,6 +233,7 @@ struct GtProblem {
 struct GemmTcArgs {
     GtProblem p[GT_MAXP];
     int n_prob;
+    int cs;            // CTAs per thread-block cluster (1, 2 or 4)
 };
 
 // walk of the tile sequence of one persistent CTA, shared by the three roles.  The CTAs take the tile list in
@@ -238,20 +241,34 @@ struct GemmTcArgs {
 // CTAs that got an extra long tile are the last to be handed a short one.
 struct GtWalk {
     int wave, tile, prob, mt, nt, sp, kc0, kc1;   // the tile's chunk range [kc0, kc1) (split sp of a split-K product)
-    __device__ __forceinline__ void start() { wave = -1; }
+    int ci, cj;        // this CTA's row / column inside the cluster tile (rank = ci * cn + cj)
+    bool valid;        // false: the cluster tile hangs over the edge of the product here (operands clamped, nothing stored)
+    int ncl, cid, rank;
+    __device__ __forceinline__ void start(const GemmTcArgs& g) {
+        wave = -1;
+        ncl = (int)gridDim.x / g.cs;
+        cid = (int)blockIdx.x / g.cs;
+        rank = (int)blockIdx.x - cid * g.cs;   // == %cluster_ctarank for a 1-D cluster
+    }
     __device__ __forceinline__ bool next(const GemmTcArgs& g) {
         ++wave;
-        tile = wave * (int)gridDim.x + ((wave & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
+        tile = wave * ncl + ((wave & 1) ? ncl - 1 - cid : cid);
         if (tile >= g.p[g.n_prob - 1].tile_end) return false;
         prob = 0;
         while (tile >= g.p[prob].tile_end) ++prob;
         const GtProblem& P = g.p[prob];
         int local = tile - (prob ? g.p[prob - 1].tile_end : 0);
-        const int per = P.MT * P.NT;
+        const int per = P.MTc * P.NTc;
         sp = local / per;
         local -= sp * per;
-        nt = local / P.MT;
-        mt = local - nt * P.MT;
+        const int ntc = local / P.MTc, mtc = local - ntc * P.MTc;
+        ci = rank / P.cn;
+        cj = rank - ci * P.cn;
+        mt = mtc * P.cm + ci;
+        nt = ntc * P.cn + cj;
+        valid = mt < P.MT && nt < P.NT;
+        if (mt >= P.MT) mt = P.MT - 1;
+        if (nt >= P.NT) nt = P.NT - 1;
         kc0 = sp * P.kc_split;
         kc1 = kc0 + P.kc_split < P.KC ? kc0 + P.kc_split : P.KC;
         return true;
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < GT_NS; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], (uint32_t)g.cs);   // every CTA of the cluster releases a stage (its operands are multicast)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -282,6 +299,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
     if (warp == 2) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (g.cs > 1) cluster_sync_all();   // nobody multicasts into a CTA whose barriers are not initialised yet
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -290,17 +308,35 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
         int s = 0;
         uint32_t ph = 1;
         GtWalk w;
-        for (w.start(); w.next(g);) {
+        for (w.start(g); w.next(g);) {
             const GtProblem& P = g.p[w.prob];
             const uint8_t* a_src = reinterpret_cast<const uint8_t*>(P.At) + (size_t)w.mt * P.KC * GT_BLOCK_BYTES;
             const uint8_t* b_src = reinterpret_cast<const uint8_t*>(P.Bt) + (size_t)w.nt * P.KC * GT_BLOCK_BYTES;
+            const uint16_t row_mask = (uint16_t)(((1u << P.cn) - 1u) << (w.ci * P.cn));
+            uint16_t col_mask = 0;
+            for (int i = 0; i < P.cm; ++i) col_mask |= (uint16_t)(1u << (i * P.cn + w.cj));
             for (int kc = w.kc0; kc < w.kc1; ++kc) {
                 if (lane == 0) {
                     mbar_wait(&empty[s], ph);
                     uint8_t* dst = smem + (size_t)s * GT_STAGE_BYTES;
                     mbar_expect_tx(&full[s], GT_STAGE_BYTES);
-                    bulk_g2s(dst, a_src + (size_t)kc * GT_BLOCK_BYTES, GT_BLOCK_BYTES, &full[s]);
-                    bulk_g2s(dst + GT_BLOCK_BYTES, b_src + (size_t)kc * GT_BLOCK_BYTES, GT_BLOCK_BYTES, &full[s]);
+                    // the A block is wanted by the cn CTAs of this cluster row, the B block by the cm CTAs of this column:
+                    // each pulls one slice and multicasts it (the per-SM request rate, not the delivered bytes, is what
+                    // bounds the ingest: tools/bench_mcast.py)
+                    const uint8_t* ab = a_src + (size_t)kc * GT_BLOCK_BYTES;
+                    const uint8_t* bb = b_src + (size_t)kc * GT_BLOCK_BYTES;
+                    if (P.cn == 1) {
+                        bulk_g2s(dst, ab, GT_BLOCK_BYTES, &full[s]);
+                    } else {
+                        const uint32_t sl = GT_BLOCK_BYTES / (uint32_t)P.cn;
+                        bulk_g2s_multicast(dst + w.cj * sl, ab + w.cj * sl, sl, &full[s], row_mask);
+                    }
+                    if (P.cm == 1) {
+                        bulk_g2s(dst + GT_BLOCK_BYTES, bb, GT_BLOCK_BYTES, &full[s]);
+                    } else {
+                        const uint32_t sl = GT_BLOCK_BYTES / (uint32_t)P.cm;
+                        bulk_g2s_multicast(dst + GT_BLOCK_BYTES + w.ci * sl, bb + w.ci * sl, sl, &full[s], col_mask);
+                    }
                 }
                 __syncwarp();
                 if (++s == GT_NS) {
@@ -315,7 +351,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
         int s = 0, acc = 0;
         uint32_t ph = 0, acc_ph = 1;
         GtWalk w;
-        for (w.start(); w.next(g);) {
+        for (w.start(g); w.next(g);) {
             const GtProblem& P = g.p[w.prob];
             const uint32_t idesc_s = P.f16 ? idesc_f16_f32(128, 256) : idesc_bf16_f32(128, 256);   // B rows [hi | lo]
             const uint32_t idesc_h = P.f16 ? idesc_f16_f32(128, 128) : idesc_bf16_f32(128, 128);   // B hi rows only
@@ -338,7 +374,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                     mma_bf16_ss_elect(d_tmem, da + 16u * k16, db + 16u * k16, idesc_s, !(slice_start && k16 == 0));
                     mma_bf16_ss_elect(d_tmem + 128u, da + (uint32_t)(GT_PLANE_BYTES >> 4) + 16u * k16, db + 16u * k16, idesc_h, true);
                 }
-                mma_commit_elect(&empty[s]);
+                if (g.cs > 1) mma_commit_multicast_elect(&empty[s], (uint16_t)((1u << g.cs) - 1u));
+                else mma_commit_elect(&empty[s]);
                 if (++s == GT_NS) {
                     s = 0;
                     ph ^= 1;
@@ -357,7 +394,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
         int acc = 0;
         uint32_t acc_ph = 0;
         GtWalk w;
-        for (w.start(); w.next(g);) {
+        for (w.start(g); w.next(g);) {
             const GtProblem& P = g.p[w.prob];
             // both cross products sit in the second 128 columns; fp16 lo planes are stored scaled by 2^11 (umma.cuh)
             const float lo_inv = P.f16 ? F16_LO_INV : 1.0f;
@@ -394,7 +431,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             // columns, so that 16 lanes cover 256 contiguous bytes of one output row; the loads of 8 rows are in flight
             // together.  Split-K partial sums take the same path (raw: no alpha / bias / mask / accumulate).
             const bool raw = P.S > 1;
-            int my_orow = row < P.M ? row : -1;
+            int my_orow = (w.valid && row < P.M) ? row : -1;
             if (!raw && P.map_Tp && my_orow >= 0) {   // padded-grid row (b, t) -> time-major row t * B + b; padding rows are dropped
                 const int bb = row / P.map_Tp, tt = row - bb * P.map_Tp;
                 my_orow = tt < P.map_T ? tt * P.map_B + bb : -1;
@@ -479,6 +516,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (g.cs > 1) cluster_sync_all();   // the peers' commits still arrive on this CTA's barriers until they are done too
     if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
@@ -552,6 +590,44 @@ int reserve_workspace(size_t bytes) {
     return arena_reserve(dev, bytes, false);
 }
 
+// clusters of `cs` CTAs of k_gemm_tc that are co-resident on this device (cached); sets the shared-memory attribute once
+static int gemm_tc_clusters(int dev, int cs, int smem, int n_sm, int* out) {
+    static int cached[64][5];
+    static bool attr_set[64] = {};   // function attributes are per device
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    if (!attr_set[dev]) {
+        CVB_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[dev] = true;
+    }
+    if (cs == 1) {
+        *out = n_sm;
+        return 0;
+    }
+    if (!cached[dev][cs]) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_sm / cs * cs);
+        cfg.blockDim = dim3(GT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_gemm_tc, &cfg) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ncl = 0;
+        }
+        if (ncl > n_sm / cs) ncl = n_sm / cs;
+        cached[dev][cs] = ncl > 0 ? ncl : -1;
+        if (getenv("CVB_DEBUG")) fprintf(stderr, "[cvb] k_gemm_tc: %d co-resident clusters of %d CTAs\n", ncl, cs);
+    }
+    *out = cached[dev][cs] > 0 ? cached[dev][cs] : 0;
+    return 0;
+}
+
 bool gemm_tc_eligible(int M, int N, int K) { return M >= 1 && N >= 1 && K >= 16 && (double)M * N * K >= 2.0e5; }
 
 static int widest_vec(const float* p, int ld) {
@@ -578,7 +654,21 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
     g.n_prob = n;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
-    const int di_sm = di.n_sm;
+    const int smem = GT_NS * GT_STAGE_BYTES + GT_EPI_BYTES + 256;
+    // thread-block clusters (CVB_GEMM_CLUSTER=2|4): the CTAs of a cluster work on neighbouring tiles and multicast the
+    // operand blocks they share.  Measured and NOT the default: the ingest of this kernel is capped by the bytes DELIVERED
+    // to the SMs (~6.3 KB/clk chip-wide), which multicast does not reduce, and the clusters run in lockstep -- bench step
+    // 22.0 ms (no clusters) / 22.4 (pairs) / 22.8 (2 x 2).  tools/bench_mcast.py: multicast only helps a loop that is
+    // bound by its own requests in flight (30 -> 42 B/clk per SM with two rounds in flight).
+    int cs = 1;
+    if (const char* e = getenv("CVB_GEMM_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cs = v; }
+    int n_cl = 0;
+    if (int rc = gemm_tc_clusters(dev, cs, smem, di.n_sm, &n_cl)) return rc;
+    if (n_cl < 1) {   // clusters of this size cannot be scheduled here
+        cs = 1;
+        n_cl = di.n_sm;
+    }
+    g.cs = cs;
     GtOperand ops[GT_MAXO];       // distinct operands of this group
     bool is_const[GT_MAXO];
     int n_ops = 0, which[GT_MAXP][2];
@@ -642,18 +732,37 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
         P.map_T = D.map_T;
         P.map_B = D.map_B;
         P.mask = D.mask;
-        // split-K: a product with few output tiles and a deep K would keep a handful of CTAs busy for its whole length
+        // cluster shape of this product: fewest padded tiles x requested bytes per CTA (each CTA pulls 1/cn of its A
+        // block and 1/cm of its B block; below ~0.52 of the full blocks the tensor pipe binds, not the ingest)
+        P.cm = P.cn = 1;
+        {
+            double best = 1e30;
+            for (int cm = 1; cm <= cs; cm *= 2) {
+                const int cn = cs / cm;
+                const double padded = (double)ceil_div(P.MT, cm) * cm * ceil_div(P.NT, cn) * cn;
+                double req = 0.5 / cm + 0.5 / cn;
+                if (req < 0.52) req = 0.52;
+                if (padded * req < best) {
+                    best = padded * req;
+                    P.cm = cm;
+                    P.cn = cn;
+                }
+            }
+        }
+        P.MTc = ceil_div(P.MT, P.cm);
+        P.NTc = ceil_div(P.NT, P.cn);
+        // split-K: a product with few output tiles and a deep K would keep a handful of clusters busy for its whole length
         P.S = 1;
         P.kc_split = P.KC;
         if (!D.map_Tp && P.MT * P.NT <= 48 && P.KC >= 16) {
-            int want = di_sm / (P.MT * P.NT);
+            int want = n_cl / (P.MTc * P.NTc);
             if (want > P.KC / 4) want = P.KC / 4;
             if (want > 1) {
                 P.kc_split = ceil_div(P.KC, want);
                 P.S = ceil_div(P.KC, P.kc_split);
             }
         }
-        tiles += P.MT * P.NT * P.S;
+        tiles += P.MTc * P.NTc * P.S;
         P.tile_end = tiles;
     }
     // place the images: cached parameter images in their own buffers, the rest bump-allocated in the arena
@@ -735,16 +844,26 @@ int gemm_tc_group(cudaStream_t s, const GemmDesc* d, int n) {
         g.p[i].At = ops[which[i][0]].img;
         g.p[i].Bt = ops[which[i][1]].img;
     }
-    const int smem = GT_NS * GT_STAGE_BYTES + GT_EPI_BYTES + 256;
-    static bool attr_set[64] = {};   // function attributes are per device
-    if (!attr_set[dev]) {
-        CVB_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set[dev] = true;
-    }
-    int grid = tiles < di.n_sm ? tiles : di.n_sm;
-    if (const char* e = getenv("CVB_GEMM_MAX_CTAS")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }   // tools/overlap_probe.py
+    int grid = (tiles < n_cl ? tiles : n_cl) * cs;
+    if (const char* e = getenv("CVB_GEMM_MAX_CTAS")) { const int v = atoi(e) / cs * cs; if (v > 0 && v < grid) grid = v; }   // tools/overlap_probe.py
     prof_begin(s, CVB_PROF_GEMM);
-    k_gemm_tc<<<grid, GT_THREADS, smem, s>>>(g);
+    if (cs == 1) {
+        k_gemm_tc<<<grid, GT_THREADS, smem, s>>>(g);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CVB_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tc, g));
+    }
     CVB_LAUNCH_CHECK();
     for (int i = 0; i < n; ++i)
         if (g.p[i].S > 1) {

@@ -179,6 +179,15 @@ __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
         : "memory");
 }
+// ... arrive(1) on the mbarrier at the same offset in every CTA of the cluster named in cta_mask
+__device__ __forceinline__ void mma_commit_multicast_elect(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
 // all previously issued MMAs of this thread complete -> arrive(1) on the mbarrier
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -123,6 +123,52 @@ __global__ void __launch_bounds__(128, 1) k_bench_allgather(int mode, int wmode,
     }
 }
 
+// GEMM-like operand ingest by thread-block clusters: every round a CTA needs a private block (a_bytes) and a block its
+// whole cluster shares (b_bytes).  mode 0: every CTA pulls both itself (unicast); mode 1: CTA r pulls slice r of the
+// shared block and multicasts it to all CTAs of the cluster.  b_all != 0: all clusters share the same block (one B tile
+// read by a whole wave), else one block per cluster.  Two rounds in flight, one cluster barrier per round.
+__global__ void __launch_bounds__(128, 1) k_bench_mcast(int mode, int a_bytes, int b_bytes, int b_all, int iters,
+                                                        const uint8_t* __restrict__ src, long long* __restrict__ out_cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar[2];
+    uint32_t cs, rank, cid;
+    asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cs));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    rank = cluster_ctarank();
+    const int stage_bytes = a_bytes + b_bytes;
+    const uint8_t* a_src = src + (size_t)blockIdx.x * a_bytes;
+    const uint8_t* b_src = src + ((size_t)32 << 20) + (b_all ? 0 : (size_t)cid * b_bytes);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    cluster_sync_all();
+    long long t0 = 0;
+    for (int it = -4; it <= iters; ++it) {
+        if (it == 0) t0 = clock64();
+        const int r = it + 4;
+        if (threadIdx.x == 0) {
+            if (it < iters) {
+                uint8_t* dst = smem + (size_t)(r & 1) * stage_bytes;
+                mbar_expect_tx(&bar[r & 1], (uint32_t)stage_bytes);
+                bulk_g2s(dst, a_src, (uint32_t)a_bytes, &bar[r & 1]);
+                if (mode == 0 || cs == 1) {
+                    bulk_g2s(dst + a_bytes, b_src, (uint32_t)b_bytes, &bar[r & 1]);
+                } else {
+                    const uint32_t sl = (uint32_t)b_bytes / cs;
+                    bulk_g2s_multicast(dst + a_bytes + rank * sl, b_src + rank * sl, sl, &bar[r & 1], (uint16_t)((1u << cs) - 1));
+                }
+            }
+            if (r > 0) mbar_wait(&bar[(r - 1) & 1], (uint32_t)((r - 1) >> 1) & 1);
+        }
+        __syncthreads();
+        cluster_sync_all();
+    }
+    if (threadIdx.x == 0) out_cycles[blockIdx.x] = clock64() - t0;
+}
+
 }  // namespace cvb
 
 extern "C" int cvb_bench_allgather(int grid, int mode, int wmode, int bytes, int inflight, int iters, void* buf, unsigned* ctr,
@@ -147,5 +193,29 @@ extern "C" int cvb_bench_ingest(int grid, int mode, int bytes, int inflight, int
     CVB_CHECK(cudaFuncSetAttribute(k_bench_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_bench_ingest<<<grid, 128, smem, (cudaStream_t)stream>>>(mode, bytes, inflight, shared_src, iters, (const uint8_t*)src, out_cycles);
     CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int cvb_bench_mcast(int grid, int cluster, int mode, int a_bytes, int b_bytes, int b_all, int iters, const void* src,
+                               long long* out_cycles, void* stream) {
+    using namespace cvb;
+    const size_t smem = 2 * (size_t)(a_bytes + b_bytes);
+    CVB_REQUIRE(a_bytes % 16 == 0 && b_bytes % (16 * cluster) == 0 && smem <= 200 * 1024 && grid % cluster == 0, "bad sizes");
+    CVB_CHECK(cudaFuncSetAttribute(k_bench_mcast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const uint8_t* s8 = (const uint8_t*)src;
+    CVB_CHECK(cudaLaunchKernelEx(&cfg, k_bench_mcast, mode, a_bytes, b_bytes, b_all, iters, s8, out_cycles));
+    count_launch();
     return 0;
 }
