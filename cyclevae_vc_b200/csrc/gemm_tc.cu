@@ -461,6 +461,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                         if (col + q < P.N) bv[q] = __ldg(bias + col + q);
                 }
                 const bool full4 = vec_ok && col + 4 <= P.N;
+                const bool pair4 = !vec_ok && (ldo & 1) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 7) == 0) &&
+                                   (!mask || (reinterpret_cast<uintptr_t>(mask) & 7) == 0) && col + 4 <= P.N;
 #pragma unroll
                 for (int it0 = 0; it0 < 16; it0 += 4) {
                     int orr[4];
@@ -490,6 +492,27 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                                 o.z = (alpha * v[j].z + bv[2]) * mk[j].z + ov[j].z;
                                 o.w = (alpha * v[j].w + bv[3]) * mk[j].w + ov[j].w;
                                 *reinterpret_cast<float4*>(obase + (size_t)orr[j] * ldo + col) = o;
+                            }
+                    } else if (pair4) {   // rows that are only 8-byte aligned (ldc = 486, 306: every conv-side output): two float2
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (orr[j] >= 0) {
+                                const size_t off = (size_t)orr[j] * ldo + col;
+                                if (mask) {
+                                    const float2 m0 = __ldg(reinterpret_cast<const float2*>(mask + off)), m1 = __ldg(reinterpret_cast<const float2*>(mask + off) + 1);
+                                    mk[j] = make_float4(m0.x, m0.y, m1.x, m1.y);
+                                }
+                                if (acc1) {
+                                    const float2 o0 = *reinterpret_cast<const float2*>(obase + off), o1 = *(reinterpret_cast<const float2*>(obase + off) + 1);
+                                    ov[j] = make_float4(o0.x, o0.y, o1.x, o1.y);
+                                }
+                            }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (orr[j] >= 0) {
+                                float2* d = reinterpret_cast<float2*>(obase + (size_t)orr[j] * ldo + col);
+                                d[0] = make_float2((alpha * v[j].x + bv[0]) * mk[j].x + ov[j].x, (alpha * v[j].y + bv[1]) * mk[j].y + ov[j].y);
+                                d[1] = make_float2((alpha * v[j].z + bv[2]) * mk[j].z + ov[j].z, (alpha * v[j].w + bv[3]) * mk[j].w + ov[j].w);
                             }
                     } else if (col < P.N) {
 #pragma unroll
