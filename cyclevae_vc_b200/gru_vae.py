@@ -556,12 +556,33 @@ def sampling_vae_batch(param, lat_dim=None, training=False, relu_vae=False, eps=
     reference; autograd already handles that here."""
     if relu_vae:
         raise NotImplementedError("sampling_vae_batch(relu_vae=True) is never used by the reference's scripts")
+    if eps is None and reference_noise_stream():
+        ld = int(param.shape[2] / 2) if lat_dim is None else int(lat_dim)
+        eps = torch.randn(param.shape[0], param.shape[1], ld).to(param.device)   # the reference's own draw (gru_vae.py:91)
     return reparam_concat(param, None, eps, lat_dim)
 
 
 def sampling_vae(param, lat_dim=None, eps=None):
     """gru_vae.py:69-82, the unbatched [T,2*lat] variant."""
+    if eps is None and reference_noise_stream():
+        ld = int(param.shape[1] / 2) if lat_dim is None else int(lat_dim)
+        eps = torch.randn(param.shape[0], ld).to(param.device)                   # gru_vae.py:75
     return reparam_concat(param, None, eps, lat_dim)
+
+
+REFERENCE_NOISE_STREAM = None   # True / False overrides the environment (CVB_REFERENCE_NOISE=1)
+
+
+def reference_noise_stream() -> bool:
+    """Opt-in: draw the latent noise exactly as the reference does -- torch.randn on the CPU generator, then a copy to the
+    device -- so that a torch.manual_seed()-ed run of the unchanged scripts consumes the same generator stream and sees
+    the same eps as with the reference module (stage-6 conversion, evaluation passes).  Off by default: the host draw
+    and the H2D copy per call are what the device-side Philox draw removes, and a host draw cannot be captured in a
+    CUDA graph.  Dropout masks are not covered: the reference draws them with torch's CUDA generator inside nn.Dropout."""
+    if REFERENCE_NOISE_STREAM is not None:
+        return bool(REFERENCE_NOISE_STREAM)
+    import os
+    return os.environ.get("CVB_REFERENCE_NOISE", "0") == "1"
 
 
 # ------------------------------------------------------------------------------------------------

@@ -216,6 +216,28 @@ def test_device_rng_statistics(cvb):
     assert torch.equal(mc, mc2)
 
 
+def test_reference_noise_stream_is_the_references_cpu_generator(cvb):
+    """Opt-in CVB_REFERENCE_NOISE / gru_vae.REFERENCE_NOISE_STREAM: sampling_vae_batch draws eps as gru_vae.py:91 does
+    (torch.randn on the CPU generator, copied to the device), so a seeded run sees the reference's own noise and leaves
+    the CPU generator in the reference's state; off by default (device-side Philox, nothing taken per element)."""
+    from cyclevae_vc_b200 import gru_vae as gv
+    g = torch.Generator().manual_seed(2)
+    latp = torch.randn(5, 17, 64, generator=g)
+    assert not gv.reference_noise_stream()
+    gv.REFERENCE_NOISE_STREAM = True
+    try:
+        torch.manual_seed(123)
+        z = cvb.sampling_vae_batch(latp.cuda(), lat_dim=32)
+        after = torch.rand(1)
+    finally:
+        gv.REFERENCE_NOISE_STREAM = None
+    torch.manual_seed(123)
+    eps = torch.randn(5, 17, 32)                      # the reference's draw
+    after_ref = torch.rand(1)
+    assert _maxabs(z, orc.sampling_vae_batch(latp, eps, 32)) < 1e-5
+    assert torch.equal(after, after_ref)              # same position of the CPU generator afterwards
+
+
 def test_adam_matches_torch(cvb):
     from cyclevae_vc_b200.cycle import FlatAdam
     torch.manual_seed(5)
