@@ -80,6 +80,18 @@ def recurrence_flops_per_frame(out_dim, backward):
     return 2 * 3 * HIDDEN * HIDDEN + 2 * 3 * HIDDEN * out_dim + 2 * out_dim * HIDDEN   # dgh W_hh ; dgi W_y ; dy W_o
 
 
+def dense_flops_per_pass(in_dim, out_dim, B, T, backward):
+    """Algorithmic FLOPs of the dense products of ONE GRU_RNN pass outside the recurrence kernels (k_gemm_tc): the composed
+    9-tap conv product on the padded grid and gx = xc W_x^T forward; dW_hh, dW_ih, dxc, dW_o, dW_y and the two front-end
+    products backward."""
+    cl, rows, rp = 9 * in_dim, B * T, B * (T + 8)
+    fwd = 2 * rp * cl * cl + 2 * rows * 3 * HIDDEN * cl
+    if not backward:
+        return fwd
+    return (2 * 3 * HIDDEN * HIDDEN * rows + 2 * 3 * HIDDEN * cl * rows + 2 * rows * cl * 3 * HIDDEN + 2 * out_dim * HIDDEN * rows
+            + 2 * 3 * HIDDEN * out_dim * rows + 2 * 2 * rp * cl * cl)
+
+
 def folded_flops_per_frame():
     return 2 * 4 * HIDDEN * HIDDEN        # [r' | z' | hn | in'] rows of the folded inference recurrence (gru_tc_eval.cu)
 
@@ -474,14 +486,14 @@ def run_native(args):
         eager.step(eager.x, eager.cv, eager.sc, eager.tc)
         barrier()
         lib.cvb_profile_reset()
-        lib.cvb_profile_enable(1)
+        lib.cvb_profile_enable(2)   # level 2 also brackets every dense-product launch (roofline_gemm)
         prof_steps = 3
         for _ in range(prof_steps):
             eager.step(eager.x, eager.cv, eager.sc, eager.tc)
         barrier()
         lib.cvb_profile_enable(0)
     prof = {}
-    for kind, name in ((0, "k_gru_fwd"), (1, "k_gru_bwd"), (3, "frontend_fwd")):
+    for kind, name in ((0, "k_gru_fwd"), (1, "k_gru_bwd"), (3, "frontend_fwd"), (2, "k_gemm_tc")):
         tot, n = C.c_float(0), C.c_int(0)
         lib.cvb_profile_summary(kind, C.byref(tot), C.byref(n))
         prof[name] = (tot.value, n.value)
@@ -610,12 +622,25 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": kname(dom), "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "avg_launch_ms": avg_ms, "launches_timed": n_l, "algorithmic_flops_per_launch": fl, "peak_source": peak_src,
-                         "share_of_step": {k: v[0] / prof_steps / ms for k, v in prof.items()},
+                         "share_of_step": {k: v[0] / prof_steps / ms for k, v in prof.items() if k != "k_gemm_tc"},
                          "us_per_recurrent_step": avg_ms * 1e3 / T, "rows_per_launch": rows, "note": note},
             "roofline_recurrence": both,
         }
         if roof_fe:
             res["roofline_frontend"] = roof_fe
+        gm_ms, gm_n = prof.get("k_gemm_tc", (0.0, 0))
+        if gm_n and not decode:
+            enc_in, dec_in = STDIM + NMCEP, LAT + args.n_spk
+            fl_g = sum(4 * dense_flops_per_pass(enc_in, 2 * LAT, B, T, bw) + 6 * dense_flops_per_pass(dec_in, NMCEP, B, T, bw) for bw in (False, True))
+            g_tf = fl_g / (gm_ms / prof_steps * 1e-3) / 1e12
+            res["roofline_gemm"] = {
+                "bound": "tensor", "kernel": "k_gemm_tc (every dense product of the step outside the recurrence kernels)", "achieved": g_tf,
+                "issued": 3 * g_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": g_tf / peak_tf, "frac_issued": 3 * g_tf / peak_tf,
+                "ms_per_step": gm_ms / prof_steps, "launches_per_step": gm_n // prof_steps, "algorithmic_flops_per_step": fl_g,
+                "share_of_step": gm_ms / prof_steps / ms,
+                "note": "split-precision products: 3 16-bit MMAs per algorithmic fp32 product (`issued`); the mainloop sits at the "
+                        "L2 -> SM delivery ceiling (64 KB per 128x128x64 stage in 1280-1560 cycles = 6.0-6.4 KB/clk chip-wide against 813 "
+                        "cycles of MMAs), DESIGN.md section 4; times are CUDA events around each group's launches in the eager profiling steps (k_gemm_tc + its split-K reductions with their launch gaps, operand pass excluded): an upper bound of the kernel time inside the replayed graph (profiles/*_step_timeline.txt: 4.1 ms)"}
         if not decode:
             res["roofline_streaming"] = streaming_rooflines(enc, dec, opt, B, T, args.n_spk, dev, peak_hbm)
         if world == 1 and not args.no_cpu_baseline:
