@@ -80,7 +80,8 @@ struct GruTcBwdArgs {
     uint16_t* gxh;    // [2 slots][2 parts][3H/64 chunks][MB][8 kblk][8 rows][8 k] bf16 (UMMA order) of dgh_t
     uint16_t* dyx;    // [2 slots][2 parts][MB][8 kblk][8 rows][8 k] bf16 (UMMA order) of dy_t, zero-initialised
     float* part;      // [G reducers][G CTAs][Q] partial sums of the y feedback (PartWalk)
-    unsigned* ctr;    // [0] = A, [32] = B (separate 128-B lines), zero-initialised
+    unsigned* ctr;    // [0] = A, [32] = B, [64] = H (separate 128-B lines), zero-initialised
+    int early_h;      // CVB_TC_BWD_EARLYH=1: dgh_t gets its own arrival counter H, released before the partial path of the step
     int S;
     int smem_max;
     int keepalive;      // CVB_TC_KEEPALIVE (default 1): dummy MMAs while the issuer polls
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
     const size_t dy_part = (size_t)L.MB * 512;
     unsigned* ctrA = a.ctr;
     unsigned* ctrB = a.ctr + 32;
+    unsigned* ctrH = a.ctr + 64;
     const int n_pairs = B * out;
 
     // ---- one-time setup --------------------------------------------------------------------------
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             const uint16_t* srcy = a.dyx + (size_t)(n & 1) * 2 * dy_part;
             if (n >= 1) {
                 if (lane == 0) {
-                    spin_until_ge(ctrA, (unsigned)G * (unsigned)n, a.relaxed != 0);
+                    spin_until_ge(a.early_h ? ctrH : ctrA, (unsigned)G * (unsigned)n, a.relaxed != 0);
                         TB_TRACE(14);
                 }
                 __syncwarp();
@@ -493,6 +495,7 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
             }
             if (etid == 0) TB_TRACE(7);
             fence_proxy_async_global();   // own generic writes of dgh_t -> visible to the peers' bulk copies (async proxy)
+            if (a.early_h) named_bar_arrive(6, 160);   // warp 3 releases counter H: the next step's dgh pulls need not wait for the partials
             if (etid == 0) TB_TRACE(8);
             if (out > 32) {   // second half of the partial accumulator (the aux warps drain [0, 32))
                 mbar_wait(part_full, (uint32_t)n & 1);
@@ -542,6 +545,14 @@ __global__ void __launch_bounds__(TB_NT, 1) k_gru_bwd_tc(GruTcBwdArgs a) {
                     float* d = f.dbhh + (size_t)(grp == 3 ? 2 : grp) * H + u;
                     *d = f.db_accumulate ? *d + tot : tot;
                 }
+            }
+        }
+    } else if (warp == 3) {
+        // ================= counter H (early_h): dgh_t is published -> release, one gpu-scope fence, off the finalisers' path
+        if (a.early_h) {
+            for (int n = 0; n < T; ++n) {
+                named_bar_sync(6, 160);
+                if (lane == 0) red_release_gpu_add(ctrH, 1u);
             }
         }
     } else if (warp >= 8) {
@@ -685,7 +696,7 @@ size_t gru_tc_bwd_scratch_floats(int B, int H) {
     size_t MB = (B + 7) / 8;
     size_t gxh = (size_t)2 * 2 * (3 * H / TB_KC) * MB * 512 / 2;   // bf16 elements -> floats
     size_t dyx = (size_t)2 * 2 * MB * 512 / 2;
-    const size_t two_hop = round_up_sz(gxh, 64) + round_up_sz(dyx, 64) + 64 + tb_part_floats(B, H);
+    const size_t two_hop = round_up_sz(gxh, 64) + round_up_sz(dyx, 64) + 128 + tb_part_floats(B, H);
     const size_t one_hop = gru_tc2_bwd_scratch_floats(B, H);
     return two_hop > one_hop ? two_hop : one_hop;
 }
@@ -769,7 +780,9 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
     a.gxh = reinterpret_cast<uint16_t*>(tc_scratch);
     a.dyx = reinterpret_cast<uint16_t*>(tc_scratch + gxh_f);
     a.ctr = reinterpret_cast<unsigned*>(tc_scratch + gxh_f + dyx_f);
-    a.part = tc_scratch + gxh_f + dyx_f + 64;
+    a.part = tc_scratch + gxh_f + dyx_f + 128;
+    a.early_h = 0;
+    if (const char* e = getenv("CVB_TC_BWD_EARLYH")) a.early_h = atoi(e) != 0;
     a.S = S;
     a.smem_max = di.max_smem_optin;
     a.trace = nullptr;
@@ -782,7 +795,7 @@ int gru_ar_bwd_tc(GruBwdArgs& f, float* tc_scratch, cudaStream_t s) {
         CVB_CHECK(cudaMalloc(&a.trace, trace_bytes));
         CVB_CHECK(cudaMemsetAsync(a.trace, 0, trace_bytes, s));
     }
-    CVB_CHECK(cudaMemsetAsync(a.dyx, 0, (dyx_f + 64) * sizeof(float), s));   // dy padding columns + both counters
+    CVB_CHECK(cudaMemsetAsync(a.dyx, 0, (dyx_f + 128) * sizeof(float), s));   // dy padding columns + the counters
     CVB_CHECK(cudaFuncSetAttribute(k_gru_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(f.H / 8);
