@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                 const bool full4 = vec_ok && col + 4 <= P.N;
                 const bool pair4 = !vec_ok && (ldo & 1) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 7) == 0) &&
                                    (!mask || (reinterpret_cast<uintptr_t>(mask) & 7) == 0) && col + 4 <= P.N;
-#pragma unroll
+#pragma unroll 1   // rolled on purpose: the unrolled store phase was bound by instruction fetch (stall_no_inst), 5-7 % per product
                 for (int it0 = 0; it0 < 16; it0 += 4) {
                     int orr[4];
                     float4 v[4], mk[4], ov[4];
