@@ -14,7 +14,7 @@
 //      (dgi^T feeds both dW_hh and dW_ih); parameter operands keep their image until the parameters change
 //      (cvb_weights_changed / cvb_adam_step), so W_x is split once per optimiser step, not once per pass.
 //   2. k_gemm_tc (persistent, warp-specialised, up to 6 products per launch): w0 bulk-copy producer (3-stage ring, 64 KB
-//      per stage: one cp.async.bulk per operand block), w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.  B's [hi | lo]
+//      per stage: one cp.async.bulk per operand block), w1 MMA issuer, w2 TMEM allocator, w4-11 epilogue (two warps per TMEM lane quadrant, 64 columns each).  B's [hi | lo]
 //      planes are adjacent in shared memory, so ONE tcgen05.mma with N = 256 forms A_hi B_hi (columns 0..127) and
 //      A_hi B_lo (columns 128..255) and a second with N = 128 adds A_lo B_hi onto the correction columns.  Two 256-column
 //      accumulators alternate; an accumulator only ever sums K = 128 (a tcgen05 accumulation chain truncates toward zero:
@@ -42,9 +42,8 @@ constexpr int GT_BLOCK_BYTES = 2 * GT_PLANE_BYTES;        // hi + lo
 constexpr int GT_STAGE_BYTES = 2 * GT_BLOCK_BYTES;        // A block, B block
 constexpr int GT_NS = 3;
 constexpr int GT_KD = 2;   // chunks (of 64) accumulated inside the tensor core before the slice is added in fp32 registers
-constexpr int GT_THREADS = 256;
-constexpr int GT_EPI_LD = 68;   // floats per staged output row (64 + 4 pad: the float4 writes of 8 lanes = 8 rows hit distinct banks)
-constexpr int GT_EPI_BYTES = 4 * 32 * GT_EPI_LD * 4;   // staging of the 4 epilogue warps
+constexpr int GT_THREADS = 384;   // w0 producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-11 epilogue
+constexpr int GT_EPI_BYTES = 8 * 32 * 32 * 4;   // staging of the 8 epilogue warps: 32 rows x 32 columns each, swizzled
 constexpr int GT_MAXP = 6;                                // products per launch
 constexpr int GT_MAXO = 2 * GT_MAXP;                      // operands per split launch
 
@@ -292,7 +291,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 128);
+            mbar_init(&tmem_empty[a], 256);
         }
         mbar_fence_init();
     }
@@ -390,7 +389,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue: TMEM lane == row of the tile =========================================
+        // ================= epilogue: 8 warps; TMEM lane == row of the tile; warp (q, hh) owns the rows [32 q, 32 q + 32) and the
+        // columns [64 hh, 64 hh + 64) (a warp reads the TMEM lanes of quadrant warp % 4).  Two warps per scheduler: a single
+        // warp ran the dependent address / predicate chains of the store phase at ~0.16 instructions per clock.
+        const int qd = warp & 3, hh = (warp - 4) >> 2;
         int acc = 0;
         uint32_t acc_ph = 0;
         GtWalk w;
@@ -399,17 +401,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             // both cross products sit in the second 128 columns; fp16 lo planes are stored scaled by 2^11 (umma.cuh)
             const float lo_inv = P.f16 ? F16_LO_INV : 1.0f;
             const int n_slices = (w.kc1 - w.kc0 + GT_KD - 1) / GT_KD;
-            const int row = w.mt * GT_BM + (warp - 4) * 32 + lane;
-            const int n0 = w.nt * GT_BN;
-            float sum[GT_BN];
+            const int row = w.mt * GT_BM + qd * 32 + lane;
+            const int n0 = w.nt * GT_BN + 64 * hh;
+            float sum[64];
 #pragma unroll
-            for (int q = 0; q < GT_BN; ++q) sum[q] = 0.f;
+            for (int q = 0; q < 64; ++q) sum[q] = 0.f;
             for (int sl = 0; sl < n_slices; ++sl) {
                 mbar_wait(&tmem_full[acc], acc_ph);
                 tc_fence_after();
-                const uint32_t taddr = tmem + (uint32_t)acc * 256u + ((uint32_t)((warp - 4) * 32) << 16);
+                const uint32_t taddr = tmem + (uint32_t)acc * 256u + ((uint32_t)(qd * 32) << 16) + 64u * (uint32_t)hh;
 #pragma unroll
-                for (int c0 = 0; c0 < GT_BN; c0 += 16) {
+                for (int c0 = 0; c0 < 64; c0 += 16) {
                     float v[16], v2[16];
                     tmem_ld_x16(taddr + c0, v);
                     tmem_ld_x16(taddr + 128 + c0, v2);
@@ -427,9 +429,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             // ---- store phase.  During the drain a lane owns one ROW of the tile; storing from there would make every
             // instruction of a warp touch 32 different lines and would chain the bias / mask / old-value loads behind the
             // stores (measured: 25 000 cycles per tile, 90 % of the epilogue warps' time on the short-K forward products).
-            // The warp transposes its 32 x 128 block through a padded shared-memory staging area in two halves of 64
-            // columns, so that 16 lanes cover 256 contiguous bytes of one output row; the loads of 8 rows are in flight
-            // together.  Split-K partial sums take the same path (raw: no alpha / bias / mask / accumulate).
+            // The warp transposes its 32 x 64 block through a swizzled 4 KB shared-memory staging area in two halves of 32
+            // columns (16-byte group g of row r sits at g ^ (r & 7): conflict-free in both directions), so that 8 lanes
+            // cover 128 contiguous bytes of one output row; the loads of 16 rows are in flight together.  Split-K partial
+            // sums take the same path (raw: no alpha / bias / mask / accumulate).
             const bool raw = P.S > 1;
             int my_orow = (w.valid && row < P.M) ? row : -1;
             if (!raw && P.map_Tp && my_orow >= 0) {   // padded-grid row (b, t) -> time-major row t * B + b; padding rows are dropped
@@ -444,16 +447,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
             const bool acc1 = !raw && P.beta1;
             const bool vec_ok = (ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0) &&
                                 (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
-            float* const stg = reinterpret_cast<float*>(smem + GT_NS * GT_STAGE_BYTES) + (warp - 4) * (32 * GT_EPI_LD);
-            const int rsub = lane >> 4, c4 = (lane & 15) * 4;
-#pragma unroll
+            const bool pair_ok = !vec_ok && (ldo & 1) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 7) == 0) &&
+                                 (!mask || (reinterpret_cast<uintptr_t>(mask) & 7) == 0);
+            float* const stg = reinterpret_cast<float*>(smem + GT_NS * GT_STAGE_BYTES) + (warp - 4) * 1024;
+            const int rsub = lane >> 3, gq = lane & 7;
+#pragma unroll 1
             for (int half = 0; half < 2; ++half) {
+                if (half == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * GT_EPI_LD + 4 * j) =
-                        make_float4(sum[64 * half + 4 * j], sum[64 * half + 4 * j + 1], sum[64 * half + 4 * j + 2], sum[64 * half + 4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                            make_float4(sum[32 + 4 * j], sum[32 + 4 * j + 1], sum[32 + 4 * j + 2], sum[32 + 4 * j + 3]);
+                }
                 __syncwarp();
-                const int col = n0 + 64 * half + c4;
+                const int col = n0 + 32 * half + 4 * gq;
                 float bv[4] = {0.f, 0.f, 0.f, 0.f};
                 if (bias) {
 #pragma unroll
@@ -461,17 +472,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_gemm_tc(const __grid_constant
                         if (col + q < P.N) bv[q] = __ldg(bias + col + q);
                 }
                 const bool full4 = vec_ok && col + 4 <= P.N;
-                const bool pair4 = !vec_ok && (ldo & 1) == 0 && ((reinterpret_cast<uintptr_t>(obase) & 7) == 0) &&
-                                   (!mask || (reinterpret_cast<uintptr_t>(mask) & 7) == 0) && col + 4 <= P.N;
-#pragma unroll 1   // rolled on purpose: the unrolled store phase was bound by instruction fetch (stall_no_inst), 5-7 % per product
-                for (int it0 = 0; it0 < 16; it0 += 4) {
+                const bool pair4 = pair_ok && col + 4 <= P.N;
+#pragma unroll 1   // rolled on purpose: the unrolled store phase was bound by instruction fetch (stall_no_inst)
+                for (int it0 = 0; it0 < 8; it0 += 4) {
                     int orr[4];
                     float4 v[4], mk[4], ov[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int r = 2 * (it0 + j) + rsub;
+                        const int r = 4 * (it0 + j) + rsub;
                         orr[j] = __shfl_sync(0xffffffffu, my_orow, r);
-                        v[j] = *reinterpret_cast<const float4*>(stg + r * GT_EPI_LD + c4);
+                        v[j] = *reinterpret_cast<const float4*>(stg + r * 32 + ((gq ^ (r & 7)) << 2));
                         mk[j] = make_float4(1.f, 1.f, 1.f, 1.f);
                         ov[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
