@@ -551,11 +551,15 @@ def test_split_precision_tensor_core_gemm(cvb, f16):
     tol = 5e-6 if f16 else 6e-5   # x sqrt(K): operand split 2^-22 / 2^-17 per product, max over the outputs (~4 sigma);
     #                             K-slices of 128 are summed in fp32 registers, so the error does not grow ~K
     shapes = [(128, 128, 64, 0, 1), (6400, 3072, 486, 0, 1), (3072, 1024, 6400, 1, 0), (6400, 306, 3072, 0, 0),
-              (200, 50, 100, 1, 1), (130, 66, 31, 1, 1), (257, 129, 65, 0, 0), (64, 1030, 777, 1, 0)]
-    for (M, N, K, ta, tb) in shapes:
+              (200, 50, 100, 1, 1), (130, 66, 31, 1, 1), (257, 129, 65, 0, 0), (64, 1030, 777, 1, 0),
+              # output rows 16-byte aligned (ldc % 4 == 0) but N % 4 != 0: the last 16-byte group of a row straddles N;
+              # 8-byte aligned rows (ldc even) with an odd N; aligned rows wider than one column tile
+              (300, 306, 200, 0, 1, 308), (300, 305, 200, 1, 0, 306), (140, 486, 130, 0, 0, 488)]
+    for shape in shapes:
+        M, N, K, ta, tb = shape[:5]
         lda = (M if ta else K) + 3
         ldb = (K if tb else N) + 5
-        ldc = N + 1
+        ldc = shape[5] if len(shape) > 5 else N + 1
         A = torch.randn((K if ta else M), lda, generator=g).cuda()
         Bm = torch.randn((N if tb else K), ldb, generator=g).cuda()
         bias = torch.randn(N, generator=g).cuda()
